@@ -1,0 +1,45 @@
+// Host-side helpers shared by every translation unit of libymp_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/ymp.h"
+
+namespace ymp {
+
+int set_error(int code, const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int num_sms();  // SM count of the current device (cached)
+
+#define YMP_CHECK_ARG(cond, ...)                                   \
+  do {                                                             \
+    if (!(cond)) return ymp::set_error(YMP_EINVAL, __VA_ARGS__);   \
+  } while (0)
+
+#define YMP_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return ymp::set_error(YMP_ECUDA, "%s failed: %s (%s:%d)", #expr,                  \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                \
+  } while (0)
+
+#define YMP_LAUNCH_CHECK()                                                              \
+  do {                                                                                  \
+    cudaError_t _e = cudaPeekAtLastError();                                             \
+    if (_e != cudaSuccess) {                                                            \
+      cudaGetLastError();                                                               \
+      return ymp::set_error(YMP_ECUDA, "kernel launch failed: %s (%s:%d)",              \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                \
+    }                                                                                   \
+    ymp::count_launch();                                                                \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace ymp

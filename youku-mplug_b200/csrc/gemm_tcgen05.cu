@@ -1,0 +1,447 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a.
+//   warp 0      : TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B, NSTAGE-deep mbarrier ring)
+//   warp 1      : MMA issuer     (tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16, fp32 accum in TMEM)
+//   warp 2      : TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps tile i+1)
+//   warps 4..11 : epilogue       (tcgen05.ld -> bias / GELU / GELU' / residual -> bf16|fp32|atomic fp32)
+// Operands may be K-major or MN-major (both handled by the UMMA smem descriptors), so the same
+// kernel serves forward (x.W^T), dgrad (dy.W) and wgrad (dy^T.x, split-K with fp32 atomics).
+#include <cuda.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ymp {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = (4 + NUM_EPI_WARPS) * 32;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct GemmKParams {
+  void* D;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* aux_out;
+  const __nv_bfloat16* aux_in;
+  int M, N, K;
+  int ldd, ldr;
+  int a_mn, b_mn;
+  int act, out_f32, accumulate, split_k;
+  int kb_per_split;
+  float alpha;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int NSTAGE = (BN == 256) ? 4 : 6;
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512 (power of two)
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 256 + 1024;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == YMP_ACT_GELU_ERF) return gelu_erf(v);
+  if (act == YMP_ACT_GELU_TANH) return gelu_tanh(v);
+  return v;
+}
+__device__ __forceinline__ float apply_dact(float x, int act) {
+  if (act == YMP_ACT_GELU_ERF) return dgelu_erf(x);
+  if (act == YMP_ACT_GELU_TANH) return dgelu_tanh(x);
+  return 1.0f;
+}
+
+// Epilogue for one thread: 32 consecutive columns of one output row.
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint32_t (&r)[32],
+                                               int row, int col0) {
+  if (row >= p.M || col0 >= p.N) return;
+  const bool full = (col0 + 32 <= p.N);
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+
+  if (full) {
+    if (p.bias) {
+      const uint4* b4 = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 b = __ldg(b4 + j);
+        v[8 * j + 0] += bf16_lo(b.x); v[8 * j + 1] += bf16_hi(b.x);
+        v[8 * j + 2] += bf16_lo(b.y); v[8 * j + 3] += bf16_hi(b.y);
+        v[8 * j + 4] += bf16_lo(b.z); v[8 * j + 5] += bf16_hi(b.z);
+        v[8 * j + 6] += bf16_lo(b.w); v[8 * j + 7] += bf16_hi(b.w);
+      }
+    }
+    const size_t off = (size_t)row * p.ldd + col0;
+    if (p.aux_out) {
+      uint4* a4 = reinterpret_cast<uint4*>(p.aux_out + off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+        o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+        o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+        o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        a4[j] = o;
+      }
+    }
+    if (p.aux_in) {
+      const uint4* a4 = reinterpret_cast<const uint4*>(p.aux_in + off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 a = __ldg(a4 + j);
+        v[8 * j + 0] *= apply_dact(bf16_lo(a.x), p.act); v[8 * j + 1] *= apply_dact(bf16_hi(a.x), p.act);
+        v[8 * j + 2] *= apply_dact(bf16_lo(a.y), p.act); v[8 * j + 3] *= apply_dact(bf16_hi(a.y), p.act);
+        v[8 * j + 4] *= apply_dact(bf16_lo(a.z), p.act); v[8 * j + 5] *= apply_dact(bf16_hi(a.z), p.act);
+        v[8 * j + 6] *= apply_dact(bf16_lo(a.w), p.act); v[8 * j + 7] *= apply_dact(bf16_hi(a.w), p.act);
+      }
+    } else if (p.act != YMP_ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+    }
+    if (p.residual) {
+      const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 a = __ldg(r4 + j);
+        v[8 * j + 0] += bf16_lo(a.x); v[8 * j + 1] += bf16_hi(a.x);
+        v[8 * j + 2] += bf16_lo(a.y); v[8 * j + 3] += bf16_hi(a.y);
+        v[8 * j + 4] += bf16_lo(a.z); v[8 * j + 5] += bf16_hi(a.z);
+        v[8 * j + 6] += bf16_lo(a.w); v[8 * j + 7] += bf16_hi(a.w);
+      }
+    }
+    if (!p.out_f32) {
+      uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+        o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+        o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+        o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        d4[j] = o;
+      }
+    } else if (!p.accumulate) {
+      float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + off);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      float* d = reinterpret_cast<float*>(p.D) + off;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4 * j),
+                     "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                     : "memory");
+      }
+    }
+  } else {
+    // ragged N tail: scalar, bounds-checked
+    for (int i = 0; i < 32; ++i) {
+      int col = col0 + i;
+      if (col >= p.N) break;
+      float x = v[i];
+      if (p.bias) x += __bfloat162float(p.bias[col]);
+      size_t off = (size_t)row * p.ldd + col;
+      if (p.aux_out) p.aux_out[off] = __float2bfloat16(x);
+      if (p.aux_in) x *= apply_dact(__bfloat162float(p.aux_in[off]), p.act);
+      else x = apply_act(x, p.act);
+      if (p.residual) x += __bfloat162float(p.residual[(size_t)row * p.ldr + col]);
+      if (!p.out_f32) reinterpret_cast<__nv_bfloat16*>(p.D)[off] = __float2bfloat16(x);
+      else if (!p.accumulate) reinterpret_cast<float*>(p.D)[off] = x;
+      else atomicAdd(reinterpret_cast<float*>(p.D) + off, x);
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
+                         const __grid_constant__ CUtensorMap tma_b, const GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int NSTAGE = Cfg::NSTAGE;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment in the shared address space
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + NSTAGE * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGE * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + NSTAGE;
+  uint64_t* tfull_bar = empty_bar + NSTAGE;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_units = num_m * num_n * p.split_k;
+  const int kb_total = (p.K + BK - 1) / BK;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp_idx == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int ks = u % p.split_k;
+        const int t = u / p.split_k;
+        const int m_blk = t % num_m;
+        const int n_blk = t / num_m;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)
+              tma_load_2d(sa + c * (64 * BK * 2), &tma_a, &full_bar[stage], m_blk * BM + c * 64,
+                          kb * BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sb + c * (64 * BK * 2), &tma_b, &full_bar[stage], n_blk * BN + c * 64,
+                          kb * BK);
+          }
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+      // K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO); LBO unused.
+      // MN-major: 64-element (128 B) MN chunks of 64 k-rows = 8192 B apart (LBO);
+      //           8-k-row groups 1024 B apart (SBO).
+      const uint32_t a_lbo = p.a_mn ? 64 * BK * 2 : 16, a_kstep = p.a_mn ? UMMA_K * 128 : UMMA_K * 2;
+      const uint32_t b_lbo = p.b_mn ? 64 * BK * 2 : 16, b_kstep = p.b_mn ? UMMA_K * 128 : UMMA_K * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int ks = u % p.split_k;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================================================================== epilogue
+    const int q = warp_idx & 3;              // TMEM lane quarter this warp may access
+    const int half = (warp_idx - 4) >> 2;    // which half of the BN columns
+    constexpr int CHUNKS = BN / 2 / 32;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int t = u / p.split_k;
+      const int m_blk = t % num_m;
+      const int n_blk = t / num_m;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int coff = half * (BN / 2) + c * 32;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + coff), r);
+        tmem_ld_wait();
+        if (c == CHUNKS - 1) {
+          // all TMEM reads of this warp are done: hand the accumulator stage back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        epilogue_chunk(p, r, row, n_blk * BN + coff);
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2D bf16 tensor map: inner (contiguous) extent `inner`, `outer` rows of stride ld elements.
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                    uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(YMP_ECUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(YMP_ECUDA, "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu",
+                     (int)r, (unsigned long long)inner, (unsigned long long)outer,
+                     (unsigned long long)ld);
+  return YMP_OK;
+}
+
+template <int BN>
+static int launch_gemm(const ymp_gemm_args* a, const GemmKParams& kp, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a->a_mn_major) rc = make_map(&ta, a->A, a->K, a->M, a->lda, BK, BM);
+  else rc = make_map(&ta, a->A, a->M, a->K, a->lda, 64, BK);
+  if (rc) return rc;
+  if (!a->b_mn_major) rc = make_map(&tb, a->B, a->K, a->N, a->ldb, BK, BN);
+  else rc = make_map(&tb, a->B, a->N, a->K, a->ldb, 64, BK);
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_m = (a->M + BM - 1) / BM, num_n = (a->N + BN - 1) / BN;
+  const int units = num_m * num_n * kp.split_k;
+  const int grid = units < num_sms() ? units : num_sms();
+  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, kp);
+  YMP_LAUNCH_CHECK();
+  return YMP_OK;
+}
+
+}  // namespace ymp
+
+extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
+  using namespace ymp;
+  YMP_CHECK_ARG(a != nullptr, "ymp_gemm: null args");
+  YMP_CHECK_ARG(a->A && a->B && a->D, "ymp_gemm: null A/B/D");
+  YMP_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "ymp_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  YMP_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "ymp_gemm: lda/ldb must be multiples of 8 (lda=%d ldb=%d)", a->lda, a->ldb);
+  YMP_CHECK_ARG(aligned16(a->A) && aligned16(a->B) && aligned16(a->D), "ymp_gemm: A/B/D must be 16-byte aligned");
+  YMP_CHECK_ARG(a->lda >= (a->a_mn_major ? a->M : a->K), "ymp_gemm: lda too small");
+  YMP_CHECK_ARG(a->ldb >= (a->b_mn_major ? a->N : a->K), "ymp_gemm: ldb too small");
+  YMP_CHECK_ARG(a->ldd >= a->N && a->ldd % 8 == 0, "ymp_gemm: ldd must be >= N and a multiple of 8 (ldd=%d)", a->ldd);
+  YMP_CHECK_ARG(a->act >= 0 && a->act <= 2, "ymp_gemm: bad act %d", a->act);
+  YMP_CHECK_ARG(!a->residual || (a->ldr >= a->N && a->ldr % 8 == 0 && aligned16(a->residual)), "ymp_gemm: bad residual ld/alignment");
+  YMP_CHECK_ARG(!a->bias || aligned16(a->bias), "ymp_gemm: bias must be 16-byte aligned");
+  YMP_CHECK_ARG(!a->aux_out || aligned16(a->aux_out), "ymp_gemm: aux_out alignment");
+  YMP_CHECK_ARG(!a->aux_in || aligned16(a->aux_in), "ymp_gemm: aux_in alignment");
+  YMP_CHECK_ARG(!(a->accumulate && a->out_dtype != YMP_DT_F32), "ymp_gemm: accumulate needs fp32 output");
+  YMP_CHECK_ARG(!(a->accumulate && (a->aux_out || a->aux_in || a->act || a->residual)),
+                "ymp_gemm: accumulate mode supports only alpha and bias-free linear epilogue");
+  YMP_CHECK_ARG(a->tile_n == 0 || a->tile_n == 128 || a->tile_n == 256, "ymp_gemm: tile_n must be 0/128/256");
+
+  const int kb_total = (a->K + BK - 1) / BK;
+  const int sms = num_sms();
+  int bn = a->tile_n;
+  if (bn == 0) {
+    // prefer the 128x256 tile unless it leaves most of the machine idle or N is narrow
+    const long t256 = (long)((a->M + BM - 1) / BM) * ((a->N + 255) / 256);
+    bn = (a->N <= 128 || (t256 < sms && a->split_k <= 1 && !a->accumulate)) ? 128 : 256;
+  }
+  int split = a->split_k;
+  if (split <= 0) {
+    split = 1;
+    if (a->accumulate) {
+      const long tiles = (long)((a->M + BM - 1) / BM) * ((a->N + bn - 1) / bn);
+      while (tiles * split < 2L * sms && split * 8 <= kb_total) split *= 2;
+    }
+  }
+  YMP_CHECK_ARG(split == 1 || (a->accumulate && a->out_dtype == YMP_DT_F32), "ymp_gemm: split_k>1 needs accumulate=1 and fp32 output");
+  if (split > kb_total) split = kb_total;
+  int per = (kb_total + split - 1) / split;
+  split = (kb_total + per - 1) / per;  // no empty splits
+
+  GemmKParams kp;
+  kp.D = a->D;
+  kp.bias = reinterpret_cast<const __nv_bfloat16*>(a->bias);
+  kp.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+  kp.aux_out = reinterpret_cast<__nv_bfloat16*>(a->aux_out);
+  kp.aux_in = reinterpret_cast<const __nv_bfloat16*>(a->aux_in);
+  kp.M = a->M; kp.N = a->N; kp.K = a->K;
+  kp.ldd = a->ldd; kp.ldr = a->ldr;
+  kp.a_mn = a->a_mn_major ? 1 : 0; kp.b_mn = a->b_mn_major ? 1 : 0;
+  kp.act = a->act; kp.out_f32 = (a->out_dtype == YMP_DT_F32); kp.accumulate = a->accumulate ? 1 : 0;
+  kp.split_k = split; kp.kb_per_split = per;
+  kp.alpha = a->alpha;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (bn == 256) return launch_gemm<256>(a, kp, st);
+  return launch_gemm<128>(a, kp, st);
+}
