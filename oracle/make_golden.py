@@ -1,0 +1,151 @@
+"""TEST INFRASTRUCTURE - generates tests/golden/*.pt from the UNMODIFIED reference.
+
+Run in the dev container (needs /root/reference):   python oracle/make_golden.py [--full]
+
+For each config it (1) builds weights with oracle.port.init_state_dict (seeded, reproducible
+anywhere), (2) loads them into the reference's DistributedGPT3_Pretrain (via oracle/ref_shims.py),
+(3) runs the reference forward+backward on seeded inputs, (4) runs oracle/port.py on the same
+inputs and ASSERTS agreement to fp32 round-off - this is what pins the oracle - and (5) stores the
+REFERENCE's outputs as the fixture.  Fixtures hold outputs + the recipe (seeds/configs), not weights.
+"""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import port, ref_shims  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def make_inputs(B, vcfg, L, vocab, seed):
+    g = torch.Generator().manual_seed(seed)
+    video = torch.randn(B, 3, vcfg["num_frames"], vcfg["img_size"], vcfg["img_size"], generator=g)
+    ids = torch.randint(0, vocab, (B, L), generator=g)
+    lens = torch.randint(max(2, L // 4), L + 1, (B,), generator=g)
+    att = (torch.arange(L)[None, :] < lens[:, None]).long()
+    return video, ids, att
+
+
+GRAD_KEYS = ["learnable_queries", "visual_fc.weight", "visual_fc.bias", "visual_encoder.cls_token",
+             "visual_encoder.pos_embed", "visual_encoder.temporal_embed",
+             "visual_encoder.patch_embed.proj.weight", "visual_encoder.norm_pre.weight",
+             "visual_encoder.blocks.0.temporal_fc.weight", "visual_encoder.blocks.0.temporal_attn.qkv.weight",
+             "visual_encoder.blocks.0.temporal_attn.q_bias", "visual_encoder.blocks.0.attn.qkv.weight",
+             "visual_encoder.blocks.0.attn.v_bias", "visual_encoder.blocks.0.attn.proj.bias",
+             "visual_encoder.blocks.0.norm1.weight", "visual_encoder.blocks.0.mlp.fc1.weight",
+             "visual_encoder.blocks.1.mlp.fc2.bias", "visual_encoder.blocks.1.temporal_ln.bias",
+             "visual_encoder.norm.bias", "attn_pool.attn.in_proj_weight", "attn_pool.attn.bias_k",
+             "attn_pool.attn.bias_v", "attn_pool.attn.out_proj.weight", "attn_pool.normk.weight",
+             "attn_pool.mlp.fc2.weight"]
+
+
+def sample_grad(g, n=4096):
+    """(stride, flattened[::stride]) - keeps fixtures small; tests apply the same stride."""
+    flat = g.flatten()
+    stride = max(1, flat.numel() // n)
+    return stride, flat[::stride].clone()
+
+
+def run(name, vcfg, gcfg, Q, B, L, wseed, iseed, randomize, sample_logits=None, grads=True):
+    t0 = time.time()
+    sd = port.init_state_dict(vcfg, gcfg, Q, seed=wseed, randomize=randomize)
+    ref_vcfg = dict(vcfg, drop_path=0, use_abs_pos_emb=True)
+    model, G = ref_shims.build_reference_pretrain(ref_vcfg, gcfg, Q)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert not missing, missing
+    video, ids, att = make_inputs(B, vcfg, L, gcfg["vocab_size"], iseed)
+    text = G.BatchEncoding(dict(input_ids=ids, attention_mask=att))
+    print(f"[{name}] built in {time.time() - t0:.1f}s; running reference ...", flush=True)
+
+    # ---- reference forward (+ hooks for intermediates) and backward
+    inter = {}
+    h1 = model.visual_encoder.register_forward_hook(lambda m, i, o: inter.__setitem__("image_embeds", o[1].detach()))
+    h2 = model.visual_fc.register_forward_hook(lambda m, i, o: inter.__setitem__("query_features", o.detach()))
+    h3 = model.text_decoder.register_forward_hook(lambda m, i, o: inter.__setitem__("gpt", o))
+    t0 = time.time()
+    loss_ref, _ = model(video, text)
+    t_fwd = time.time() - t0
+    t0 = time.time()
+    if grads:
+        loss_ref.backward()
+    t_bwd = time.time() - t0
+    for h in (h1, h2, h3):
+        h.remove()
+    out = inter["gpt"]
+    ref_grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()
+                 if p.grad is not None} if grads else {}
+    print(f"[{name}] reference loss {loss_ref.item():.6f} fwd {t_fwd:.1f}s bwd {t_bwd:.1f}s", flush=True)
+    del model
+
+    # ---- the port on the same weights/inputs: this comparison is what pins the oracle
+    psd = {k: v.clone().requires_grad_(k in port.trainable_keys(sd) and grads) for k, v in sd.items()}
+    res = port.pretrain_forward(video, ids, att, psd, vcfg, gcfg, return_all=True)
+    if grads:
+        res["loss"].backward()
+
+    def chk(a, b, what, tol=2e-4):
+        err = (a.float() - b.float()).abs().max().item()
+        scale = b.float().abs().max().item() + 1e-12
+        assert err <= tol * scale + 1e-6, f"{name}: port != reference for {what}: {err} (scale {scale})"
+        return err / scale
+
+    worst = 0.0
+    worst = max(worst, chk(res["loss"], loss_ref, "loss", 1e-5))
+    worst = max(worst, chk(res["image_embeds"], inter["image_embeds"], "image_embeds"))
+    worst = max(worst, chk(res["query_features"], inter["query_features"], "query_features"))
+    worst = max(worst, chk(res["logits"], out.logits, "logits"))
+    worst = max(worst, chk(res["losses"][:, :-1], out.losses, "losses"))
+    worst = max(worst, chk(res["hidden"], out.last_hidden_state, "hidden"))
+    ref_targets, ref_mask = port.build_targets(ids, att, Q)
+    assert torch.equal(res["targets"], ref_targets)
+    for k, gref in ref_grads.items():
+        worst = max(worst, chk(psd[k].grad, gref, "grad " + k, 5e-4))
+    assert set(ref_grads) == {k for k in psd if psd[k].grad is not None}, "trainable set differs"
+    print(f"[{name}] port == reference (worst rel err {worst:.2e}); {len(ref_grads)} grads", flush=True)
+
+    fix = dict(name=name, vcfg=vcfg, gcfg=gcfg, Q=Q, B=B, L=L, wseed=wseed, iseed=iseed,
+               randomize=randomize, torch_version=torch.__version__,
+               sd_checksum=float(sum(v.double().abs().sum() for v in sd.values())),
+               input_checksum=float(video.double().abs().sum() + ids.double().sum() + att.double().sum()),
+               loss=loss_ref.detach(), losses=out.losses.detach(), targets=ref_targets, loss_mask=ref_mask,
+               ref_fwd_s=t_fwd, ref_bwd_s=t_bwd, port_vs_ref_worst_rel=worst)
+    if sample_logits is None:
+        fix.update(logits=out.logits.detach(), hidden=out.last_hidden_state.detach(),
+                   image_embeds=inter["image_embeds"], query_features=inter["query_features"],
+                   grad_norms={k: v.norm() for k, v in ref_grads.items()},
+                   grads={k: sample_grad(ref_grads[k]) for k in GRAD_KEYS if k in ref_grads})
+    else:
+        g = torch.Generator().manual_seed(7)
+        lg = out.logits.detach()
+        idx = torch.stack([torch.randint(0, n, (sample_logits,), generator=g) for n in lg.shape], dim=1)
+        fix.update(logit_idx=idx, logit_vals=lg[idx[:, 0], idx[:, 1], idx[:, 2]],
+                   logits_abs_mean=lg.abs().mean(), logits_absmax=lg.abs().max(),
+                   image_embeds_norm=inter["image_embeds"].norm(dim=-1),
+                   query_features_norm=inter["query_features"].norm(dim=-1),
+                   hidden_norm=out.last_hidden_state.detach().norm(dim=-1),
+                   grad_norms={k: v.norm() for k, v in ref_grads.items()},
+                   grads={k: sample_grad(ref_grads[k]) for k in GRAD_KEYS if k in ref_grads})
+    os.makedirs(GOLD, exist_ok=True)
+    path = os.path.join(GOLD, name + ".pt")
+    torch.save(fix, path)
+    print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="also the real 1.3B / T=8 / B=1 config (~6 GB RAM, minutes)")
+    a = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    run("tiny_pretrain", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=2, L=8, wseed=11, iseed=12, randomize=True)
+    run("tiny_pretrain_refinit", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=1, L=6, wseed=13, iseed=14, randomize=False)
+    if a.full:
+        run("full_1p3b_T8_B1", port.VCFG_CLIP_B16, port.GCFG_1_3B, Q=128, B=1, L=128, wseed=0, iseed=1234,
+            randomize=False, sample_logits=2048)

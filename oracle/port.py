@@ -1,0 +1,328 @@
+"""TEST INFRASTRUCTURE - CPU oracle: a plain-PyTorch fp32 restatement of the reference hot path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this file.  It is the CHECKER, never the product: the product path (youku-mplug_b200/)
+has no dependency on it and fails loudly when its CUDA library is missing.
+
+Parity status: PINNED.  The reference ships no tests or golden vectors, so
+the pin is generated from the reference itself: oracle/make_golden.py runs the unmodified
+reference modules (through oracle/ref_shims.py) and this port on identical seeded inputs and
+weights, asserts they agree to fp32 round-off, and commits the reference outputs as fixtures
+under tests/golden/.  tests/test_oracle_golden.py re-checks the port against those fixtures on
+every run (CPU, no reference tree needed).
+
+Every function cites the reference lines it restates (paths relative to the reference root).
+Weights are addressed by the reference's own state_dict keys.
+"""
+import math
+import re
+
+import torch
+import torch.nn.functional as F
+
+
+def layer_norm(x, w, b, eps):
+    """LayerNormWithForceFP32.forward - models/vision_transformer.py:69-71 (fp32 statistics);
+    megatron LayerNorm - models/modeling_distributed_gpt3.py:1002-1020."""
+    return F.layer_norm(x.float(), (x.shape[-1],), w.float(), b.float(), eps).to(x.dtype)
+
+
+def vit_attention(x, sd, pre, heads):
+    """Attention.forward - models/vision_transformer.py:169-207.
+    bias = cat(q_bias, 0, v_bias); q scaled by head_dim**-0.5; softmax over fp32 scores."""
+    B, N, C = x.shape
+    bias = torch.cat([sd[pre + "q_bias"], torch.zeros_like(sd[pre + "v_bias"]), sd[pre + "v_bias"]])
+    qkv = F.linear(x, sd[pre + "qkv.weight"], bias).reshape(B, N, 3, heads, -1).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    q = q * ((C // heads) ** -0.5)
+    attn = (q.float() @ k.float().transpose(-2, -1)).softmax(dim=-1).to(x.dtype)
+    out = (attn @ v).transpose(1, 2).reshape(B, N, -1)
+    return F.linear(out, sd[pre + "proj.weight"], sd[pre + "proj.bias"])
+
+
+def mlp(x, sd, pre):
+    """Mlp.forward - models/vision_transformer.py:103-110 (exact-erf GELU)."""
+    h = F.gelu(F.linear(x, sd[pre + "fc1.weight"], sd[pre + "fc1.bias"]))
+    return F.linear(h, sd[pre + "fc2.weight"], sd[pre + "fc2.bias"])
+
+
+def timesformer_block(x, cls, sd, pre, heads, eps=1e-6):
+    """Block.forward - models/vision_transformer.py:243-275.  x [B,T,N,D], cls [B,D]."""
+    B, T, N, D = x.shape
+    # temporal attention over T for every patch, then temporal_fc, residual in (n t) order
+    xt = x.permute(0, 2, 1, 3).reshape(B * N, T, D)
+    xt = vit_attention(layer_norm(xt, sd[pre + "temporal_ln.weight"], sd[pre + "temporal_ln.bias"], eps),
+                       sd, pre + "temporal_attn.", heads)
+    xt = F.linear(xt.reshape(B, N * T, D), sd[pre + "temporal_fc.weight"], sd[pre + "temporal_fc.bias"])
+    xt = x.permute(0, 2, 1, 3).reshape(B, N * T, D) + xt
+    # spatial attention per frame with the (shared) cls token prepended
+    cls_rep = cls[:, None, :].expand(B, T, D).reshape(B * T, 1, D)
+    xs = xt.reshape(B, N, T, D).permute(0, 2, 1, 3).reshape(B * T, N, D)
+    xs = torch.cat([cls_rep, xs], dim=1)
+    xs = vit_attention(layer_norm(xs, sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], eps),
+                       sd, pre + "attn.", heads)
+    cls_new = xs[:, 0].reshape(B, T, D).mean(dim=1, keepdim=True)  # averaged over frames
+    xs = xs[:, 1:].reshape(B, T, N, D).permute(0, 2, 1, 3).reshape(B, N * T, D)
+    y = torch.cat([cls[:, None, :], xt], dim=1) + torch.cat([cls_new, xs], dim=1)
+    y = y + mlp(layer_norm(y, sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], eps), sd, pre + "mlp.")
+    cls_out, y = y[:, 0], y[:, 1:]
+    return y.reshape(B, N, T, D).permute(0, 2, 1, 3), cls_out
+
+
+def timesformer(video, sd, cfg, pre="visual_encoder."):
+    """TimeSformer.forward_features - models/vision_transformer.py:544-587 (CLIP mode: conv
+    without bias, norm_pre after the position embeddings).  video [B,3,T,H,W] ->
+    image_embeds [B, 1+T*N, D] in (t n) order."""
+    B, C, T, H, W = video.shape
+    P, D, heads, eps = cfg["patch_size"], cfg["embed_dim"], cfg["num_heads"], 1e-6
+    x = video.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W)
+    x = F.conv2d(x, sd[pre + "patch_embed.proj.weight"], sd.get(pre + "patch_embed.proj.bias"), stride=P)
+    x = x.flatten(2).transpose(1, 2)  # [(b t), n, D]
+    N = x.shape[1]
+    x = x.reshape(B, T * N, D)
+    x = torch.cat([sd[pre + "cls_token"].expand(B, -1, -1), x], dim=1)
+    pos = sd[pre + "pos_embed"]
+    total = torch.cat([pos[:, :1], pos[:, 1:].repeat(1, T, 1) +
+                       sd[pre + "temporal_embed"].repeat_interleave(N, 1)], dim=1)
+    x = x + total
+    if pre + "norm_pre.weight" in sd:
+        x = layer_norm(x, sd[pre + "norm_pre.weight"], sd[pre + "norm_pre.bias"], eps)
+    cls, x = x[:, 0], x[:, 1:].reshape(B, T, N, D)
+    for i in range(cfg["depth"]):
+        x, cls = timesformer_block(x, cls, sd, f"{pre}blocks.{i}.", heads, eps)
+    x = torch.cat([cls[:, None, :], x.reshape(B, T * N, D)], dim=1)
+    return layer_norm(x, sd[pre + "norm.weight"], sd[pre + "norm.bias"], eps)
+
+
+def attention_pool(q, k, sd, heads, pre="attn_pool.", eps=1e-6):
+    """AttentionPool.forward - models/vision_transformer.py:368-374 with nn.MultiheadAttention
+    (bias=True, add_bias_kv=True): one learned key/value row is appended; the residual is taken
+    from the already-normalised query."""
+    B, Q, D = q.shape
+    hd = D // heads
+    x = layer_norm(q, sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], eps)
+    kv = layer_norm(k, sd[pre + "normk.weight"], sd[pre + "normk.bias"], eps)
+    w, b = sd[pre + "attn.in_proj_weight"], sd[pre + "attn.in_proj_bias"]
+    qp = F.linear(x, w[:D], b[:D])
+    kp = F.linear(kv, w[D:2 * D], b[D:2 * D])
+    vp = F.linear(kv, w[2 * D:], b[2 * D:])
+    kp = torch.cat([kp, sd[pre + "attn.bias_k"].reshape(1, 1, D).expand(B, 1, D)], dim=1)
+    vp = torch.cat([vp, sd[pre + "attn.bias_v"].reshape(1, 1, D).expand(B, 1, D)], dim=1)
+    S = kp.shape[1]
+    qh = qp.reshape(B, Q, heads, hd).transpose(1, 2) * (hd ** -0.5)
+    kh = kp.reshape(B, S, heads, hd).transpose(1, 2)
+    vh = vp.reshape(B, S, heads, hd).transpose(1, 2)
+    att = (qh @ kh.transpose(-2, -1)).softmax(dim=-1)
+    o = (att @ vh).transpose(1, 2).reshape(B, Q, D)
+    x = x + F.linear(o, sd[pre + "attn.out_proj.weight"], sd[pre + "attn.out_proj.bias"])
+    return x + mlp(layer_norm(x, sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], eps), sd, pre + "mlp.")
+
+
+def gelu_tanh(x):
+    """bias_gelu_impl (megatron_util, un-vendored; tanh approximation) -
+    call site models/modeling_distributed_gpt3.py:586-588."""
+    return x * 0.5 * (1.0 + torch.tanh(0.79788456 * x * (1 + 0.044715 * x * x)))
+
+
+GPT_PRE = "text_decoder.dist_model.language_model."
+
+
+def gpt3_layer(x, sd, pre, heads, layer_number, eps):
+    """GPT3ParallelTransformerLayer.forward - models/modeling_distributed_gpt3.py:1034-1089 with
+    GPT3ParallelAttention (:868-938) and GPT3CoreAttention (:734-817).  x is [B,S,h] here (the
+    reference uses [S,B,h]; the arithmetic per (b, head) is identical).  QKV rows are grouped per
+    head as [q|k|v]; scores = q.k / (sqrt(hn)*layer) * layer; causal fill value -10000."""
+    B, S, H = x.shape
+    hn = H // heads
+    ln1 = layer_norm(x, sd[pre + "input_layernorm.weight"], sd[pre + "input_layernorm.bias"], eps)
+    qkv = F.linear(ln1, sd[pre + "self_attention.query_key_value.weight"],
+                   sd[pre + "self_attention.query_key_value.bias"]).reshape(B, S, heads, 3 * hn)
+    q, k, v = qkv.split(hn, dim=-1)
+    q, k, v = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)  # [B,np,S,hn]
+    coeff = max(1, layer_number)
+    scores = (q @ k.transpose(-2, -1)) * (1.0 / (math.sqrt(hn) * coeff))
+    scores = scores.float() * coeff
+    mask = torch.ones(S, S, dtype=torch.bool, device=x.device).triu(1)
+    scores = scores.masked_fill(mask, -10000.0)
+    probs = scores.softmax(dim=-1).to(x.dtype)
+    ctx = (probs @ v).transpose(1, 2).reshape(B, S, H)
+    attn_out = F.linear(ctx, sd[pre + "self_attention.dense.weight"]) + sd[pre + "self_attention.dense.bias"]
+    x = x + attn_out  # bias-dropout-add with p=0 (:1051-1062)
+    ln2 = layer_norm(x, sd[pre + "post_attention_layernorm.weight"], sd[pre + "post_attention_layernorm.bias"], eps)
+    h = gelu_tanh(F.linear(ln2, sd[pre + "mlp.dense_h_to_4h.weight"]) + sd[pre + "mlp.dense_h_to_4h.bias"])
+    mlp_out = F.linear(h, sd[pre + "mlp.dense_4h_to_h.weight"]) + sd[pre + "mlp.dense_4h_to_h.bias"]
+    return x + mlp_out
+
+
+def gpt3_decoder(input_embeds, sd, gcfg, pre=GPT_PRE):
+    """GPT3Embedding.forward (:640-666, position ids = arange(S) incl. the visual prefix) +
+    GPT3ParallelTransformer.forward (:1140-1186).  Returns final-LN hidden states [B,S,h]."""
+    B, S, H = input_embeds.shape
+    eps = gcfg.get("layernorm_epsilon", 1e-12)
+    x = input_embeds + sd[pre + "embedding.position_embeddings.weight"][:S][None]
+    for i in range(gcfg["num_hidden_layers"]):
+        x = gpt3_layer(x, sd, f"{pre}encoder.layers.{i}.", gcfg["num_attention_heads"], i + 1, eps)
+    return layer_norm(x, sd[pre + "encoder.final_layernorm.weight"], sd[pre + "encoder.final_layernorm.bias"], eps)
+
+
+def lm_head_losses(hidden, emb_w, labels):
+    """GPT3Model.forward tail - models/modeling_distributed_gpt3.py:1348-1364: tied LM head, CE on
+    fp32 logits, unreduced per-token losses [B,S]."""
+    logits = F.linear(hidden, emb_w)
+    B, S, V = logits.shape
+    losses = F.cross_entropy(logits.float().reshape(-1, V), labels.reshape(-1), reduction="none").view(B, S)
+    return logits, losses
+
+
+def build_targets(input_ids, attention_mask, num_query):
+    """models/distributed_gpt3.py:142-159 - integer work, bit-exact.  Visual-prefix labels are
+    100 (not -100) and are neutralised by loss_mask, not by ignore_index."""
+    B = input_ids.shape[0]
+    targets = torch.cat([input_ids[:, 1:], input_ids[:, 1:2]], dim=1)
+    targets = torch.cat([torch.full((B, num_query), 100, dtype=torch.long, device=input_ids.device), targets], dim=1)
+    loss_mask = torch.cat([torch.zeros((B, num_query), dtype=torch.long, device=input_ids.device),
+                           attention_mask[:, 1:]], dim=1)
+    return targets, loss_mask
+
+
+def masked_mean_loss(losses, loss_mask):
+    """DistributedGPT3.forward - models/modeling_distributed_gpt3.py:1612-1617."""
+    lm = loss_mask.reshape(-1).float()
+    return torch.sum(losses[:, :-1].reshape(-1).float() * lm) / lm.sum()
+
+
+def pretrain_forward(video, input_ids, attention_mask, sd, vcfg, gcfg, return_all=False):
+    """DistributedGPT3_Pretrain.forward (use_contrastive=False) - models/distributed_gpt3.py:130-166."""
+    image_embeds = timesformer(video, sd, vcfg)
+    B = video.shape[0]
+    image_query = attention_pool(sd["learnable_queries"].expand(B, -1, -1), image_embeds, sd, vcfg["num_heads"])
+    query_features = F.linear(image_query, sd["visual_fc.weight"], sd["visual_fc.bias"])
+    Q = query_features.shape[1]
+    targets, loss_mask = build_targets(input_ids, attention_mask, Q)
+    emb_w = sd[GPT_PRE + "embedding.word_embeddings.weight"]
+    input_embeds = torch.cat([query_features, emb_w[input_ids]], dim=1)
+    hidden = gpt3_decoder(input_embeds, sd, gcfg)
+    logits, losses = lm_head_losses(hidden, emb_w, targets)
+    loss = masked_mean_loss(losses, loss_mask)
+    if return_all:
+        return dict(loss=loss, logits=logits, losses=losses, hidden=hidden, image_embeds=image_embeds,
+                    image_query=image_query, query_features=query_features, targets=targets,
+                    loss_mask=loss_mask)
+    return loss
+
+
+# ------------------------------------------------------------------------------------------
+# Random-init state dicts with the reference's keys / shapes / init laws (for benches & tests)
+# ------------------------------------------------------------------------------------------
+def init_state_dict(vcfg, gcfg, num_query, seed=0, dtype=torch.float32, randomize=False):
+    """Same parameter names, shapes and init distributions as the reference constructors
+    (TimeSformer.__init__ models/vision_transformer.py:441-519, DistributedGPT3_Pretrain.__init__
+    models/distributed_gpt3.py:96-116, GPT3 init_method_normal / scaled models/
+    modeling_distributed_gpt3.py:1253-1269).  Not bit-identical to the reference's RNG stream -
+    use oracle/make_golden.py fixtures when exact reference weights are needed."""
+    g = torch.Generator().manual_seed(seed)
+    D, depth, P = vcfg["embed_dim"], vcfg["depth"], vcfg["patch_size"]
+    T, N = vcfg["num_frames"], (vcfg["img_size"] // P) ** 2
+    hid = int(D * vcfg["mlp_ratio"])
+    sd = {}
+
+    def tn(*shape, std=0.015):
+        return torch.nn.init.trunc_normal_(torch.empty(*shape), std=std, generator=g)
+
+    def nrm(*shape, std):
+        return torch.empty(*shape).normal_(0.0, std, generator=g)
+
+    ve = "visual_encoder."
+    sd[ve + "cls_token"] = tn(1, 1, D)
+    sd[ve + "pos_embed"] = tn(1, N + 1, D)
+    sd[ve + "temporal_embed"] = torch.zeros(1, T, D)
+    sd[ve + "patch_embed.proj.weight"] = tn(D, 3, P, P)
+    for nm in ("norm_pre", "norm"):
+        sd[ve + nm + ".weight"], sd[ve + nm + ".bias"] = torch.ones(D), torch.zeros(D)
+    for i in range(depth):
+        b = f"{ve}blocks.{i}."
+        for nm in ("norm1", "norm2", "temporal_ln"):
+            sd[b + nm + ".weight"], sd[b + nm + ".bias"] = torch.ones(D), torch.zeros(D)
+        for at in ("attn.", "temporal_attn."):
+            sd[b + at + "qkv.weight"] = tn(3 * D, D)
+            sd[b + at + "q_bias"], sd[b + at + "v_bias"] = torch.zeros(D), torch.zeros(D)
+            sd[b + at + "proj.weight"], sd[b + at + "proj.bias"] = tn(D, D), torch.zeros(D)
+        sd[b + "attn.proj.weight"] /= math.sqrt(2.0 * (i + 1))
+        sd[b + "temporal_fc.weight"] = tn(D, D) if i == 0 else torch.zeros(D, D)
+        sd[b + "temporal_fc.bias"] = torch.zeros(D)
+        sd[b + "mlp.fc1.weight"], sd[b + "mlp.fc1.bias"] = tn(hid, D), torch.zeros(hid)
+        sd[b + "mlp.fc2.weight"], sd[b + "mlp.fc2.bias"] = tn(D, hid) / math.sqrt(2.0 * (i + 1)), torch.zeros(D)
+    sd["learnable_queries"] = tn(1, num_query, D)
+    ap = "attn_pool."
+    for nm in ("norm1", "normk", "norm2"):
+        sd[ap + nm + ".weight"], sd[ap + nm + ".bias"] = torch.ones(D), torch.zeros(D)
+    sd[ap + "attn.in_proj_weight"] = torch.nn.init.xavier_uniform_(torch.empty(3 * D, D), generator=g)
+    sd[ap + "attn.in_proj_bias"] = torch.zeros(3 * D)
+    sd[ap + "attn.bias_k"] = torch.nn.init.xavier_normal_(torch.empty(1, 1, D), generator=g)
+    sd[ap + "attn.bias_v"] = torch.nn.init.xavier_normal_(torch.empty(1, 1, D), generator=g)
+    bound = 1.0 / math.sqrt(D)
+    sd[ap + "attn.out_proj.weight"] = torch.empty(D, D).uniform_(-bound, bound, generator=g)
+    sd[ap + "attn.out_proj.bias"] = torch.zeros(D)
+    sd[ap + "mlp.fc1.weight"] = torch.empty(hid, D).uniform_(-bound, bound, generator=g)
+    sd[ap + "mlp.fc1.bias"] = torch.empty(hid).uniform_(-bound, bound, generator=g)
+    b2 = 1.0 / math.sqrt(hid)
+    sd[ap + "mlp.fc2.weight"] = torch.empty(D, hid).uniform_(-b2, b2, generator=g)
+    sd[ap + "mlp.fc2.bias"] = torch.empty(D).uniform_(-b2, b2, generator=g)
+    H, V, Lyr = gcfg["hidden_size"], gcfg["vocab_size"], gcfg["num_hidden_layers"]
+    F4 = gcfg.get("ffn_hidden_size") or 4 * H
+    sd["visual_fc.weight"] = tn(H, D)
+    sd["visual_fc.bias"] = torch.empty(H).uniform_(-bound, bound, generator=g)
+    std = gcfg.get("init_method_std", 0.02)
+    std_out = std / math.sqrt(2.0 * Lyr)
+    sd[GPT_PRE + "embedding.word_embeddings.weight"] = nrm(V, H, std=std)
+    sd[GPT_PRE + "embedding.position_embeddings.weight"] = nrm(gcfg["max_position_embeddings"], H, std=std)
+    for i in range(Lyr):
+        b = f"{GPT_PRE}encoder.layers.{i}."
+        for nm in ("input_layernorm", "post_attention_layernorm"):
+            sd[b + nm + ".weight"], sd[b + nm + ".bias"] = torch.ones(H), torch.zeros(H)
+        sd[b + "self_attention.query_key_value.weight"] = nrm(3 * H, H, std=std)
+        sd[b + "self_attention.query_key_value.bias"] = torch.zeros(3 * H)
+        sd[b + "self_attention.dense.weight"] = nrm(H, H, std=std_out)
+        sd[b + "self_attention.dense.bias"] = torch.zeros(H)
+        sd[b + "mlp.dense_h_to_4h.weight"] = nrm(F4, H, std=std)
+        sd[b + "mlp.dense_h_to_4h.bias"] = torch.zeros(F4)
+        sd[b + "mlp.dense_4h_to_h.weight"] = nrm(H, F4, std=std_out)
+        sd[b + "mlp.dense_4h_to_h.bias"] = torch.zeros(H)
+    sd[GPT_PRE + "encoder.final_layernorm.weight"] = torch.ones(H)
+    sd[GPT_PRE + "encoder.final_layernorm.bias"] = torch.zeros(H)
+    if randomize:
+        # parity fixtures: make every zero/one-initialised tensor non-trivial so that all code
+        # paths (biases, LN affine, temporal_fc of blocks > 0, temporal_embed) are exercised
+        for k in sorted(sd):
+            v = sd[k]
+            if k.endswith("norm.weight") or k.endswith("layernorm.weight") or \
+                    re.search(r"(norm1|norm2|normk|norm_pre|temporal_ln)\.weight$", k):
+                sd[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+            elif float(v.abs().max()) == 0.0:
+                sd[k] = 0.02 * torch.randn(v.shape, generator=g)
+    return {k: v.to(dtype) for k, v in sd.items()}
+
+
+def trainable_keys(sd, freeze_vit=False):
+    """Parameters with requires_grad in the reference (models/distributed_gpt3.py:86-93):
+    everything except the GPT-3 decoder; with freeze_vit only names containing time/temporal."""
+    out = []
+    for k in sd:
+        if k.startswith("text_decoder."):
+            continue
+        if freeze_vit and k.startswith("visual_encoder.") and not any(s in k for s in ("time", "temporal")):
+            continue
+        out.append(k)
+    return out
+
+
+VCFG_CLIP_B16 = dict(img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=8, mlp_ratio=4,
+                     num_frames=8, clip_model=True)
+GCFG_1_3B = dict(vocab_size=51200, hidden_size=2048, ffn_hidden_size=8192, num_hidden_layers=24,
+                 num_attention_heads=32, max_position_embeddings=2048, layernorm_epsilon=1e-5,
+                 init_method_std=0.02)
+VCFG_TINY = dict(img_size=32, patch_size=16, embed_dim=192, depth=2, num_heads=2, mlp_ratio=4,
+                 num_frames=2, clip_model=True)
+GCFG_TINY = dict(vocab_size=512, hidden_size=128, ffn_hidden_size=512, num_hidden_layers=2,
+                 num_attention_heads=2, max_position_embeddings=64, layernorm_epsilon=1e-5,
+                 init_method_std=0.02)
