@@ -85,9 +85,180 @@ typedef struct ymp_gemm_args {
   int32_t split_k;      /* >=1; >1 requires accumulate=1 and out_dtype=F32; 0 = library picks */
   float alpha;
   int32_t tile_n;       /* 0 = auto, else 128 or 256 */
+  int32_t res_row_mod;  /* >0: residual row = m % res_row_mod (broadcast tables: position embeddings) */
+  int32_t d_row_block;  /* >0: D row = (m / d_row_block) * d_row_stride + m % d_row_block           */
+  int32_t d_row_stride; /*     (writes [B*Q] rows into a [B, S>=Q] buffer without a copy)           */
 } ymp_gemm_args;
 
 int ymp_gemm(const ymp_gemm_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm (fp32 statistics, bf16 in/out), one warp per row.
+ * Replaces LayerNormWithForceFP32.forward (models/vision_transformer.py:69-71: cast->LN->cast,
+ * three kernels) and megatron MixedFusedLayerNorm (models/modeling_distributed_gpt3.py:1002-1020,
+ * 1131-1135) plus their autograd backward.
+ *   in_rows (optional int32 [rows]): output row r normalises input row in_rows[r]; used for the
+ *   final TimeSformer norm to emit the reference's (t n) token order (vision_transformer.py:582-585).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ymp_layernorm_args {
+  const void* x;      /* bf16 [*, D], row stride ldx */
+  const void* gamma;  /* bf16 [D] */
+  const void* beta;   /* bf16 [D] */
+  void* y;            /* bf16 [rows, D], row stride ldy */
+  float* mean;        /* fp32 [rows] or NULL (saved for backward) */
+  float* rstd;        /* fp32 [rows] or NULL */
+  const int32_t* in_rows;
+  int32_t rows, D, ldx, ldy;
+  float eps;
+} ymp_layernorm_args;
+int ymp_layernorm_fwd(const ymp_layernorm_args* a, void* stream);
+
+typedef struct ymp_layernorm_bwd_args {
+  const void* dy;     /* bf16 [rows, D], stride lddy */
+  const void* x;      /* bf16, the forward input (stride ldx) */
+  const void* gamma;
+  const float* mean;
+  const float* rstd;
+  const void* add;    /* optional bf16 [*, D] (stride ldadd): gradient of the skip branch, added to dx */
+  void* dx;           /* bf16, same indexing/stride as x */
+  float* dgamma;      /* fp32 [D], ACCUMULATED (atomics); NULL (with dbeta) when the affine is frozen */
+  float* dbeta;
+  const int32_t* in_rows;
+  int32_t rows, D, ldx, lddy, ldadd;
+} ymp_layernorm_bwd_args;
+int ymp_layernorm_bwd(const ymp_layernorm_bwd_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused attention: O = softmax(scale * Q K^T [causal]) V, scores never materialised.
+ * Replaces Attention.forward core (models/vision_transformer.py:179-204), nn.MultiheadAttention
+ * inside AttentionPool (:371) and GPT3CoreAttention.forward (models/modeling_distributed_gpt3.py:
+ * 734-817: baddbmm -> scale/mask(-10000)/softmax -> bmm) and their backward.
+ *
+ * Rows of a sequence are found through a ymp_seqmap, so Q/K/V are read in place from packed QKV
+ * GEMM outputs:  row(s, i) =
+ *     i <  n_prefix : prefix_base + (prefix_per_seq ? s : s / seq_div) * prefix_stride + i
+ *     i >= n_prefix : (s / seq_div) * outer_stride + (s % seq_div) * inner_stride
+ *                     + (i - n_prefix) * pos_stride
+ * element(s, i, head, d) = base[row(s,i) * ld + head * head_stride + d].
+ *   dense [n_seq, S] rows:           seq_div=1, outer_stride=S, pos_stride=1
+ *   TimeSformer frame (b,t) tokens stored (b, n, t) with one cls row per b appended after all
+ *   tokens (vision_transformer.py:254-267):  seq_div=T, outer_stride=N*T, inner_stride=1,
+ *   pos_stride=T, n_prefix=1, prefix_base=B*N*T, prefix_stride=1
+ * lse: fp32 [n_seq, n_heads, s_q] (natural log), needed by the backward.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ymp_seqmap {
+  int32_t seq_div;
+  int32_t n_prefix;
+  int32_t prefix_per_seq;
+  int32_t _pad;
+  int64_t outer_stride, inner_stride, pos_stride;
+  int64_t prefix_base, prefix_stride;
+} ymp_seqmap;
+
+typedef struct ymp_attn_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  float* lse;
+  int32_t ldq, ldk, ldv, ldo;
+  int32_t q_head_stride, k_head_stride, v_head_stride, o_head_stride;
+  ymp_seqmap map_q, map_kv, map_o;
+  int32_t n_seq, n_heads, head_dim, s_q, s_kv;
+  int32_t causal;
+  float scale;
+} ymp_attn_args;
+int ymp_attn_fwd(const ymp_attn_args* a, void* stream);
+
+typedef struct ymp_attn_bwd_args {
+  ymp_attn_args fwd;      /* the forward call's arguments (q,k,v,o,lse and maps) */
+  const void* dout;       /* bf16, addressed by map_do / lddo / do_head_stride */
+  void* dq;               /* bf16 outputs; every addressed element is written exactly once */
+  void* dk;
+  void* dv;
+  int32_t lddo, lddq, lddk, lddv;
+  int32_t do_head_stride, dq_head_stride, dk_head_stride, dv_head_stride;
+  ymp_seqmap map_do, map_dq, map_dkv;
+} ymp_attn_bwd_args;
+int ymp_attn_bwd(const ymp_attn_bwd_args* a, void* stream);
+
+/* TimeSformer temporal attention (sequence length = num_frames <= 16): dense sequences of S
+ * consecutive rows, one warp per (sequence, head).  vision_transformer.py:246-248 via :179-204. */
+typedef struct ymp_attn_small_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  const void* dout;  /* backward only */
+  void* dq;
+  void* dk;
+  void* dv;
+  int32_t ld, head_stride;      /* q,k,v */
+  int32_t ldo, o_head_stride;   /* o and dout */
+  int32_t ldd, d_head_stride;   /* dq,dk,dv */
+  int32_t n_seq, n_heads, S, D;
+  float scale;
+} ymp_attn_small_args;
+int ymp_attn_small_fwd(const ymp_attn_small_args* a, void* stream);
+int ymp_attn_small_bwd(const ymp_attn_small_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Patch-embedding im2col: video [B,C,T,H,W] bf16 -> patches [(b,n,t), C*P*P] (the A operand of
+ * the conv-as-GEMM).  Replaces the `(b t) c h w` rearrange + Conv2d(k=stride=P)
+ * (models/vision_transformer.py:546-548,397).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ymp_im2col_args {
+  const void* video;
+  void* out;
+  int32_t B, C, T, H, W, P, ldo;
+} ymp_im2col_args;
+int ymp_im2col(const ymp_im2col_args* a, void* stream);
+
+/* Word-embedding gather + learned position add, written straight into the decoder input
+ * buffer [B, S, hidden] at rows row_offset..row_offset+L-1 of each sample.  Replaces
+ * word_embeddings(ids) + cat + position add (models/distributed_gpt3.py:155-156,
+ * models/modeling_distributed_gpt3.py:640-650).  Index work is bit-exact. */
+typedef struct ymp_embed_args {
+  const int64_t* ids;  /* [B, L] */
+  const void* table;   /* bf16 [vocab, hidden] */
+  const void* pos;     /* bf16 [max_pos, hidden] or NULL */
+  void* out;           /* bf16 [B*S, hidden] rows of stride ldo */
+  int32_t B, L, S, row_offset, hidden, vocab, ldo;
+} ymp_embed_args;
+int ymp_embed_gather(const ymp_embed_args* a, void* stream);
+
+/* Softmax cross entropy over the vocabulary, per-token (unreduced) losses.  Replaces
+ * logits.clone().float() + vocab_parallel_cross_entropy (modeling_distributed_gpt3.py:1353-1359).
+ * bwd: dlogits = grad_rows[row] * (softmax - onehot), may alias logits. */
+typedef struct ymp_ce_args {
+  const void* logits;      /* bf16 [rows, V], stride ld */
+  const int64_t* labels;   /* [rows] */
+  float* loss;             /* fp32 [rows] (fwd) */
+  float* lse;              /* fp32 [rows] (fwd out / bwd in) */
+  const float* grad_rows;  /* fp32 [rows] (bwd) */
+  void* dlogits;           /* bf16 [rows, V] (bwd) */
+  int32_t rows, V, ld;
+} ymp_ce_args;
+int ymp_ce_fwd(const ymp_ce_args* a, void* stream);
+int ymp_ce_bwd(const ymp_ce_args* a, void* stream);
+
+/* out[c] += sum_r in[r,c]  (bias gradients, batch sums).  out is fp32 and ACCUMULATED. */
+typedef struct ymp_colsum_args {
+  const void* in;  /* bf16 [R, C], stride ld */
+  float* out;      /* fp32 [C] */
+  int32_t R, C, ld;
+} ymp_colsum_args;
+int ymp_colsum(const ymp_colsum_args* a, void* stream);
+
+/* broadcast=0: out[g,:] = scale * sum_t in[g,t,:]   (cls mean over frames, vision_transformer.py:262)
+ * broadcast=1: out[g,t,:] = scale * in[g,:]          (its backward) */
+typedef struct ymp_group_args {
+  const void* in;
+  void* out;
+  int32_t G, T, C, ld_in, ld_out, broadcast;
+  float scale;
+} ymp_group_args;
+int ymp_group_reduce(const ymp_group_args* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,297 @@
+"""GPU parity for the non-GEMM kernels: each op vs a plain fp32 torch restatement of the same math
+(the checker runs in fp32 on the same bf16-rounded inputs; tolerances are bf16 output rounding)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-6)).item()
+
+
+@pytest.mark.parametrize("rows,D", [(100, 768), (37, 2048), (16, 2560), (9, 1408), (64, 192), (5, 128)])
+def test_layernorm_fwd_bwd(cuda, rows, D):
+    from ymp import ops
+    torch.manual_seed(0)
+    x = (torch.randn(rows, D, device=cuda) * 2 + 0.5).to(bf16)
+    g = (1 + 0.1 * torch.randn(D, device=cuda)).to(bf16)
+    b = (0.1 * torch.randn(D, device=cuda)).to(bf16)
+    dy = torch.randn(rows, D, device=cuda).to(bf16)
+    add = torch.randn(rows, D, device=cuda).to(bf16)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-6)
+    xf, gf, bf_ = x.float().requires_grad_(), g.float().requires_grad_(), b.float().requires_grad_()
+    ref = torch.nn.functional.layer_norm(xf, (D,), gf, bf_, 1e-6)
+    assert _rel(y, ref) < 1e-2
+    ref.backward(dy.float())
+    dgam = torch.zeros(D, device=cuda)
+    dbet = torch.zeros(D, device=cuda)
+    dx = ops.layernorm_bwd(dy, x, g, mean, rstd, add=add, dgamma=dgam, dbeta=dbet)
+    assert _rel(dx, xf.grad + add.float()) < 1e-2
+    assert _rel(dgam, gf.grad) < 5e-3
+    assert _rel(dbet, bf_.grad) < 5e-3
+    dx2 = ops.layernorm_bwd(dy, x, g, mean, rstd)  # frozen affine, no add
+    assert _rel(dx2, xf.grad) < 1e-2
+
+
+def test_layernorm_row_gather(cuda):
+    from ymp import ops
+    torch.manual_seed(1)
+    rows, D = 50, 768
+    x = torch.randn(rows, D, device=cuda).to(bf16)
+    g = torch.ones(D, device=cuda, dtype=bf16)
+    b = torch.zeros(D, device=cuda, dtype=bf16)
+    perm = torch.randperm(rows, device=cuda).int()
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-6, in_rows=perm)
+    ref = torch.nn.functional.layer_norm(x.float()[perm.long()], (D,))
+    assert _rel(y, ref) < 1e-2
+    dy = torch.randn(rows, D, device=cuda).to(bf16)
+    dx = ops.layernorm_bwd(dy, x, g, mean, rstd, in_rows=perm)
+    xf = x.float().requires_grad_()
+    torch.nn.functional.layer_norm(xf[perm.long()], (D,)).backward(dy.float())
+    assert _rel(dx, xf.grad) < 1e-2
+
+
+def _attn_ref(q, k, v, scale, causal):
+    """q [n,h,sq,d] etc. fp32 -> out, with autograd."""
+    s = (q @ k.transpose(-1, -2)) * scale
+    if causal:
+        m = torch.ones(s.shape[-2:], dtype=torch.bool, device=s.device).triu(1)
+        s = s.masked_fill(m, -10000.0)
+    return s.softmax(-1) @ v
+
+
+@pytest.mark.parametrize("hd,heads,S,causal,layout", [
+    (64, 4, 256, True, "gpt"), (64, 2, 100, True, "gpt"), (80, 2, 130, True, "gpt"),
+    (96, 2, 197, False, "vit"), (96, 8, 64, False, "vit"), (64, 2, 300, False, "vit")])
+def test_attn_dense_fwd_bwd(cuda, hd, heads, S, causal, layout):
+    from ymp import ops
+    torch.manual_seed(2)
+    n = 3
+    C = heads * hd
+    qkv = (torch.randn(n * S, 3 * C, device=cuda) * 0.7).to(bf16)
+    if layout == "gpt":  # per head [q|k|v]
+        hs, offs = 3 * hd, (0, hd, 2 * hd)
+        qkv5 = qkv.float().view(n, S, heads, 3, hd)
+        q, k, v = (qkv5[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
+    else:                # [3, heads, hd]
+        hs, offs = hd, (0, C, 2 * C)
+        qkv5 = qkv.float().view(n, S, 3, heads, hd)
+        q, k, v = (qkv5[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    q, k, v = (t.contiguous().requires_grad_() for t in (q, k, v))
+    scale = hd ** -0.5
+    m = ops.dense_map(S)
+    out = torch.zeros(n * S, C, device=cuda, dtype=bf16)
+    tq, tk, tv = (ops.TView(qkv, o, hs, m) for o in offs)
+    to = ops.TView(out, 0, hd, m)
+    kw = dict(n_seq=n, n_heads=heads, head_dim=hd, s_q=S, s_kv=S, causal=causal, scale=scale)
+    lse = ops.attn_fwd(tq, tk, tv, to, **kw)
+    ref = _attn_ref(q, k, v, scale, causal)
+    assert _rel(out.view(n, S, heads, hd).permute(0, 2, 1, 3), ref) < 2e-2
+    dout = torch.randn(n * S, C, device=cuda).to(bf16)
+    ref.backward(dout.float().view(n, S, heads, hd).permute(0, 2, 1, 3))
+    dqkv = torch.zeros_like(qkv)
+    tdo = ops.TView(dout, 0, hd, m)
+    tdq, tdk, tdv = (ops.TView(dqkv, o, hs, m) for o in offs)
+    ops.attn_bwd(tq, tk, tv, to, lse, tdo, tdq, tdk, tdv, **kw)
+    if layout == "gpt":
+        d5 = dqkv.float().view(n, S, heads, 3, hd)
+        dq, dk, dv = (d5[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
+    else:
+        d5 = dqkv.float().view(n, S, 3, heads, hd)
+        dq, dk, dv = (d5[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    assert _rel(dq, q.grad) < 3e-2
+    assert _rel(dk, k.grad) < 3e-2
+    assert _rel(dv, v.grad) < 3e-2
+
+
+def test_attn_cross_shared_q(cuda):
+    """Abstractor pattern: one shared query block for every sample, long KV with a ragged tail."""
+    from ymp import ops
+    torch.manual_seed(3)
+    B, Q, S, heads, hd = 2, 128, 330, 8, 96
+    C = heads * hd
+    qp = (torch.randn(Q, C, device=cuda) * 0.5).to(bf16)
+    kv = (torch.randn(B * S, 2 * C, device=cuda) * 0.5).to(bf16)
+    out = torch.zeros(B * Q, C, device=cuda, dtype=bf16)
+    mq = ops.seqmap(seq_div=1, outer_stride=0, pos_stride=1)  # every sequence reads the same rows
+    mkv, mo = ops.dense_map(S), ops.dense_map(Q)
+    tq, tk, tv, to = ops.TView(qp, 0, hd, mq), ops.TView(kv, 0, hd, mkv), ops.TView(kv, C, hd, mkv), ops.TView(out, 0, hd, mo)
+    kw = dict(n_seq=B, n_heads=heads, head_dim=hd, s_q=Q, s_kv=S, causal=False, scale=hd ** -0.5)
+    lse = ops.attn_fwd(tq, tk, tv, to, **kw)
+    q = qp.float().view(1, Q, heads, hd).permute(0, 2, 1, 3).expand(B, -1, -1, -1).contiguous().requires_grad_()
+    k = kv.float()[:, :C].reshape(B, S, heads, hd).permute(0, 2, 1, 3).contiguous().requires_grad_()
+    v = kv.float()[:, C:].reshape(B, S, heads, hd).permute(0, 2, 1, 3).contiguous().requires_grad_()
+    ref = _attn_ref(q, k, v, hd ** -0.5, False)
+    assert _rel(out.view(B, Q, heads, hd).permute(0, 2, 1, 3), ref) < 2e-2
+    dout = torch.randn(B * Q, C, device=cuda).to(bf16)
+    ref.backward(dout.float().view(B, Q, heads, hd).permute(0, 2, 1, 3))
+    dq = torch.zeros(B * Q, C, device=cuda, dtype=bf16)   # per-sample dq, summed by the caller
+    dkv = torch.zeros_like(kv)
+    ops.attn_bwd(tq, tk, tv, to, lse, ops.TView(dout, 0, hd, mo), ops.TView(dq, 0, hd, mo),
+                 ops.TView(dkv, 0, hd, mkv), ops.TView(dkv, C, hd, mkv), **kw)
+    assert _rel(dq.view(B, Q, heads, hd).permute(0, 2, 1, 3), q.grad) < 3e-2
+    assert _rel(dkv[:, :C].reshape(B, S, heads, hd).permute(0, 2, 1, 3), k.grad) < 3e-2
+    assert _rel(dkv[:, C:].reshape(B, S, heads, hd).permute(0, 2, 1, 3), v.grad) < 3e-2
+
+
+def test_attn_timesformer_spatial_map(cuda):
+    """Per-frame sequences [cls_b ; x[b, :, t]] read in place from the (b n t)+cls row layout."""
+    from ymp import ops
+    torch.manual_seed(4)
+    B, N, T, heads, hd = 2, 9, 3, 2, 96
+    C = heads * hd
+    R = B * N * T
+    qkv = (torch.randn(R + B, 3 * C, device=cuda) * 0.6).to(bf16)
+    out = torch.zeros(R, C, device=cuda, dtype=bf16)
+    cls_out = torch.zeros(B * T, C, device=cuda, dtype=bf16)
+    m_in = ops.seqmap(seq_div=T, outer_stride=N * T, inner_stride=1, pos_stride=T, n_prefix=1,
+                      prefix_base=R, prefix_stride=1, prefix_per_seq=0)
+    # outputs: tokens back in (b n t) rows of `out`; the per-frame cls outputs go to cls_out[(b t)]
+    big = torch.cat([out, cls_out], 0)  # one buffer: token rows then B*T cls rows
+    m_out = ops.seqmap(seq_div=T, outer_stride=N * T, inner_stride=1, pos_stride=T, n_prefix=1,
+                       prefix_base=R, prefix_stride=1, prefix_per_seq=1)
+    kw = dict(n_seq=B * T, n_heads=heads, head_dim=hd, s_q=N + 1, s_kv=N + 1, causal=False, scale=hd ** -0.5)
+    tq, tk, tv = (ops.TView(qkv, i * C, hd, m_in) for i in range(3))
+    to = ops.TView(big, 0, hd, m_out)
+    lse = ops.attn_fwd(tq, tk, tv, to, **kw)
+    # reference: build the explicit sequences
+    f = qkv.float()
+    tok = f[:R].view(B, N, T, 3, heads, hd)
+    cls = f[R:].view(B, 1, 1, 3, heads, hd).expand(B, 1, T, 3, heads, hd)
+    seq = torch.cat([cls, tok], dim=1).permute(0, 2, 3, 4, 1, 5).reshape(B * T, 3, heads, N + 1, hd)
+    q, k, v = (seq[:, i].contiguous().requires_grad_() for i in range(3))
+    ref = _attn_ref(q, k, v, hd ** -0.5, False)          # [B*T, heads, N+1, hd]
+    got_tok = big[:R].float().view(B, N, T, heads, hd).permute(0, 2, 3, 1, 4).reshape(B * T, heads, N, hd)
+    got_cls = big[R:].float().view(B * T, heads, 1, hd)
+    assert _rel(got_tok, ref[:, :, 1:]) < 2e-2
+    assert _rel(got_cls, ref[:, :, :1]) < 2e-2
+    # backward: token grads in place, cls-row grads per frame (caller sums over T)
+    dbig = torch.randn_like(big.float()).to(bf16)
+    dref = torch.cat([dbig[R:].float().view(B * T, heads, 1, hd),
+                      dbig[:R].float().view(B, N, T, heads, hd).permute(0, 2, 3, 1, 4).reshape(B * T, heads, N, hd)], 2)
+    ref.backward(dref)
+    dqkv = torch.zeros(R + B * T, 3 * C, device=cuda, dtype=bf16)
+    tdq, tdk, tdv = (ops.TView(dqkv, i * C, hd, m_out) for i in range(3))
+    ops.attn_bwd(tq, tk, tv, to, lse, ops.TView(dbig, 0, hd, m_out), tdq, tdk, tdv, **kw)
+    for i, gr in enumerate((q.grad, k.grad, v.grad)):
+        d = dqkv.float()[:, i * C:(i + 1) * C]
+        d_tok = d[:R].view(B, N, T, heads, hd).permute(0, 2, 3, 1, 4).reshape(B * T, heads, N, hd)
+        d_cls = d[R:].view(B * T, heads, 1, hd)
+        assert _rel(d_tok, gr[:, :, 1:]) < 3e-2, i
+        assert _rel(d_cls, gr[:, :, :1]) < 3e-2, i
+
+
+@pytest.mark.parametrize("S,heads,hd", [(8, 8, 96), (4, 2, 96), (2, 2, 64), (16, 4, 80)])
+def test_attn_small(cuda, S, heads, hd):
+    from ymp import ops
+    torch.manual_seed(5)
+    n, C = 37, heads * hd
+    qkv = (torch.randn(n * S, 3 * C, device=cuda) * 0.6).to(bf16)
+    out = torch.zeros(n * S, C, device=cuda, dtype=bf16)
+    scale = hd ** -0.5
+    ops.attn_small_fwd(qkv, out, n_seq=n, n_heads=heads, S=S, D=hd, scale=scale)
+    q5 = qkv.float().view(n, S, 3, heads, hd)
+    q, k, v = (q5[:, :, i].permute(0, 2, 1, 3).contiguous().requires_grad_() for i in range(3))
+    ref = _attn_ref(q, k, v, scale, False)
+    assert _rel(out.view(n, S, heads, hd).permute(0, 2, 1, 3), ref) < 2e-2
+    dout = torch.randn(n * S, C, device=cuda).to(bf16)
+    ref.backward(dout.float().view(n, S, heads, hd).permute(0, 2, 1, 3))
+    dqkv = torch.zeros_like(qkv)
+    ops.attn_small_bwd(qkv, dout, dqkv, n_seq=n, n_heads=heads, S=S, D=hd, scale=scale)
+    d5 = dqkv.float().view(n, S, 3, heads, hd)
+    for i, gr in enumerate((q.grad, k.grad, v.grad)):
+        assert _rel(d5[:, :, i].permute(0, 2, 1, 3), gr) < 3e-2, i
+
+
+def test_im2col_matches_conv(cuda):
+    from ymp import ops
+    torch.manual_seed(6)
+    B, T, H, P, D = 2, 3, 64, 16, 128
+    video = torch.randn(B, 3, T, H, H, device=cuda).to(bf16)
+    w = (torch.randn(D, 3, P, P, device=cuda) * 0.05).to(bf16)
+    patches = ops.im2col(video, P)
+    y = ops.gemm(patches, w.view(D, -1))
+    N = (H // P) ** 2
+    ref = torch.nn.functional.conv2d(video.float().permute(0, 2, 1, 3, 4).reshape(B * T, 3, H, H), w.float(), stride=P)
+    ref = ref.flatten(2).transpose(1, 2).reshape(B, T, N, D).permute(0, 2, 1, 3).reshape(B * N * T, D)
+    assert _rel(y, ref) < 1e-2
+    # bit-exact gather
+    ref_p = video.view(B, 3, T, H // P, P, H // P, P).permute(0, 3, 5, 2, 1, 4, 6).reshape(B * N * T, 3 * P * P)
+    assert torch.equal(patches, ref_p)
+
+
+def test_embed_gather_bit_exact(cuda):
+    from ymp import ops
+    torch.manual_seed(7)
+    B, Ln, Q, Hd, V = 3, 10, 6, 256, 1000
+    S = Q + Ln
+    table = torch.randn(V, Hd, device=cuda).to(bf16)
+    pos = torch.randn(64, Hd, device=cuda).to(bf16)
+    ids = torch.randint(0, V, (B, Ln), device=cuda)
+    out = torch.zeros(B * S, Hd, device=cuda, dtype=bf16)
+    ops.embed_gather(ids, table, pos, out, S, Q)
+    ref = (table[ids].float() + pos[Q:Q + Ln].float()[None]).to(bf16)
+    assert torch.equal(out.view(B, S, Hd)[:, Q:], ref)
+    assert out.view(B, S, Hd)[:, :Q].abs().sum() == 0
+    out2 = torch.zeros(B * S, Hd, device=cuda, dtype=bf16)
+    ops.embed_gather(ids, table, None, out2, S, Q)
+    assert torch.equal(out2.view(B, S, Hd)[:, Q:], table[ids])
+
+
+@pytest.mark.parametrize("V", [512, 51200, 1000])
+def test_cross_entropy(cuda, V):
+    from ymp import ops
+    torch.manual_seed(8)
+    rows = 33
+    logits = (torch.randn(rows, V, device=cuda) * 3).to(bf16)
+    labels = torch.randint(0, V, (rows,), device=cuda)
+    loss, lse = ops.ce_fwd(logits, labels)
+    lf = logits.float().requires_grad_()
+    ref = torch.nn.functional.cross_entropy(lf, labels, reduction="none")
+    assert _rel(loss, ref) < 1e-4
+    g = torch.rand(rows, device=cuda)
+    g[::5] = 0
+    ref.backward(g)
+    d = ops.ce_bwd(logits, labels, lse, g, dlogits=torch.empty_like(logits))
+    assert _rel(d, lf.grad) < 1e-2
+    d2 = ops.ce_bwd(logits.clone(), labels, lse, g)  # in place
+    assert torch.equal(d2, d)
+
+
+def test_colsum_and_group(cuda):
+    from ymp import ops
+    torch.manual_seed(9)
+    x = torch.randn(1000, 768, device=cuda).to(bf16)
+    out = torch.ones(768, device=cuda)
+    ops.colsum(x, out)
+    assert _rel(out, x.float().sum(0) + 1) < 1e-4
+    xs = torch.randn(500, 2304, device=cuda).to(bf16)[:, 768:1536]  # strided slice
+    o2 = torch.zeros(768, device=cuda)
+    ops.colsum(xs, o2)
+    assert _rel(o2, xs.float().sum(0)) < 1e-4
+    G, T, C = 6, 8, 768
+    y = torch.randn(G * T, C, device=cuda).to(bf16)
+    o = torch.empty(G, C, device=cuda, dtype=bf16)
+    ops.group_reduce(y, G, T, o, scale=1.0 / T)
+    assert _rel(o, y.float().view(G, T, C).mean(1)) < 1e-2
+    bb = torch.empty(G * T, C, device=cuda, dtype=bf16)
+    ops.group_reduce(o, G, T, bb, scale=0.5, broadcast=True)
+    assert _rel(bb.view(G, T, C), (o.float() * 0.5)[:, None].expand(G, T, C)) < 1e-2
+
+
+def test_gemm_row_remap_and_broadcast_residual(cuda):
+    from ymp import ops
+    torch.manual_seed(10)
+    B, Q, S, K, N = 3, 8, 20, 64, 128
+    a = torch.randn(B * Q, K, device=cuda).to(bf16)
+    w = (torch.randn(N, K, device=cuda) * 0.1).to(bf16)
+    pos = torch.randn(32, N, device=cuda).to(bf16)
+    out = torch.zeros(B * S, N, device=cuda, dtype=bf16)
+    ops.gemm(a, w, residual=pos, res_row_mod=Q, out=out, d_row_block=Q, d_row_stride=S)
+    ref = (a.float() @ w.float().t()).view(B, Q, N) + pos[:Q].float()[None]
+    assert _rel(out.view(B, S, N)[:, :Q], ref) < 1e-2
+    assert out.view(B, S, N)[:, Q:].abs().sum() == 0

@@ -30,6 +30,8 @@ struct GemmKParams {
   int a_mn, b_mn;
   int act, out_f32, accumulate, split_k;
   int kb_per_split;
+  int res_row_mod;                 // residual row = row % res_row_mod (0: plain)
+  int d_row_block, d_row_stride;   // D row = (row / block) * stride + row % block (0: plain)
   float alpha;
 };
 
@@ -58,6 +60,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
                                                int row, int col0) {
   if (row >= p.M || col0 >= p.N) return;
   const bool full = (col0 + 32 <= p.N);
+  const int drow = p.d_row_block ? (row / p.d_row_block) * p.d_row_stride + row % p.d_row_block : row;
+  const int rrow = p.res_row_mod ? row % p.res_row_mod : row;
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
@@ -74,7 +78,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
         v[8 * j + 6] += bf16_lo(b.w); v[8 * j + 7] += bf16_hi(b.w);
       }
     }
-    const size_t off = (size_t)row * p.ldd + col0;
+    const size_t off = (size_t)row * p.ldd + col0;          // aux tensors: plain rows
+    const size_t doff = (size_t)drow * p.ldd + col0;        // D: optionally re-blocked rows
     if (p.aux_out) {
       uint4* a4 = reinterpret_cast<uint4*>(p.aux_out + off);
 #pragma unroll
@@ -102,7 +107,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
       for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
     }
     if (p.residual) {
-      const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + col0);
+      const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (size_t)rrow * p.ldr + col0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 a = __ldg(r4 + j);
@@ -113,7 +118,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
       }
     }
     if (!p.out_f32) {
-      uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + off);
+      uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + doff);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 o;
@@ -124,11 +129,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
         d4[j] = o;
       }
     } else if (!p.accumulate) {
-      float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + off);
+      float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + doff);
 #pragma unroll
       for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     } else {
-      float* d = reinterpret_cast<float*>(p.D) + off;
+      float* d = reinterpret_cast<float*>(p.D) + doff;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4 * j),
@@ -138,19 +143,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
     }
   } else {
     // ragged N tail: scalar, bounds-checked
+#pragma unroll
     for (int i = 0; i < 32; ++i) {
-      int col = col0 + i;
-      if (col >= p.N) break;
-      float x = v[i];
-      if (p.bias) x += __bfloat162float(p.bias[col]);
-      size_t off = (size_t)row * p.ldd + col;
-      if (p.aux_out) p.aux_out[off] = __float2bfloat16(x);
-      if (p.aux_in) x *= apply_dact(__bfloat162float(p.aux_in[off]), p.act);
-      else x = apply_act(x, p.act);
-      if (p.residual) x += __bfloat162float(p.residual[(size_t)row * p.ldr + col]);
-      if (!p.out_f32) reinterpret_cast<__nv_bfloat16*>(p.D)[off] = __float2bfloat16(x);
-      else if (!p.accumulate) reinterpret_cast<float*>(p.D)[off] = x;
-      else atomicAdd(reinterpret_cast<float*>(p.D) + off, x);
+      const int col = col0 + i;
+      if (col < p.N) {
+        float x = v[i];
+        if (p.bias) x += __bfloat162float(p.bias[col]);
+        const size_t off = (size_t)row * p.ldd + col, doff = (size_t)drow * p.ldd + col;
+        if (p.aux_out) p.aux_out[off] = __float2bfloat16(x);
+        if (p.aux_in) x *= apply_dact(__bfloat162float(p.aux_in[off]), p.act);
+        else x = apply_act(x, p.act);
+        if (p.residual) x += __bfloat162float(p.residual[(size_t)rrow * p.ldr + col]);
+        if (!p.out_f32) reinterpret_cast<__nv_bfloat16*>(p.D)[doff] = __float2bfloat16(x);
+        else if (!p.accumulate) reinterpret_cast<float*>(p.D)[doff] = x;
+        else atomicAdd(reinterpret_cast<float*>(p.D) + doff, x);
+      }
     }
   }
 }
@@ -406,6 +413,8 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
   YMP_CHECK_ARG(!(a->accumulate && a->out_dtype != YMP_DT_F32), "ymp_gemm: accumulate needs fp32 output");
   YMP_CHECK_ARG(!(a->accumulate && (a->aux_out || a->aux_in || a->act || a->residual)),
                 "ymp_gemm: accumulate mode supports only alpha and bias-free linear epilogue");
+  YMP_CHECK_ARG(a->res_row_mod >= 0 && a->d_row_block >= 0 && (a->d_row_block == 0 || a->d_row_stride >= a->d_row_block),
+                "ymp_gemm: bad res_row_mod / d_row_block / d_row_stride");
   YMP_CHECK_ARG(a->tile_n == 0 || a->tile_n == 128 || a->tile_n == 256, "ymp_gemm: tile_n must be 0/128/256");
 
   const int kb_total = (a->K + BK - 1) / BK;
@@ -441,6 +450,7 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
   kp.act = a->act; kp.out_f32 = (a->out_dtype == YMP_DT_F32); kp.accumulate = a->accumulate ? 1 : 0;
   kp.split_k = split; kp.kb_per_split = per;
   kp.alpha = a->alpha;
+  kp.res_row_mod = a->res_row_mod; kp.d_row_block = a->d_row_block; kp.d_row_stride = a->d_row_stride;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (bn == 256) return launch_gemm<256>(a, kp, st);
   return launch_gemm<128>(a, kp, st);

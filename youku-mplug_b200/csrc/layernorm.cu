@@ -1,0 +1,236 @@
+// LayerNorm forward / backward: one warp per row, 128-bit coalesced loads, fp32 statistics,
+// warp-shuffle reductions.  HBM-bound (reads x once, writes y once).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ymp {
+
+constexpr int LN_WARPS = 8;
+
+struct LnParams {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* gamma;
+  const __nv_bfloat16* beta;
+  __nv_bfloat16* y;
+  float* mean;
+  float* rstd;
+  const int32_t* in_rows;
+  int rows, D, ldx, ldy;
+  float eps;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
+  u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  return u;
+}
+
+// VPL = 16-byte vectors per lane (D <= VPL*256)
+template <int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nvec = p.D >> 3;
+  for (int row = blockIdx.x * LN_WARPS + warp; row < p.rows; row += gridDim.x * LN_WARPS) {
+    const int irow = p.in_rows ? p.in_rows[row] : row;
+    const uint4* xr = reinterpret_cast<const uint4*>(p.x + (size_t)irow * p.ldx);
+    float v[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int vi = j * 32 + lane;
+      if (vi < nvec) {
+        unpack8(__ldg(xr + vi), v[j]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += v[j][e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
+      }
+    }
+    const float mu = warp_sum(s) / (float)p.D;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      if (j * 32 + lane < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { float d = v[j][e] - mu; q += d * d; }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) / (float)p.D + p.eps);
+    if (lane == 0) {
+      if (p.mean) p.mean[row] = mu;
+      if (p.rstd) p.rstd[row] = rs;
+    }
+    uint4* yr = reinterpret_cast<uint4*>(p.y + (size_t)row * p.ldy);
+    const uint4* g4 = reinterpret_cast<const uint4*>(p.gamma);
+    const uint4* b4 = reinterpret_cast<const uint4*>(p.beta);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int vi = j * 32 + lane;
+      if (vi < nvec) {
+        float g[8], b[8], o[8];
+        unpack8(__ldg(g4 + vi), g);
+        unpack8(__ldg(b4 + vi), b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf((v[j][e] - mu) * rs, g[e], b[e]);
+        yr[vi] = pack8(o);
+      }
+    }
+  }
+}
+
+struct LnBwdParams {
+  const __nv_bfloat16* dy;
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* gamma;
+  const float* mean;
+  const float* rstd;
+  const __nv_bfloat16* add;  // optional gradient of the residual branch, added to dx
+  __nv_bfloat16* dx;
+  float* dgamma;  // fp32 [D], accumulated with atomics (caller zeroes); NULL = frozen
+  float* dbeta;
+  const int32_t* in_rows;
+  int rows, D, ldx, lddy, ldadd;
+};
+
+template <int VPL, bool WGRAD>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nvec = p.D >> 3;
+  float dg[WGRAD ? VPL : 1][8], db[WGRAD ? VPL : 1][8];
+  if (WGRAD) {
+#pragma unroll
+    for (int j = 0; j < VPL; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { dg[j][e] = 0.f; db[j][e] = 0.f; }
+  }
+  const uint4* g4 = reinterpret_cast<const uint4*>(p.gamma);
+  for (int row = blockIdx.x * LN_WARPS + warp; row < p.rows; row += gridDim.x * LN_WARPS) {
+    const int irow = p.in_rows ? p.in_rows[row] : row;
+    const uint4* xr = reinterpret_cast<const uint4*>(p.x + (size_t)irow * p.ldx);
+    const uint4* dyr = reinterpret_cast<const uint4*>(p.dy + (size_t)row * p.lddy);
+    const float mu = p.mean[row], rs = p.rstd[row];
+    float xh[VPL][8], gy[VPL][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int vi = j * 32 + lane;
+      if (vi < nvec) {
+        float xv[8], dyv[8], g[8];
+        unpack8(__ldg(xr + vi), xv);
+        unpack8(__ldg(dyr + vi), dyv);
+        unpack8(__ldg(g4 + vi), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xh[j][e] = (xv[e] - mu) * rs;
+          gy[j][e] = dyv[e] * g[e];
+          s1 += gy[j][e];
+          s2 += gy[j][e] * xh[j][e];
+          if (WGRAD) { dg[j][e] += dyv[e] * xh[j][e]; db[j][e] += dyv[e]; }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { xh[j][e] = 0.f; gy[j][e] = 0.f; }
+      }
+    }
+    s1 = warp_sum(s1) / (float)p.D;
+    s2 = warp_sum(s2) / (float)p.D;
+    uint4* dxr = reinterpret_cast<uint4*>(p.dx + (size_t)irow * p.ldx);
+    const uint4* ar = p.add ? reinterpret_cast<const uint4*>(p.add + (size_t)irow * p.ldadd) : nullptr;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int vi = j * 32 + lane;
+      if (vi < nvec) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rs * (gy[j][e] - s1 - xh[j][e] * s2);
+        if (ar) {
+          float a[8];
+          unpack8(__ldg(ar + vi), a);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] += a[e];
+        }
+        dxr[vi] = pack8(o);
+      }
+    }
+  }
+  if (WGRAD) {
+    // block-level reduce across the 8 warps, then one atomic per column per block
+    __shared__ float red[LN_WARPS][32 * 8 + 1];
+    for (int j = 0; j < VPL; ++j) {
+      for (int pass = 0; pass < 2; ++pass) {
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = pass == 0 ? dg[j][e] : db[j][e];
+        __syncthreads();
+        for (int c = threadIdx.x; c < 256; c += LN_WARPS * 32) {
+          float s = 0.f;
+#pragma unroll
+          for (int w = 0; w < LN_WARPS; ++w) s += red[w][c];
+          const int col = j * 256 + c;
+          if (col < p.D) atomicAdd((pass == 0 ? p.dgamma : p.dbeta) + col, s);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace ymp
+
+extern "C" int ymp_layernorm_fwd(const ymp_layernorm_args* a, void* stream) {
+  using namespace ymp;
+  YMP_CHECK_ARG(a && a->x && a->y && a->gamma && a->beta, "ymp_layernorm_fwd: null pointer");
+  YMP_CHECK_ARG(a->rows > 0 && a->D > 0 && a->D % 8 == 0 && a->D <= 4096, "ymp_layernorm_fwd: D=%d must be a multiple of 8 and <= 4096", a->D);
+  YMP_CHECK_ARG(a->ldx % 8 == 0 && a->ldy % 8 == 0 && a->ldx >= a->D && a->ldy >= a->D, "ymp_layernorm_fwd: bad ld");
+  YMP_CHECK_ARG(aligned16(a->x) && aligned16(a->y) && aligned16(a->gamma) && aligned16(a->beta), "ymp_layernorm_fwd: 16-byte alignment required");
+  LnParams p;
+  p.x = (const __nv_bfloat16*)a->x; p.gamma = (const __nv_bfloat16*)a->gamma; p.beta = (const __nv_bfloat16*)a->beta;
+  p.y = (__nv_bfloat16*)a->y; p.mean = a->mean; p.rstd = a->rstd; p.in_rows = a->in_rows;
+  p.rows = a->rows; p.D = a->D; p.ldx = a->ldx; p.ldy = a->ldy; p.eps = a->eps;
+  const int blocks = min((a->rows + LN_WARPS - 1) / LN_WARPS, num_sms() * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int vpl = (a->D / 8 + 31) / 32;
+  if (vpl <= 3) ln_fwd_kernel<3><<<blocks, LN_WARPS * 32, 0, st>>>(p);
+  else if (vpl <= 8) ln_fwd_kernel<8><<<blocks, LN_WARPS * 32, 0, st>>>(p);
+  else ln_fwd_kernel<16><<<blocks, LN_WARPS * 32, 0, st>>>(p);
+  YMP_LAUNCH_CHECK();
+  return YMP_OK;
+}
+
+extern "C" int ymp_layernorm_bwd(const ymp_layernorm_bwd_args* a, void* stream) {
+  using namespace ymp;
+  YMP_CHECK_ARG(a && a->dy && a->x && a->gamma && a->mean && a->rstd && a->dx, "ymp_layernorm_bwd: null pointer");
+  YMP_CHECK_ARG(a->rows > 0 && a->D > 0 && a->D % 8 == 0 && a->D <= 4096, "ymp_layernorm_bwd: bad D=%d", a->D);
+  YMP_CHECK_ARG((a->dgamma == nullptr) == (a->dbeta == nullptr), "ymp_layernorm_bwd: dgamma/dbeta must both be set or both NULL");
+  YMP_CHECK_ARG(a->ldx % 8 == 0 && a->lddy % 8 == 0 && (!a->add || a->ldadd % 8 == 0), "ymp_layernorm_bwd: bad ld");
+  LnBwdParams p;
+  p.dy = (const __nv_bfloat16*)a->dy; p.x = (const __nv_bfloat16*)a->x; p.gamma = (const __nv_bfloat16*)a->gamma;
+  p.mean = a->mean; p.rstd = a->rstd; p.add = (const __nv_bfloat16*)a->add; p.dx = (__nv_bfloat16*)a->dx;
+  p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.in_rows = a->in_rows;
+  p.rows = a->rows; p.D = a->D; p.ldx = a->ldx; p.lddy = a->lddy; p.ldadd = a->ldadd;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int vpl = (a->D / 8 + 31) / 32;
+  const bool wg = a->dgamma != nullptr;
+  // with weight grads each block ends with D atomics: keep the grid at ~2 blocks per SM
+  const int cap = wg ? num_sms() * 2 : num_sms() * 8;
+  const int blocks = min((a->rows + LN_WARPS - 1) / LN_WARPS, cap);
+  const int thr = LN_WARPS * 32;
+  if (wg) {
+    if (vpl <= 3) ln_bwd_kernel<3, true><<<blocks, thr, 0, st>>>(p);
+    else if (vpl <= 8) ln_bwd_kernel<8, true><<<blocks, thr, 0, st>>>(p);
+    else ln_bwd_kernel<16, true><<<blocks, thr, 0, st>>>(p);
+  } else {
+    if (vpl <= 3) ln_bwd_kernel<3, false><<<blocks, thr, 0, st>>>(p);
+    else if (vpl <= 8) ln_bwd_kernel<8, false><<<blocks, thr, 0, st>>>(p);
+    else ln_bwd_kernel<16, false><<<blocks, thr, 0, st>>>(p);
+  }
+  YMP_LAUNCH_CHECK();
+  return YMP_OK;
+}

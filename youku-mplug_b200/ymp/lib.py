@@ -40,7 +40,85 @@ class GemmArgs(C.Structure):
         ("act", c_i32), ("aux_out", c_vp), ("aux_in", c_vp),
         ("out_dtype", c_i32), ("accumulate", c_i32), ("split_k", c_i32),
         ("alpha", C.c_float), ("tile_n", c_i32),
+        ("res_row_mod", c_i32), ("d_row_block", c_i32), ("d_row_stride", c_i32),
     ]
+
+
+class LayerNormArgs(C.Structure):
+    _fields_ = [
+        ("x", c_vp), ("gamma", c_vp), ("beta", c_vp), ("y", c_vp), ("mean", c_vp), ("rstd", c_vp),
+        ("in_rows", c_vp), ("rows", c_i32), ("D", c_i32), ("ldx", c_i32), ("ldy", c_i32),
+        ("eps", C.c_float),
+    ]
+
+
+class LayerNormBwdArgs(C.Structure):
+    _fields_ = [
+        ("dy", c_vp), ("x", c_vp), ("gamma", c_vp), ("mean", c_vp), ("rstd", c_vp), ("add", c_vp),
+        ("dx", c_vp), ("dgamma", c_vp), ("dbeta", c_vp), ("in_rows", c_vp),
+        ("rows", c_i32), ("D", c_i32), ("ldx", c_i32), ("lddy", c_i32), ("ldadd", c_i32),
+    ]
+
+
+class SeqMap(C.Structure):
+    _fields_ = [
+        ("seq_div", c_i32), ("n_prefix", c_i32), ("prefix_per_seq", c_i32), ("_pad", c_i32),
+        ("outer_stride", C.c_int64), ("inner_stride", C.c_int64), ("pos_stride", C.c_int64),
+        ("prefix_base", C.c_int64), ("prefix_stride", C.c_int64),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", c_vp), ("k", c_vp), ("v", c_vp), ("o", c_vp), ("lse", c_vp),
+        ("ldq", c_i32), ("ldk", c_i32), ("ldv", c_i32), ("ldo", c_i32),
+        ("q_head_stride", c_i32), ("k_head_stride", c_i32), ("v_head_stride", c_i32), ("o_head_stride", c_i32),
+        ("map_q", SeqMap), ("map_kv", SeqMap), ("map_o", SeqMap),
+        ("n_seq", c_i32), ("n_heads", c_i32), ("head_dim", c_i32), ("s_q", c_i32), ("s_kv", c_i32),
+        ("causal", c_i32), ("scale", C.c_float),
+    ]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [
+        ("fwd", AttnArgs), ("dout", c_vp), ("dq", c_vp), ("dk", c_vp), ("dv", c_vp),
+        ("lddo", c_i32), ("lddq", c_i32), ("lddk", c_i32), ("lddv", c_i32),
+        ("do_head_stride", c_i32), ("dq_head_stride", c_i32), ("dk_head_stride", c_i32), ("dv_head_stride", c_i32),
+        ("map_do", SeqMap), ("map_dq", SeqMap), ("map_dkv", SeqMap),
+    ]
+
+
+class AttnSmallArgs(C.Structure):
+    _fields_ = [
+        ("q", c_vp), ("k", c_vp), ("v", c_vp), ("o", c_vp), ("dout", c_vp), ("dq", c_vp), ("dk", c_vp), ("dv", c_vp),
+        ("ld", c_i32), ("head_stride", c_i32), ("ldo", c_i32), ("o_head_stride", c_i32),
+        ("ldd", c_i32), ("d_head_stride", c_i32),
+        ("n_seq", c_i32), ("n_heads", c_i32), ("S", c_i32), ("D", c_i32), ("scale", C.c_float),
+    ]
+
+
+class Im2colArgs(C.Structure):
+    _fields_ = [("video", c_vp), ("out", c_vp), ("B", c_i32), ("C", c_i32), ("T", c_i32), ("H", c_i32),
+                ("W", c_i32), ("P", c_i32), ("ldo", c_i32)]
+
+
+class EmbedArgs(C.Structure):
+    _fields_ = [("ids", c_vp), ("table", c_vp), ("pos", c_vp), ("out", c_vp), ("B", c_i32), ("L", c_i32),
+                ("S", c_i32), ("row_offset", c_i32), ("hidden", c_i32), ("vocab", c_i32), ("ldo", c_i32)]
+
+
+class CeArgs(C.Structure):
+    _fields_ = [("logits", c_vp), ("labels", c_vp), ("loss", c_vp), ("lse", c_vp), ("grad_rows", c_vp),
+                ("dlogits", c_vp), ("rows", c_i32), ("V", c_i32), ("ld", c_i32)]
+
+
+class ColsumArgs(C.Structure):
+    _fields_ = [("in_", c_vp), ("out", c_vp), ("R", c_i32), ("C", c_i32), ("ld", c_i32)]
+
+
+class GroupArgs(C.Structure):
+    _fields_ = [("in_", c_vp), ("out", c_vp), ("G", c_i32), ("T", c_i32), ("C", c_i32), ("ld_in", c_i32),
+                ("ld_out", c_i32), ("broadcast", c_i32), ("scale", C.c_float)]
 
 
 lib.ymp_last_error.restype = C.c_char_p
@@ -56,6 +134,18 @@ def _declare(name, argstruct):
 
 
 _gemm = _declare("ymp_gemm", GemmArgs)
+_ln_fwd = _declare("ymp_layernorm_fwd", LayerNormArgs)
+_ln_bwd = _declare("ymp_layernorm_bwd", LayerNormBwdArgs)
+_attn_fwd = _declare("ymp_attn_fwd", AttnArgs)
+_attn_bwd = _declare("ymp_attn_bwd", AttnBwdArgs)
+_attn_small_fwd = _declare("ymp_attn_small_fwd", AttnSmallArgs)
+_attn_small_bwd = _declare("ymp_attn_small_bwd", AttnSmallArgs)
+_im2col = _declare("ymp_im2col", Im2colArgs)
+_embed = _declare("ymp_embed_gather", EmbedArgs)
+_ce_fwd = _declare("ymp_ce_fwd", CeArgs)
+_ce_bwd = _declare("ymp_ce_bwd", CeArgs)
+_colsum = _declare("ymp_colsum", ColsumArgs)
+_group = _declare("ymp_group_reduce", GroupArgs)
 
 
 def check(rc, what):

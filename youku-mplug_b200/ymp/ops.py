@@ -16,7 +16,8 @@ def _chk2d(t, name):
 
 
 def gemm(a, b, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, aux_out=None,
-         aux_in=None, out=None, out_dtype=bf16, accumulate=False, split_k=0, alpha=1.0, tile_n=0):
+         aux_in=None, out=None, out_dtype=bf16, accumulate=False, split_k=0, alpha=1.0, tile_n=0,
+         res_row_mod=0, d_row_block=0, d_row_stride=0):
     """D[M,N] = epilogue(alpha * op(A) @ op(B)^T).
 
     a: [M,K] (or [K,M] when a_t)      b: [N,K] like nn.Linear.weight (or [K,N] when b_t)
@@ -30,7 +31,10 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, 
         out = torch.empty((M, N), device=a.device, dtype=out_dtype)
         assert not accumulate, "accumulate needs an explicit (zeroed or running) output"
     _chk2d(out, "out")
-    assert out.shape == (M, N)
+    if d_row_block:
+        assert out.shape[1] == N and out.shape[0] >= (M // d_row_block) * d_row_stride
+    else:
+        assert out.shape == (M, N), f"gemm: out shape {tuple(out.shape)} != {(M, N)}"
     g = L.GemmArgs()
     g.A, g.B, g.D = a.data_ptr(), b.data_ptr(), out.data_ptr()
     g.M, g.N, g.K = M, N, K
@@ -50,5 +54,207 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, 
     g.split_k = split_k
     g.alpha = alpha
     g.tile_n = tile_n
+    g.res_row_mod, g.d_row_block, g.d_row_stride = res_row_mod, d_row_block, d_row_stride
     L.call(L._gemm, g, "ymp_gemm")
+    return out
+
+
+# ---------------------------------------------------------------------------------- LayerNorm
+def layernorm_fwd(x, gamma, beta, eps, out=None, in_rows=None, rows=None, stats=True):
+    """y = LN(x) row-wise (fp32 statistics).  Returns (y, mean, rstd)."""
+    _chk2d(x, "x")
+    D = x.shape[1]
+    rows = rows if rows is not None else (in_rows.numel() if in_rows is not None else x.shape[0])
+    if out is None:
+        out = torch.empty((rows, D), device=x.device, dtype=bf16)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32) if stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if stats else None
+    a = L.LayerNormArgs()
+    a.x, a.gamma, a.beta, a.y = x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr()
+    a.mean, a.rstd, a.in_rows = L.ptr(mean), L.ptr(rstd), L.ptr(in_rows)
+    a.rows, a.D, a.ldx, a.ldy, a.eps = rows, D, x.stride(0), out.stride(0), eps
+    L.call(L._ln_fwd, a, "ymp_layernorm_fwd")
+    return out, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, add=None, dgamma=None, dbeta=None, in_rows=None, dx=None):
+    """dx (+ add) and, when dgamma/dbeta (fp32, accumulated) are given, the affine grads."""
+    _chk2d(dy, "dy"); _chk2d(x, "x")
+    rows, D = dy.shape
+    if dx is None:
+        dx = torch.empty((x.shape[0], D), device=x.device, dtype=bf16)
+    assert dx.stride(0) == x.stride(0)
+    a = L.LayerNormBwdArgs()
+    a.dy, a.x, a.gamma, a.mean, a.rstd = dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    a.add, a.dx, a.dgamma, a.dbeta, a.in_rows = L.ptr(add), dx.data_ptr(), L.ptr(dgamma), L.ptr(dbeta), L.ptr(in_rows)
+    a.rows, a.D, a.ldx, a.lddy = rows, D, x.stride(0), dy.stride(0)
+    a.ldadd = add.stride(0) if add is not None else 0
+    L.call(L._ln_bwd, a, "ymp_layernorm_bwd")
+    return dx
+
+
+# ---------------------------------------------------------------------------------- attention
+def seqmap(seq_div=1, outer_stride=0, inner_stride=0, pos_stride=1, n_prefix=0, prefix_base=0,
+           prefix_stride=0, prefix_per_seq=0):
+    m = L.SeqMap()
+    m.seq_div, m.n_prefix, m.prefix_per_seq = seq_div, n_prefix, prefix_per_seq
+    m.outer_stride, m.inner_stride, m.pos_stride = outer_stride, inner_stride, pos_stride
+    m.prefix_base, m.prefix_stride = prefix_base, prefix_stride
+    return m
+
+
+def dense_map(S):
+    return seqmap(seq_div=1, outer_stride=S, pos_stride=1)
+
+
+class TView:
+    """A (tensor, column offset, head stride, seqmap) view: where one of q/k/v/o lives."""
+    __slots__ = ("t", "col", "hs", "m")
+
+    def __init__(self, t, col, hs, m):
+        assert t.dtype == bf16 and t.dim() == 2 and t.stride(1) == 1
+        self.t, self.col, self.hs, self.m = t, col, hs, m
+
+    @property
+    def p(self):
+        return self.t.data_ptr() + 2 * self.col
+
+    @property
+    def ld(self):
+        return self.t.stride(0)
+
+
+def _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale):
+    a = L.AttnArgs()
+    a.q, a.k, a.v, a.o, a.lse = q.p, k.p, v.p, o.p, L.ptr(lse)
+    a.ldq, a.ldk, a.ldv, a.ldo = q.ld, k.ld, v.ld, o.ld
+    a.q_head_stride, a.k_head_stride, a.v_head_stride, a.o_head_stride = q.hs, k.hs, v.hs, o.hs
+    a.map_q, a.map_kv, a.map_o = q.m, k.m, o.m
+    a.n_seq, a.n_heads, a.head_dim, a.s_q, a.s_kv = n_seq, n_heads, head_dim, s_q, s_kv
+    a.causal, a.scale = int(causal), scale
+    return a
+
+
+def attn_fwd(q, k, v, o, *, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, lse=None):
+    """q,k,v,o: TView.  Returns lse [n_seq, n_heads, s_q] fp32."""
+    if lse is None:
+        lse = torch.empty((n_seq, n_heads, s_q), device=q.t.device, dtype=torch.float32)
+    a = _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale)
+    L.call(L._attn_fwd, a, "ymp_attn_fwd")
+    return lse
+
+
+def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, *, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale):
+    """dout,dq,dk,dv: TView (dk and dv share dk's seqmap)."""
+    b = L.AttnBwdArgs()
+    b.fwd = _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale)
+    b.dout, b.dq, b.dk, b.dv = dout.p, dq.p, dk.p, dv.p
+    b.lddo, b.lddq, b.lddk, b.lddv = dout.ld, dq.ld, dk.ld, dv.ld
+    b.do_head_stride, b.dq_head_stride, b.dk_head_stride, b.dv_head_stride = dout.hs, dq.hs, dk.hs, dv.hs
+    b.map_do, b.map_dq, b.map_dkv = dout.m, dq.m, dk.m
+    L.call(L._attn_bwd, b, "ymp_attn_bwd")
+
+
+def _small_args(qkv, C, n_seq, n_heads, S, D, scale):
+    a = L.AttnSmallArgs()
+    base = qkv.data_ptr()
+    a.q, a.k, a.v = base, base + 2 * C, base + 4 * C
+    a.ld, a.head_stride = qkv.stride(0), D
+    a.n_seq, a.n_heads, a.S, a.D, a.scale = n_seq, n_heads, S, D, scale
+    return a
+
+
+def attn_small_fwd(qkv, out, *, n_seq, n_heads, S, D, scale):
+    """qkv [n_seq*S, 3*C] in ViT layout [3, heads, D]; out [n_seq*S, C]."""
+    C = n_heads * D
+    a = _small_args(qkv, C, n_seq, n_heads, S, D, scale)
+    a.o, a.ldo, a.o_head_stride = out.data_ptr(), out.stride(0), D
+    L.call(L._attn_small_fwd, a, "ymp_attn_small_fwd")
+    return out
+
+
+def attn_small_bwd(qkv, dout, dqkv, *, n_seq, n_heads, S, D, scale):
+    C = n_heads * D
+    a = _small_args(qkv, C, n_seq, n_heads, S, D, scale)
+    a.dout, a.ldo, a.o_head_stride = dout.data_ptr(), dout.stride(0), D
+    base = dqkv.data_ptr()
+    a.dq, a.dk, a.dv = base, base + 2 * C, base + 4 * C
+    a.ldd, a.d_head_stride = dqkv.stride(0), D
+    L.call(L._attn_small_bwd, a, "ymp_attn_small_bwd")
+    return dqkv
+
+
+# ---------------------------------------------------------------------------------- misc
+def im2col(video, P, out=None):
+    """video [B,C,T,H,W] bf16 contiguous -> [(b n t), C*P*P]."""
+    assert video.is_contiguous() and video.dtype == bf16
+    B, Cc, T, H, W = video.shape
+    rows = B * (H // P) * (W // P) * T
+    if out is None:
+        out = torch.empty((rows, Cc * P * P), device=video.device, dtype=bf16)
+    a = L.Im2colArgs()
+    a.video, a.out = video.data_ptr(), out.data_ptr()
+    a.B, a.C, a.T, a.H, a.W, a.P, a.ldo = B, Cc, T, H, W, P, out.stride(0)
+    L.call(L._im2col, a, "ymp_im2col")
+    return out
+
+
+def embed_gather(ids, table, pos, out, S, row_offset):
+    """out[(b*S + row_offset + l)] = table[ids[b,l]] + pos[row_offset + l]."""
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    B, Ln = ids.shape
+    a = L.EmbedArgs()
+    a.ids, a.table, a.pos, a.out = ids.data_ptr(), table.data_ptr(), L.ptr(pos), out.data_ptr()
+    a.B, a.L, a.S, a.row_offset = B, Ln, S, row_offset
+    a.hidden, a.vocab, a.ldo = table.shape[1], table.shape[0], out.stride(0)
+    L.call(L._embed, a, "ymp_embed_gather")
+    return out
+
+
+def ce_fwd(logits, labels):
+    """Per-row losses and logsumexp (fp32) of bf16 logits [rows, V]."""
+    _chk2d(logits, "logits")
+    rows, V = logits.shape
+    labels = labels.reshape(-1)
+    assert labels.dtype == torch.int64 and labels.numel() == rows and labels.is_contiguous()
+    loss = torch.empty(rows, device=logits.device, dtype=torch.float32)
+    lse = torch.empty(rows, device=logits.device, dtype=torch.float32)
+    a = L.CeArgs()
+    a.logits, a.labels, a.loss, a.lse = logits.data_ptr(), labels.data_ptr(), loss.data_ptr(), lse.data_ptr()
+    a.rows, a.V, a.ld = rows, V, logits.stride(0)
+    L.call(L._ce_fwd, a, "ymp_ce_fwd")
+    return loss, lse
+
+
+def ce_bwd(logits, labels, lse, grad_rows, dlogits=None):
+    """dlogits = grad_rows[:,None] * (softmax(logits) - onehot); in place when dlogits is None."""
+    rows, V = logits.shape
+    if dlogits is None:
+        dlogits = logits
+    labels = labels.reshape(-1)
+    a = L.CeArgs()
+    a.logits, a.labels, a.lse = logits.data_ptr(), labels.data_ptr(), lse.data_ptr()
+    a.grad_rows, a.dlogits = grad_rows.data_ptr(), dlogits.data_ptr()
+    assert grad_rows.dtype == torch.float32 and grad_rows.is_contiguous()
+    a.rows, a.V, a.ld = rows, V, logits.stride(0)
+    L.call(L._ce_bwd, a, "ymp_ce_bwd")
+    return dlogits
+
+
+def colsum(x, out):
+    """out[c] (fp32, accumulated) += sum_r x[r,c]."""
+    _chk2d(x, "x")
+    assert out.dtype == torch.float32 and out.numel() == x.shape[1]
+    a = L.ColsumArgs()
+    a.in_, a.out, a.R, a.C, a.ld = x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], x.stride(0)
+    L.call(L._colsum, a, "ymp_colsum")
+    return out
+
+
+def group_reduce(x, G, T, out, scale=1.0, broadcast=False):
+    """broadcast=False: out[g] = scale*sum_t x[g,t];  True: out[g,t] = scale*x[g]."""
+    a = L.GroupArgs()
+    a.in_, a.out, a.G, a.T, a.C = x.data_ptr(), out.data_ptr(), G, T, x.shape[1]
+    a.ld_in, a.ld_out, a.broadcast, a.scale = x.stride(0), out.stride(0), int(broadcast), scale
+    L.call(L._group, a, "ymp_group_reduce")
     return out
