@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the mPLUG-Video pre-training hot path (BASELINE.json configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's algorithm on host cores
+
+A step = one pre-training iteration through the public model API: forward (TimeSformer ->
+abstractor -> frozen GPT-3 1.3B -> masked CE), backward (dgrad everywhere, wgrad for the 130 M
+trainable parameters), gradient all-reduce (N>1), global-norm clip + AdamW.  Workload: 32
+samples/GPU of (3, 8, 224, 224) video + 128 text tokens, 128 learnable queries, bf16, random-init
+weights, synthetic data (weak scaling).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "youku-mplug_b200")
+for _p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "video-text samples/sec (pretrain 1.3B, 8f x 224^2)"
+GF_PER_SAMPLE = 2563.8  # algorithmic fwd+bwd GFLOP per sample, SURVEY.md section 8(d) config 2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if mx and x > 0.5 * mx] or sm
+        return dict(sm_mhz=statistics.median(busy) if busy else None, sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def make_text(G, B, L, vocab, seed, bos=1, pad=0):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, vocab, (B, L), generator=g)
+    ids[:, 0] = bos
+    lens = torch.randint(16, L + 1, (B,), generator=g)
+    att = (torch.arange(L)[None, :] < lens[:, None]).long()
+    ids = torch.where(att.bool(), ids, torch.full_like(ids, pad))
+    return ids, att
+
+
+def cpu_baseline(port, torch, T, L, Q, iters=1):
+    """The oracle port (fp32, all host threads) on a bounded sample: `iters` fwd+bwd of ONE sample of
+    the same workload.  Returns (samples/s, description)."""
+    vcfg = dict(port.VCFG_CLIP_B16, num_frames=T)
+    torch.set_num_threads(os.cpu_count())
+    sd = port.init_state_dict(vcfg, port.GCFG_1_3B, Q, seed=0)
+    train = set(port.trainable_keys(sd))
+    psd = {k: v.requires_grad_(k in train) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(1234)
+    video = torch.randn(1, 3, T, 224, 224, generator=g)
+    ids = torch.randint(0, 51200, (1, L), generator=g)
+    att = torch.ones(1, L, dtype=torch.long)
+    times = []
+    for _ in range(iters):
+        t0 = time.time()
+        loss = port.pretrain_forward(video, ids, att, psd, vcfg, port.GCFG_1_3B)
+        loss.backward()
+        times.append(time.time() - t0)
+        for v in psd.values():
+            v.grad = None
+    dt = statistics.median(times)
+    return 1.0 / dt, f"{iters} x (fwd+bwd of 1 sample, T={T}, L={L}, Q={Q}, fp32 torch CPU, {dt:.1f}s each)"
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's algorithm (oracle/port.py, pinned against the unmodified
+    reference) on the box's host cores; the Python reference itself cannot travel to the GPU box."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import port
+    steps = max(1, min(args.steps, 3))
+    val, sample = cpu_baseline(port, torch, args.frames, args.text_len, args.queries, iters=steps)
+    cores = os.cpu_count()
+    line = dict(metric=METRIC, value=val, unit="samples/s", n_gpus=args.gpus, steps=steps, warmup=0,
+                ms_per_step=1000.0 / val, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload="mPLUG-Video GPT-3 1.3B pretrain step, 8f x 224^2, text 128, 128 queries",
+                            per_step="1 sample fwd+bwd (bounded sample of the 32/GPU workload)", note=f"steps capped at {steps}"),
+                cpu_baseline=dict(value=val, unit="samples/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=val, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def run_ymp(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    os.environ["YMP_ALLOW_RANDOM_INIT"] = "1"
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from helpers import make_model_dir, pretrain_config
+    from oracle import port
+    import models.distributed_gpt3 as D
+    import models.modeling_distributed_gpt3 as G
+    from ymp import lib, ops, train
+
+    B, T, L, Q = args.batch, args.frames, args.text_len, args.queries
+    vcfg = dict(port.VCFG_CLIP_B16, num_frames=T)
+    td = make_model_dir(vcfg, port.GCFG_1_3B)
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = D.DistributedGPT3_Pretrain(config=pretrain_config(td, Q), tokenizer=None)
+    model = model.to(torch.bfloat16)
+    n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    eng = train.TrainEngine(model, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.05, clip_grad=3.0)
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    video_h = torch.randn(B, 3, T, 224, 224, generator=g).pin_memory()      # fp32 host frames (the loader's dtype)
+    ids_h, att_h = make_text(G, B, L, 51200, 4321 + rank)
+    ids_h, att_h = ids_h.pin_memory(), att_h.pin_memory()
+    video_d = video_h.to(dev).bfloat16()
+    text_d = G.BatchEncoding(dict(input_ids=ids_h.to(dev), attention_mask=att_h.to(dev)))
+
+    def step_resident():
+        loss, _ = eng(video_d, text_d)
+        eng.backward(loss)
+        eng.step()
+        return loss
+
+    def step_e2e():
+        v = video_h.to(dev, non_blocking=True).bfloat16()
+        t = G.BatchEncoding(dict(input_ids=ids_h.to(dev, non_blocking=True), attention_mask=att_h.to(dev, non_blocking=True)))
+        loss, _ = eng(v, t)
+        eng.backward(loss)
+        eng.step()
+        return loss.item()     # D2H read of the step's result, as the reference loop does (run_pretrain...py:115)
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(steps):
+            last = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), last
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.launch_count()
+    ms, last_loss = timed(step_resident, args.steps)
+    launches = lib.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = float(last_loss.item())
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every launch of one
+    # extra, untimed step on the launching stream; achieved = sum(2MNK) / sum(duration)
+    rec = []
+    orig = ops.gemm
+
+    def gemm_rec(a, b, **kw):
+        M, K = (a.shape[1], a.shape[0]) if kw.get("a_t") else (a.shape[0], a.shape[1])
+        N = b.shape[1] if kw.get("b_t") else b.shape[0]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig(a, b, **kw)
+        e1.record()
+        rec.append((2.0 * M * N * K, e0, e1))
+        return out
+
+    ops.gemm = gemm_rec
+    import ymp.engine as _eng_mod
+    step_resident()
+    torch.cuda.synchronize()
+    ops.gemm = orig
+    gemm_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in rec)
+    gemm_flop = sum(f for f, _, _ in rec)
+    pk = peaks()
+    tf = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    ms_step = ms / args.steps
+    step_tf = GF_PER_SAMPLE * (B if (T, L, Q) == (8, 128, 128) else float("nan")) / ms_step / 1e3
+    roofline = dict(bound="tensor", kernel="gemm_bf16_tcgen05_kernel", achieved=tf, peak=pk["tf_sustained"], unit="TFLOP/s",
+                    frac=tf / pk["tf_sustained"], traffic=None, peak_source=pk["source"] + ", sustained figure",
+                    launches_per_step=len(rec), gemm_ms_per_step=gemm_ms, gemm_share_of_step=gemm_ms / ms_step,
+                    note="events around each GEMM launch of one extra untimed step; algorithmic 2MNK per launch")
+    value = B * world * args.steps / (ms * 1e-3)
+    e2e_val = B * world * args.steps / (ms_e2e * 1e-3)
+    h2d = video_h.numel() * 4 + ids_h.numel() * 8 + att_h.numel() * 8
+    if rank != 0:
+        return
+    line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                data="synthetic", impl="ymp_b200",
+                config=dict(workload="mPLUG-Video GPT-3 1.3B pretrain step (BASELINE configs[1])", batch_per_gpu=B,
+                            global_batch=B * world, frames=T, image=224, text_len=L, queries=Q, parallelism=f"dp{world}",
+                            trainable_params=n_train, step="fwd+bwd+allreduce+clip+AdamW, dropout 0",
+                            l2="per-step working set (~30 GB of activations) >> 126 MB L2; no explicit flush"),
+                clocks=clocks, gpu_launches=int(launches),
+                e2e=dict(value=e2e_val, unit="samples/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
+                         ms_per_step=ms_e2e / args.steps),
+                roofline=roofline,
+                step_model=dict(algorithmic_gflop_per_sample=GF_PER_SAMPLE, achieved_tflops=step_tf,
+                                frac_of_sustained_peak=step_tf / pk["tf_sustained"]),
+                final_loss=final_loss)
+    if world == 1 and not args.no_cpu_baseline:
+        del eng, model
+        torch.cuda.empty_cache()
+        val, sample = cpu_baseline(port, torch, T, L, Q, iters=1)
+        line["cpu_baseline"] = dict(value=val, unit="samples/s", cores=os.cpu_count(), kind="port", sample=sample)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ymp", choices=["ymp", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--frames", type=int, default=8)
+    ap.add_argument("--text-len", type=int, default=128)
+    ap.add_argument("--queries", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+    run_ymp(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

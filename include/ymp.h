@@ -260,6 +260,31 @@ typedef struct ymp_group_args {
 } ymp_group_args;
 int ymp_group_reduce(const ymp_group_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Optimizer step on flat buffers (next row N1 of SURVEY.md section 8f; needed so that the timed
+ * training step skips no work).  Replaces DeepSpeed FusedAdam(adam_w_mode) + global-norm clipping
+ * (reference utils.py:490-526; invoked by model.step(), run_pretrain_distributed_gpt3.py:137).
+ *   ymp_sumsq : *out += sum(g[i]^2)            (fp32, atomics; the caller zeroes *out)
+ *   ymp_adamw : g' = g * grad_scale * min(1, max_grad_norm / (sqrt(*sumsq)*grad_scale + 1e-6))
+ *               AdamW on the fp32 master weights, bf16 model weights refreshed in the same pass.
+ * ------------------------------------------------------------------------------------------ */
+int ymp_sumsq(const float* g, int64_t n, float* out, void* stream);
+
+typedef struct ymp_adamw_args {
+  float* master;        /* fp32 [n] */
+  void* param;          /* bf16 [n] */
+  const float* grad;    /* fp32 [n] */
+  float* m;             /* fp32 [n] */
+  float* v;             /* fp32 [n] */
+  const float* sumsq;   /* device scalar or NULL (no clipping) */
+  int64_t n;
+  int32_t step;         /* 1-based step count for bias correction */
+  float lr, beta1, beta2, eps, weight_decay;
+  float grad_scale;     /* e.g. 1/world_size after a summing all-reduce */
+  float max_grad_norm;  /* <= 0: no clipping */
+} ymp_adamw_args;
+int ymp_adamw(const ymp_adamw_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,37 @@
+import json
+import os
+import tempfile
+
+import torch
+
+
+def make_model_dir(vcfg, gcfg):
+    td = tempfile.mkdtemp(prefix="ymp_model_")
+    with open(os.path.join(td, "config.json"), "w") as f:
+        json.dump(dict(gcfg, hidden_dropout=0.0, attention_dropout=0.0), f)
+    with open(os.path.join(td, "vis.json"), "w") as f:
+        json.dump(dict(vcfg, pretrained_ckpt=None, grad_ckpt=False), f)
+    return td
+
+
+def pretrain_config(td, Q, **extra):
+    cfg = dict(visual_cfg=os.path.join(td, "vis.json"), text_cfg=os.path.join(td, "config.json"), text_decoder=td,
+               megatron_cfg={"world_size": 1, "model_parallel_size": 1, "tensor_model_parallel_size": 1},
+               num_learnable_token=Q, use_contrastive=False, freeze_text_decoder=True)
+    cfg.update(extra)
+    return cfg
+
+
+def build_pretrain(vcfg, gcfg, Q, sd=None, device="cpu", dtype=None, cls_name="DistributedGPT3_Pretrain", **extra):
+    os.environ["YMP_ALLOW_RANDOM_INIT"] = "1"
+    import models.distributed_gpt3 as D
+    td = make_model_dir(vcfg, gcfg)
+    model = getattr(D, cls_name)(config=pretrain_config(td, Q, **extra), tokenizer=None)
+    if sd is not None:
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not unexpected, unexpected
+        assert not [m for m in missing if not m.startswith(("vision_proj", "text_proj", "temp", "cls_head"))], missing
+    model = model.to(device)
+    if dtype is not None:
+        model = model.to(dtype)
+    return model

@@ -38,6 +38,15 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnParams p)
   const int nvec = p.D >> 3;
   for (int row = blockIdx.x * LN_WARPS + warp; row < p.rows; row += gridDim.x * LN_WARPS) {
     const int irow = p.in_rows ? p.in_rows[row] : row;
+    if (irow < 0) {  // padding slot: emit a zero row (the caller overwrites it), no statistics
+      uint4* yz = reinterpret_cast<uint4*>(p.y + (size_t)row * p.ldy);
+      for (int vi = lane; vi < nvec; vi += 32) yz[vi] = make_uint4(0, 0, 0, 0);
+      if (lane == 0) {
+        if (p.mean) p.mean[row] = 0.f;
+        if (p.rstd) p.rstd[row] = 0.f;
+      }
+      continue;
+    }
     const uint4* xr = reinterpret_cast<const uint4*>(p.x + (size_t)irow * p.ldx);
     float v[VPL][8];
     float s = 0.f;
@@ -114,6 +123,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
   const uint4* g4 = reinterpret_cast<const uint4*>(p.gamma);
   for (int row = blockIdx.x * LN_WARPS + warp; row < p.rows; row += gridDim.x * LN_WARPS) {
     const int irow = p.in_rows ? p.in_rows[row] : row;
+    if (irow < 0) continue;  // padding slot of the forward: no input row behind it
     const uint4* xr = reinterpret_cast<const uint4*>(p.x + (size_t)irow * p.ldx);
     const uint4* dyr = reinterpret_cast<const uint4*>(p.dy + (size_t)row * p.lddy);
     const float mu = p.mean[row], rs = p.rstd[row];

@@ -1,0 +1,290 @@
+"""mPLUG-Video task models on the B200 kernels - drop-in for the reference `models/distributed_gpt3.py`.
+
+DistributedGPT3_Pretrain (:31-226) is the hot path: TimeSformer -> AttentionPool abstractor ->
+visual_fc -> frozen GPT-3 causal decoder over [visual prefix | text] -> masked token CE.  Same
+constructor (config dict, tokenizer), same forward(image, text) -> (loss_caption, loss_contrastive),
+same parameter names.  Integer work (targets / loss_mask, :142-159) is done with the same torch
+index ops as the reference and is bit-exact.
+"""
+import json
+from functools import partial
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ymp import functional as YF
+
+from ._params import add_param, linear_default, named_param_list, trunc_normal
+from .distributed_utils import all_gather_cat, concat_all_gather  # noqa: F401
+from .modeling_distributed_gpt3 import DistributedGPT3, GPT3Config
+from .vision_transformer import AttentionPool, LayerNormWithForceFP32, TimeSformer, _convert_pretrained_vit
+
+
+class _Linear(nn.Linear):
+    """nn.Linear whose forward runs on the tcgen05 GEMM (same parameters / state_dict keys)."""
+
+    def forward(self, x):
+        return YF.LinearFn.apply(x, self.weight, self.bias)
+
+
+def _build_visual_encoder(visual_cfg, num_frames):
+    return TimeSformer(
+        img_size=visual_cfg['img_size'], num_frames=num_frames, patch_size=visual_cfg['patch_size'],
+        embed_dim=visual_cfg['embed_dim'], depth=visual_cfg['depth'], num_heads=visual_cfg['num_heads'],
+        mlp_ratio=visual_cfg['mlp_ratio'], qkv_bias=True, norm_layer=partial(LayerNormWithForceFP32, eps=1e-6),
+        init_std=0.015, grad_ckpt=visual_cfg.get('grad_ckpt', True), drop_path_rate=visual_cfg.get('drop_path', False),
+        stop_grad_conv1=visual_cfg.get('stop_grad_conv1', False),
+        use_shared_rel_pos_bias=visual_cfg.get('use_shared_rel_pos_bias', False),
+        use_abs_pos_emb=visual_cfg.get('use_abs_pos_emb', True),
+        init_values=visual_cfg.get('layer_scale_init_value', 0), postnorm=visual_cfg.get('postnorm', False),
+        clip_model=visual_cfg.get('clip_model', False))
+
+
+def _load_pretrained_vit(encoder, visual_cfg):
+    ckpt = visual_cfg.get("pretrained_ckpt", None)
+    if ckpt is None:
+        return
+    if ckpt.startswith("clip"):
+        path = "/".join(ckpt.split("/")[1:])
+        weights = _convert_pretrained_vit(torch.load(path, map_location='cpu'))
+        msg = encoder.load_state_dict(weights, strict=False)
+        print("Initialize Vision Encoder from CKPT {}".format(path))
+        print(msg)
+    else:
+        raise NotImplementedError(f"pretrained_ckpt={ckpt!r}: timm hub checkpoints need network access")
+
+
+class _PrefixModelBase(nn.Module):
+    """Shared construction: visual encoder + frozen decoder + learnable queries + abstractor + visual_fc
+    (reference :31-116 / :431-520 / :662-750)."""
+
+    def _build(self, config, tokenizer, num_frames):
+        self.tokenizer = tokenizer
+        with open(config['visual_cfg'], 'r') as f:
+            visual_cfg = json.load(f)
+        text_cfg = GPT3Config.from_json_file(config['text_cfg'])
+        self.visual_cfg = visual_cfg
+        self.visual_encoder = _build_visual_encoder(visual_cfg, num_frames if num_frames is not None else visual_cfg['num_frames'])
+        _load_pretrained_vit(self.visual_encoder, visual_cfg)
+        rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        self.text_decoder = DistributedGPT3(
+            model_dir=config['text_decoder'], rank=rank, path_load_tag='model', megatron_cfg=config['megatron_cfg'],
+            checkpoint_model_parallel_size=1 if text_cfg.num_hidden_layers < 40 else 8)
+        if config.get('freeze_vit', False):
+            for name, param in self.visual_encoder.named_parameters():
+                if not any(x in name for x in ['time', 'temporal']):
+                    param.requires_grad = False
+        if config.get('freeze_text_decoder', True):
+            for param in self.text_decoder.parameters():
+                param.requires_grad = False
+        self.vision_width = visual_cfg['embed_dim']
+        self.text_width = self.text_decoder.config.hidden_size
+        self.learnable_token = True
+        self.num_learnable_token = config.get('num_learnable_token', 256)
+        self.learnable_queries = nn.Parameter(trunc_normal((1, self.num_learnable_token, self.vision_width), 0.015))
+        self.attn_pool = AttentionPool(self.vision_width, num_heads=visual_cfg['num_heads'],
+                                       mlp_ratio=visual_cfg['mlp_ratio'],
+                                       norm_layer=partial(LayerNormWithForceFP32, eps=1e-6))
+        self.visual_fc = _Linear(self.vision_width, self.text_width)
+        with torch.no_grad():
+            self.visual_fc.weight.copy_(trunc_normal((self.text_width, self.vision_width), 0.015))
+        if visual_cfg.get('connect_ln', False):
+            raise NotImplementedError("connect_ln (visual_norm) is not wired into the fused path yet")
+        self.visual_norm = nn.Identity()
+        self.prompt = config.get('prompt', "")
+
+    def _word_embedding(self):
+        return self.text_decoder.dist_model.language_model.embedding.word_embeddings
+
+    def visual_prefix(self, image):
+        """image -> (image_embeds [B,1+TN,D], image_query [B,Q,D], query_features [B,Q,H])."""
+        pooled, image_embeds = self.visual_encoder(image)
+        image_query = self.attn_pool(None, image_embeds, queries_param=self.learnable_queries)
+        query_features = self.visual_norm(self.visual_fc(image_query))
+        return pooled, image_embeds, image_query, query_features
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'visual_encoder.pos_embed', 'visual_encoder.cls_token', 'visual_encoder.temporal_embed'}
+
+
+def build_targets(input_ids, text_loss_atts, num_query):
+    """targets = [100]*Q ++ ids[:,1:] ++ ids[:,1] ; loss_mask = [0]*Q ++ mask[:,1:]  (:142-159)."""
+    B = input_ids.shape[0]
+    targets = input_ids[:, 1:].clone()
+    targets = torch.cat([targets, targets[:, 0:1]], dim=1)  # last column is not used
+    empty_targets = torch.ones((B, num_query), dtype=torch.long, device=input_ids.device).fill_(100)
+    targets = torch.cat([empty_targets, targets], dim=1)
+    query_atts = torch.ones((B, num_query), dtype=torch.long, device=input_ids.device)
+    loss_mask = torch.cat([1 - query_atts, text_loss_atts], dim=1)
+    return targets, loss_mask
+
+
+class DistributedGPT3_Pretrain(_PrefixModelBase):
+    def __init__(self, config=None, tokenizer=None):
+        super().__init__()
+        self._build(config, tokenizer, None)
+        self.use_contrastive = config.get('use_contrastive', False)
+        if self.use_contrastive:
+            embed_dim = config.get('contrastive_embed_dim', 256)
+            self.vision_proj = _Linear(self.vision_width, embed_dim)
+            self.text_proj = _Linear(self.text_width, embed_dim)
+            self.temp = nn.Parameter(torch.ones([]) * config.get('temp', 0.07))
+        self.last_losses = None
+
+    def _fused_params(self):
+        keys, params = named_param_list(self)
+        drop = ("vision_proj.", "text_proj.", "temp")
+        kp = [(k, p) for k, p in zip(keys, params) if not k.startswith(drop)]
+        return [k for k, _ in kp], [p for _, p in kp]
+
+    def forward(self, image, text):
+        if self.prompt != "":
+            raise NotImplementedError("a non-empty prompt crashes in the reference too (prompt_length is "
+                                      "never set, models/distributed_gpt3.py:118-120,146-148)")
+        text_loss_atts = text.attention_mask[:, 1:]
+        targets, loss_mask = build_targets(text.input_ids, text_loss_atts, self.num_learnable_token)
+        if not self.use_contrastive:
+            keys, params = self._fused_params()
+            loss_caption, losses = YF.PretrainFn.apply(image, text.input_ids, targets, loss_mask,
+                                                       self.visual_encoder.vcfg, self.text_decoder.config.engine_cfg(),
+                                                       keys, *params)
+            self.last_losses = losses
+            return loss_caption, torch.tensor(0.0, device=image.device)
+
+        # ---- contrastive variant (:168-217): component path so that image_query is exposed
+        _, image_embeds, image_query, query_features = self.visual_prefix(image)
+        input_embeds = torch.cat([query_features, self._word_embedding()(text.input_ids).to(query_features.dtype)], dim=1)
+        outputs = self.text_decoder(input_embeds=input_embeds, loss_mask=loss_mask, labels=targets)
+        loss_caption = outputs.loss
+        targets_dep = torch.cat([text.input_ids[:, 1:], text.input_ids[:, 1:2]], dim=1)
+        outputs_text = self.text_decoder(tokens=text.input_ids, loss_mask=text.attention_mask[:, 1:].clone(),
+                                         labels=targets_dep)
+        vision_feats = F.normalize(self.vision_proj(image_query).float(), dim=-1)
+        pooled = outputs_text.last_hidden_state
+        pooled = pooled[torch.arange(pooled.shape[0]), text.attention_mask.sum(dim=-1) - 1]
+        text_feat = F.normalize(self.text_proj(pooled).float(), dim=-1)
+        vision_feats_all = all_gather_cat(vision_feats)          # [B*W, Q, E]
+        text_feat_all = all_gather_cat(text_feat)                # [B*W, E]
+        # sim_q2t[b, j, q] = <vision_feats[b,q], text_all[j]> ; max over queries (:186-202)
+        sim_i2t = torch.einsum('bqe,je->bjq', vision_feats, text_feat_all).max(-1)[0] / self.temp
+        sim_t2i = torch.einsum('be,jqe->bjq', text_feat, vision_feats_all).max(-1)[0] / self.temp
+        rank = torch.distributed.get_rank()
+        bs = image.size(0)
+        tgt = torch.arange(rank * bs, rank * bs + bs, device=image.device)
+        loss_contrastive = (F.cross_entropy(sim_i2t, tgt, label_smoothing=0.1)
+                            + F.cross_entropy(sim_t2i, tgt, label_smoothing=0.1)) / 2
+        return loss_caption, loss_contrastive
+
+
+class DistributedGPT3_Caption(_PrefixModelBase):
+    """Caption fine-tuning forward (:751-788); generate() (beam search over a KV cache) is the
+    'next' row N2 of SURVEY.md section 8f and is not built yet."""
+
+    def __init__(self, config=None, tokenizer=None):
+        super().__init__()
+        self._build(config, tokenizer, config.get('num_frames', None))
+
+    def forward(self, image, text=None):
+        _, _, _, query_features = self.visual_prefix(image)
+        Q = query_features.shape[1]
+        text_loss_atts = text.attention_mask[:, 1:].clone()
+        if self.prompt != "":
+            for i, ln in enumerate(text.prompt_lengths.tolist()):
+                text_loss_atts[i, :ln] = 0
+        targets, loss_mask = build_targets(text.input_ids, text_loss_atts, Q)
+        input_embeds = torch.cat([query_features, self._word_embedding()(text.input_ids).to(query_features.dtype)], dim=1)
+        return self.text_decoder(input_embeds=input_embeds, loss_mask=loss_mask, labels=targets).loss
+
+    def generate(self, image, text):
+        raise NotImplementedError("generation (KV-cache beam search) is SURVEY.md section 8f row N2")
+
+
+class DistributedGPT3_Cls(_PrefixModelBase):
+    """Video category prediction (:431-657).  Training: caption-style loss on [prompt+label] (+
+    optional cls_head); eval: every class prompt scored by softmax(-sum(losses * mask))."""
+
+    def __init__(self, config=None, tokenizer=None):
+        super().__init__()
+        self._build(config, tokenizer, config.get('num_frames', None))
+        self.use_cls = config.get('use_cls', False)
+        self.num_classes = config.get('num_classes', 45)
+        if self.use_cls:
+            self.cls_head = nn.Sequential(_Linear(self.text_width, self.text_width), nn.ReLU(),
+                                          _Linear(self.text_width, self.num_classes))
+
+    def _caption_pass(self, query_features, text):
+        Q = query_features.shape[1]
+        text_loss_atts = text.attention_mask[:, 1:].clone()
+        if getattr(text, "prompt_lengths", None) is not None:
+            for i, ln in enumerate(text.prompt_lengths.tolist()):
+                text_loss_atts[i, :ln] = 0
+        targets, loss_mask = build_targets(text.input_ids, text_loss_atts, Q)
+        input_embeds = torch.cat([query_features, self._word_embedding()(text.input_ids).to(query_features.dtype)], dim=1)
+        return self.text_decoder(input_embeds=input_embeds, loss_mask=loss_mask, labels=targets), loss_mask
+
+    def forward(self, image, text=None, prompt_text=None, labels=None, train=True):
+        _, _, _, query_features = self.visual_prefix(image)
+        B, Q, _ = query_features.shape
+        if train:
+            out, _ = self._caption_pass(query_features, prompt_text if prompt_text is not None else text)
+            loss_cls = torch.tensor(0.0, device=image.device)
+            if self.use_cls:
+                out_t, _ = self._caption_pass(query_features, text)
+                last = out_t.last_hidden_state[torch.arange(B), Q + text.attention_mask.sum(-1) - 1]
+                loss_cls = F.cross_entropy(self.cls_head(last).float(), labels)
+            return out.loss, loss_cls
+        # eval: prompt_text holds num_cls prompts per video, flattened [B*num_cls, L]
+        num_cls = prompt_text.input_ids.shape[0] // B
+        qf = query_features.unsqueeze(1).expand(B, num_cls, Q, -1).reshape(B * num_cls, Q, -1)
+        out, loss_mask = self._caption_pass(qf, prompt_text)
+        scores = -(out.losses * loss_mask.float()).sum(-1).view(B, num_cls)
+        generation_logits = scores.softmax(-1)
+        cls_logits = None
+        if self.use_cls and text is not None:
+            out_t, _ = self._caption_pass(query_features, text)
+            last = out_t.last_hidden_state[torch.arange(B), Q + text.attention_mask.sum(-1) - 1]
+            cls_logits = self.cls_head(last).float()
+        return generation_logits, cls_logits
+
+
+class DistributedGPT3_Retrieval(_PrefixModelBase):
+    """Contrastive video-text retrieval (:817-985): CLS-pooled ViT feature vs last-valid-token GPT
+    hidden state, all-gathered across ranks (C2/C3 of SURVEY.md section 2.3)."""
+
+    def __init__(self, config=None, tokenizer=None):
+        super().__init__()
+        self._build(config, tokenizer, config.get('num_frames', None))
+        embed_dim = config.get('embed_dim', 256)
+        self.vision_proj = _Linear(self.vision_width, embed_dim)
+        self.text_proj = _Linear(self.text_width, embed_dim)
+        self.temp = nn.Parameter(torch.ones([]) * config.get('temp', 0.07))
+
+    def extract_vision_feature(self, image):
+        pooled, _ = self.visual_encoder(image)
+        return F.normalize(self.vision_proj(pooled).float(), dim=-1)
+
+    def extract_text_feature(self, text):
+        targets = torch.cat([text.input_ids[:, 1:], text.input_ids[:, 1:2]], dim=1)
+        out = self.text_decoder(tokens=text.input_ids, loss_mask=text.attention_mask[:, 1:].clone(), labels=targets)
+        hid = out.last_hidden_state
+        pooled = hid[torch.arange(hid.shape[0]), text.attention_mask.sum(dim=-1) - 1]
+        return F.normalize(self.text_proj(pooled).float(), dim=-1)
+
+    def forward(self, image, text, idx):
+        image_feat = self.extract_vision_feature(image)
+        text_feat = self.extract_text_feature(text)
+        if torch.distributed.is_initialized():
+            image_feat_all = all_gather_cat(image_feat)
+            text_feat_all = all_gather_cat(text_feat)
+            idx_all = concat_all_gather(idx.view(-1))
+        else:
+            image_feat_all, text_feat_all, idx_all = image_feat, text_feat, idx.view(-1)
+        sim_i2t = image_feat @ text_feat_all.t() / self.temp
+        sim_t2i = text_feat @ image_feat_all.t() / self.temp
+        pos = torch.eq(idx.view(-1, 1), idx_all.view(1, -1)).float()
+        sim_targets = pos / pos.sum(1, keepdim=True)
+        loss_i2t = -torch.sum(F.log_softmax(sim_i2t, dim=1) * sim_targets, dim=1).mean()
+        loss_t2i = -torch.sum(F.log_softmax(sim_t2i, dim=1) * sim_targets, dim=1).mean()
+        return (loss_i2t + loss_t2i) / 2

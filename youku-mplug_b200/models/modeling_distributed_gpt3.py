@@ -1,0 +1,347 @@
+"""GPT-3 (1.3B / 2.7B Megatron-style) decoder of mPLUG-Video on the B200 kernels.
+
+Mirrors the reference module `models/modeling_distributed_gpt3.py`: GPT3Config (:459-547),
+BatchEncoding (:139-178), DistributedGPT3Tokenizer (:180-319), DistributedGPT3 (:1522-1618).
+No megatron_util: tensor-model-parallel size must be 1 - the path is pure data
+parallel.  Parameter names equal the reference's (`dist_model.language_model....`), including the
+per-head [q|k|v] row grouping of query_key_value, so `model/mp_rank_00_model_states.pt` loads as is.
+"""
+import json
+import math
+import os
+import os.path as osp
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ymp import functional as YF
+
+from ._params import EmbedHolder, Holder, add_param, named_param_list
+
+
+class AttrDict(dict):
+    """addict.Dict-like result container (attribute access; missing keys -> None)."""
+    __getattr__ = dict.get
+    __setattr__ = dict.__setitem__
+
+
+class GPT3Config:
+    model_type = 'gpt3'
+
+    def __init__(self, vocab_size=25600, hidden_size=768, ffn_hidden_size=None, num_hidden_layers=12,
+                 num_attention_heads=12, intermediate_size=3072, hidden_act='gelu', hidden_dropout_prob=0.1,
+                 attention_probs_dropout_prob=0.1, max_position_embeddings=2048, type_vocab_size=2,
+                 layernorm_epsilon=1e-12, bias_gelu_fusion=True, fp32_residual_connection=False,
+                 sequence_parallel=False, fp16=False, bf16=False, apply_query_key_layer_scaling=True,
+                 attention_softmax_in_fp32=False, kv_channels=None, masked_softmax_fusion=True,
+                 attention_dropout=0.1, bias_dropout_fusion=True,
+                 apply_residual_connection_post_layernorm=False, hidden_dropout=0.1, init_method_std=0.02,
+                 eod_id=7, tokens_to_generate=100, top_k=0, top_p=0.9, **kwargs):
+        self.vocab_size = vocab_size
+        self.hidden_size = hidden_size
+        self.ffn_hidden_size = 4 * hidden_size if ffn_hidden_size is None else ffn_hidden_size
+        self.num_hidden_layers = num_hidden_layers
+        self.num_attention_heads = num_attention_heads
+        self.intermediate_size = intermediate_size
+        self.hidden_act = hidden_act
+        self.hidden_dropout_prob = hidden_dropout_prob
+        self.attention_probs_dropout_prob = attention_probs_dropout_prob
+        self.max_position_embeddings = max_position_embeddings
+        self.type_vocab_size = type_vocab_size
+        self.layernorm_epsilon = layernorm_epsilon
+        self.layer_norm_eps = layernorm_epsilon
+        self.fp16, self.bf16 = fp16, bf16
+        assert not (fp16 and bf16)
+        assert hidden_size % num_attention_heads == 0
+        self.kv_channels = hidden_size // num_attention_heads if kv_channels is None else kv_channels
+        self.attention_dropout = attention_dropout
+        self.hidden_dropout = hidden_dropout
+        self.init_method_std = init_method_std
+        self.apply_query_key_layer_scaling = apply_query_key_layer_scaling
+        self.apply_residual_connection_post_layernorm = apply_residual_connection_post_layernorm
+        self.sequence_parallel = sequence_parallel
+        self.eod_id, self.tokens_to_generate, self.top_k, self.top_p = eod_id, tokens_to_generate, top_k, top_p
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+        if apply_residual_connection_post_layernorm or sequence_parallel or fp32_residual_connection:
+            raise NotImplementedError("unsupported GPT3Config option for the B200 path")
+
+    @classmethod
+    def from_json_file(cls, path):
+        with open(path, 'r') as f:
+            return cls(**json.load(f))
+
+    @classmethod
+    def from_pretrained(cls, model_dir):
+        return cls.from_json_file(osp.join(model_dir, 'config.json'))
+
+    def to_dict(self):
+        return dict(self.__dict__)
+
+    def engine_cfg(self):
+        return dict(vocab_size=self.vocab_size, hidden_size=self.hidden_size, ffn_hidden_size=self.ffn_hidden_size,
+                    num_hidden_layers=self.num_hidden_layers, num_attention_heads=self.num_attention_heads,
+                    max_position_embeddings=self.max_position_embeddings, layernorm_epsilon=self.layernorm_epsilon)
+
+
+# ------------------------------------------------------------------------------------------ tokenizer
+class JiebaBPETokenizer:
+    """BPE tokenizer (tokenizers json) with jieba pre-segmentation, <sep> as BOS and
+    <|endoftext|> as EOS/PAD (reference :42-137)."""
+
+    def __init__(self, tokenizer_json_file):
+        from tokenizers import Tokenizer
+        self.tokenizer = Tokenizer.from_file(tokenizer_json_file)
+        try:
+            import jieba
+            self._cut = lambda s: list(jieba.cut(s))
+        except ImportError:  # not in this image: whitespace segmentation keeps the API usable
+            self._cut = lambda s: s.split()
+        self.eod_id = self.eos_id = self.pad_id = self.tokenizer.token_to_id('<|endoftext|>')
+        self.bos_id = self.sep_token = self.tokenizer.token_to_id('<sep>')
+
+    @property
+    def vocab_size(self):
+        return self.tokenizer.get_vocab_size(with_added_tokens=True)
+
+    @property
+    def vocab(self):
+        return self.tokenizer.get_vocab(with_added_tokens=True)
+
+    def _ids(self, text, is_code):
+        if is_code:
+            return self.tokenizer.encode(text, is_pretokenized=False, add_special_tokens=True).ids
+        return self.tokenizer.encode(self._cut(text), is_pretokenized=True, add_special_tokens=True).ids
+
+    def tokenize(self, text, is_code=False, add_special_tokens=True):
+        ids = self._ids(text, is_code)
+        return [self.bos_id] + ids + [self.eos_id] if add_special_tokens else ids
+
+    def tokenize_prompt(self, prompt_text, text, is_code=False, add_special_tokens=True):
+        return [[self.bos_id], self._ids(prompt_text, is_code), self._ids(text, is_code), [self.eos_id]]
+
+    def detokenize(self, token_ids):
+        return self.tokenizer.decode(token_ids, skip_special_tokens=True)
+
+    eod = property(lambda self: self.eod_id)
+    eos = property(lambda self: self.eos_id)
+    bos = property(lambda self: self.bos_id)
+    pad = property(lambda self: self.pad_id)
+
+
+class BatchEncoding:
+    def __init__(self, data):
+        self.data = data
+
+    def __getitem__(self, item):
+        if isinstance(item, str):
+            return self.data[item]
+        raise KeyError("integer indexing is not available for this tokenizer")
+
+    def __getattr__(self, item):
+        try:
+            return self.__dict__["data"][item]
+        except KeyError:
+            raise AttributeError(item)
+
+    def __getstate__(self):
+        return {"data": self.data}
+
+    def __setstate__(self, state):
+        self.__dict__["data"] = state["data"]
+
+    def __repr__(self):
+        return str(self.data)
+
+    def keys(self):
+        return self.data.keys()
+
+    def values(self):
+        return self.data.values()
+
+    def items(self):
+        return self.data.items()
+
+    def to(self, device):
+        self.data = {k: v.to(device=device) for k, v in self.data.items()}
+        return self
+
+
+class DistributedGPT3Tokenizer:
+    def __init__(self, model_dir, sequence_length=128):
+        self.tokenizer = JiebaBPETokenizer(osp.join(model_dir, 'tokenizer.json'))
+        self.max_length = sequence_length
+
+    def decode(self, tokens, **kwargs):
+        if isinstance(tokens, torch.Tensor):
+            tokens = tokens.detach().cpu().tolist()
+        return self.tokenizer.detokenize(tokens)
+
+    def _fit(self, ids, length):
+        """pad with the pad id / cut to `length`; returns (array, number of real tokens)."""
+        ids = list(ids)[:length]
+        n = len(ids)
+        return np.asarray(ids + [self.tokenizer.pad] * (length - n), dtype=np.int64), n
+
+    def _fit_prompt(self, parts, length):
+        bos, prompt, text, eos = parts
+        if len(bos) + len(prompt) + len(text) + len(eos) > length:
+            room = length - len(text) - 2
+            if room >= 0 and len(prompt) >= room:   # shorten the prompt first
+                prompt = prompt[:room]
+            else:                                    # otherwise cut the target
+                text = text[:length - 2 - len(prompt)]
+        arr, n = self._fit(bos + prompt + text + eos, length)
+        return arr, len(prompt), n
+
+    def __call__(self, data, padding='longest', truncation=True, max_length=None, return_tensors='pt',
+                 add_special_tokens=True, **kwargs):
+        max_length = self.max_length if max_length is None else max_length
+        pairs = not isinstance(data[0], str)
+        if pairs:
+            toks = [self.tokenizer.tokenize_prompt(p, t) for p, t in data]
+            longest = max(sum(len(x) for x in t) for t in toks)
+            # the reference pads pair inputs to max_length whenever truncation is on (:289-296)
+            length = max_length if (truncation or padding == 'max_length') else longest
+        else:
+            # NB: the reference passes add_special_tokens positionally into `is_code` (:240);
+            # keep the observable behaviour: text path, specials always added.
+            toks = [self.tokenizer.tokenize(t) for t in data]
+            longest = max(len(t) for t in toks)
+            if padding == 'max_length':
+                length = max_length
+            else:
+                length = min(longest, max_length) if truncation else longest
+        ids, mask, plen = [], [], []
+        for t in toks:
+            if pairs:
+                arr, pl, n = self._fit_prompt(t, length)
+                plen.append(pl)
+            else:
+                arr, n = self._fit(t, length)
+            m = np.zeros(length, dtype=np.int64)
+            m[:n] = 1
+            ids.append(arr)
+            mask.append(m)
+        out = dict(input_ids=np.stack(ids), attention_mask=np.stack(mask))
+        if pairs:
+            out["prompt_lengths"] = np.asarray(plen, dtype=np.int64)
+        if return_tensors == 'pt':
+            out = {k: torch.from_numpy(v).long() for k, v in out.items()}
+        return BatchEncoding(out)
+
+
+# ------------------------------------------------------------------------------------------ model
+def _ckpt_name(mp_rank, load_dir, tag):
+    return osp.join(load_dir, str(tag), 'mp_rank_{:02d}_model_states.pt'.format(mp_rank))
+
+
+def pre_load(mp_rank, load_dir, tag=''):
+    """{text_decoder}/model/mp_rank_00_model_states.pt['module'] (reference :431-441)."""
+    ckpt = torch.load(_ckpt_name(mp_rank, load_dir, tag), map_location='cpu', weights_only=False)
+    return ckpt['module']
+
+
+def _check_tp1(megatron_cfg):
+    if not megatron_cfg:
+        return
+    for k in ('tensor_model_parallel_size', 'model_parallel_size'):
+        v = megatron_cfg.get(k, 1)
+        if v not in (None, 1):
+            raise ValueError(f"megatron_cfg.{k}={v}: the B200 path is pure data parallel; set it to 1 "
+                             "(as the reference's own scripts/*.sh:13-14 and retrieval yaml do)")
+
+
+class GPT3Model(nn.Module):
+    """Parameter container with the reference's names: language_model.{embedding,encoder}...."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        H, F4, V, Lyr = config.hidden_size, config.ffn_hidden_size, config.vocab_size, config.num_hidden_layers
+        std = config.init_method_std
+        std_out = std / math.sqrt(2.0 * Lyr)
+
+        def n(*shape, s=std):
+            return torch.empty(*shape).normal_(0.0, s)
+
+        lm = Holder()
+        self.add_module("language_model", lm)
+        lm.add_module("embedding", Holder())
+        lm.embedding.add_module("word_embeddings", EmbedHolder())
+        add_param(lm, "embedding.word_embeddings.weight", n(V, H))
+        add_param(lm, "embedding.position_embeddings.weight", n(config.max_position_embeddings, H))
+        for i in range(Lyr):
+            b = f"encoder.layers.{i}."
+            for nm in ("input_layernorm", "post_attention_layernorm"):
+                add_param(lm, b + nm + ".weight", torch.ones(H))
+                add_param(lm, b + nm + ".bias", torch.zeros(H))
+            add_param(lm, b + "self_attention.query_key_value.weight", n(3 * H, H))
+            add_param(lm, b + "self_attention.query_key_value.bias", torch.zeros(3 * H))
+            add_param(lm, b + "self_attention.dense.weight", n(H, H, s=std_out))
+            add_param(lm, b + "self_attention.dense.bias", torch.zeros(H))
+            add_param(lm, b + "mlp.dense_h_to_4h.weight", n(F4, H))
+            add_param(lm, b + "mlp.dense_h_to_4h.bias", torch.zeros(F4))
+            add_param(lm, b + "mlp.dense_4h_to_h.weight", n(H, F4, s=std_out))
+            add_param(lm, b + "mlp.dense_4h_to_h.bias", torch.zeros(H))
+        add_param(lm, "encoder.final_layernorm.weight", torch.ones(H))
+        add_param(lm, "encoder.final_layernorm.bias", torch.zeros(H))
+
+    def word_embeddings_weight(self):
+        return self.language_model.embedding.word_embeddings.weight
+
+
+class DistributedGPT3(nn.Module):
+    def __init__(self, model_dir, rank=0, path_load_tag='model', *args, **kwargs):
+        super().__init__()
+        _check_tp1(kwargs.pop('megatron_cfg', None))
+        self.config = GPT3Config.from_pretrained(model_dir)
+        self.dist_model = GPT3Model(self.config)
+        kwargs.pop('checkpoint_model_parallel_size', None)
+        if kwargs.pop('load_state_dict', True):
+            path = _ckpt_name(0, model_dir, path_load_tag)
+            if osp.exists(path):
+                self.dist_model.load_state_dict(pre_load(0, model_dir, tag=path_load_tag))
+            elif os.environ.get("YMP_ALLOW_RANDOM_INIT", "0") != "1":
+                raise FileNotFoundError(f"{path} not found (set YMP_ALLOW_RANDOM_INIT=1 to run with "
+                                        "random-initialised decoder weights, e.g. for benchmarks)")
+        self.inference_params = None
+        self._keys_prefix = "text_decoder.dist_model."
+
+    def train(self, mode=True):
+        if mode:
+            self.inference_params = None
+        return super().train(mode)
+
+    def _param_list(self):
+        return named_param_list(self.dist_model, self._keys_prefix)
+
+    def forward(self, tokens=None, input_embeds=None, query_embeds=None, attention_mask=None,
+                position_ids=None, labels=None, prompt_length=None, loss_mask=None, is_pair=(False,)):
+        """Same contract as the reference (:1578-1618): returns Dict(logits, loss, losses,
+        last_hidden_state).  A plain causal mask over the whole sequence and position ids
+        arange(S) are always used (the reference never forwards `attention_mask` into the layers
+        on this path, :1329-1332), so explicit attention_mask/position_ids are accepted only in
+        that default form."""
+        if tokens is not None and input_embeds is not None:
+            raise ValueError("You cannot specify both decoder_input_ids and decoder_inputs_embeds at the same time")
+        if tokens is None and input_embeds is None:
+            raise ValueError("You have to specify either decoder_input_ids or decoder_inputs_embeds")
+        if position_ids is not None:
+            raise NotImplementedError("custom position_ids are not supported on the B200 path")
+        if tokens is not None:
+            input_embeds = self.dist_model.language_model.embedding.word_embeddings(tokens)
+        if query_embeds is not None:
+            input_embeds = torch.cat([query_embeds.to(input_embeds.dtype), input_embeds], dim=1)
+        if labels is None:
+            raise NotImplementedError("KV-cache decoding is a later row (SURVEY.md section 8f N2); pass labels")
+        keys, params = self._param_list()
+        logits, losses, hidden = YF.GptFn.apply(input_embeds, labels.contiguous(), self.config.engine_cfg(), True,
+                                                keys, *params)
+        if loss_mask is None:
+            loss_mask = attention_mask[:, 1:].contiguous()
+        losses = losses[:, :-1].contiguous().float()
+        lm = loss_mask.reshape(-1).float()
+        loss = torch.sum(losses.reshape(-1) * lm) / lm.sum()
+        return AttrDict(logits=logits, loss=loss, losses=losses, last_hidden_state=hidden)

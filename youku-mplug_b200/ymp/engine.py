@@ -1,0 +1,466 @@
+"""Hand-scheduled forward/backward of the mPLUG-Video pre-training hot path on the C-ABI kernels.
+
+No autograd inside: every stage saves exactly what its backward needs, weight gradients are
+accumulated in fp32 (split-K atomics in the GEMM epilogue), and the frozen GPT-3 decoder runs
+dgrad only (no wgrad GEMMs, no saved GEMM inputs).
+
+Weights are addressed by the reference's own state_dict keys.  `W` maps key -> bf16 CUDA tensor,
+`G` maps key -> fp32 gradient accumulator for the *trainable* keys (absent key == frozen).
+
+Row layouts (all activations are 2-D [rows, features] bf16):
+  ViT tokens : row = (b*N + n)*T + t  (patch-major, as inside the reference Block,
+               models/vision_transformer.py:247-274), followed by B cls rows  -> RB = B*N*T + B rows
+  decoder    : row = b*S + s  (the reference uses [s,b,h]; per-(b,head) arithmetic is identical)
+"""
+import math
+
+import torch
+
+from . import ops
+from .ops import ACT_GELU_ERF, ACT_GELU_TANH, TView, bf16
+
+GPT = "text_decoder.dist_model.language_model."
+VE = "visual_encoder."
+AP = "attn_pool."
+
+
+def _zeros_f32(n, dev):
+    return torch.zeros(n, device=dev, dtype=torch.float32)
+
+
+class Ctx(dict):
+    """Saved activations of one forward (attribute access for brevity)."""
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+# ------------------------------------------------------------------------------------------
+# linear helpers
+# ------------------------------------------------------------------------------------------
+def linear_wgrad(dy, x, wkey, bkey, G):
+    """G[wkey] += dy^T x ; G[bkey] += colsum(dy)   (both optional / skipped when frozen)."""
+    if wkey in G:
+        g = G[wkey]
+        ops.gemm(dy, x, a_t=True, b_t=True, out=g.view(dy.shape[1], x.shape[1]), accumulate=True)
+    if bkey is not None and bkey in G:
+        ops.colsum(dy, G[bkey])
+
+
+def linear_dgrad(dy, w, **kw):
+    """dx = dy @ w   (w is the forward [out, in] weight, consumed MN-major: no transpose copy)."""
+    return ops.gemm(dy, w, b_t=True, **kw)
+
+
+# ------------------------------------------------------------------------------------------
+# TimeSformer encoder
+# ------------------------------------------------------------------------------------------
+class VitDims:
+    def __init__(self, vcfg, B):
+        self.P, self.D, self.depth = vcfg["patch_size"], vcfg["embed_dim"], vcfg["depth"]
+        self.heads, self.T = vcfg["num_heads"], vcfg["num_frames"]
+        self.hd = self.D // self.heads
+        self.N = (vcfg["img_size"] // self.P) ** 2
+        self.hid = int(self.D * vcfg["mlp_ratio"])
+        self.B = B
+        self.R = B * self.N * self.T
+        self.RB = self.R + B
+        self.eps = 1e-6
+        self.scale = self.hd ** -0.5
+
+
+_gather_cache = {}
+
+
+def _final_gather_rows(d, dev):
+    """Output row (b, 0)=cls, (b, 1 + t*N + n) <- internal token row (b*N + n)*T + t
+    (models/vision_transformer.py:582-585 emits (t n) order after the cls token)."""
+    key = (d.B, d.N, d.T, str(dev))
+    if key not in _gather_cache:
+        b = torch.arange(d.B).view(d.B, 1, 1)
+        t = torch.arange(d.T).view(1, d.T, 1)
+        n = torch.arange(d.N).view(1, 1, d.N)
+        tok = ((b * d.N + n) * d.T + t).reshape(d.B, d.T * d.N)
+        cls = (d.R + torch.arange(d.B)).view(d.B, 1)
+        _gather_cache[key] = torch.cat([cls, tok], 1).reshape(-1).int().to(dev)
+    return _gather_cache[key]
+
+
+def _qkv_bias(W, pre):
+    """cat(q_bias, 0, v_bias) - models/vision_transformer.py:171-175 (K has no bias)."""
+    qb, vb = W[pre + "q_bias"], W[pre + "v_bias"]
+    return torch.cat([qb, torch.zeros_like(vb), vb])
+
+
+def _spatial_maps(d, prefix_base_in, prefix_base_out):
+    m_in = ops.seqmap(seq_div=d.T, outer_stride=d.N * d.T, inner_stride=1, pos_stride=d.T, n_prefix=1,
+                      prefix_base=prefix_base_in, prefix_stride=1, prefix_per_seq=0)
+    m_out = ops.seqmap(seq_div=d.T, outer_stride=d.N * d.T, inner_stride=1, pos_stride=d.T, n_prefix=1,
+                       prefix_base=prefix_base_out, prefix_stride=1, prefix_per_seq=1)
+    return m_in, m_out
+
+
+def vit_block_fwd(W, pre, x, d, save=True):
+    """Block.forward - models/vision_transformer.py:243-275.  x [RB, D] -> [RB, D]."""
+    R, RB, D, B, T = d.R, d.RB, d.D, d.B, d.T
+    c = Ctx()
+    # ---- temporal attention over the T frames of each patch
+    ln_t, c.m_t, c.r_t = ops.layernorm_fwd(x[:R], W[pre + "temporal_ln.weight"], W[pre + "temporal_ln.bias"], d.eps)
+    qkv_t = ops.gemm(ln_t, W[pre + "temporal_attn.qkv.weight"], bias=_qkv_bias(W, pre + "temporal_attn."))
+    att_t = torch.empty((R, D), device=x.device, dtype=bf16)
+    ops.attn_small_fwd(qkv_t, att_t, n_seq=R // T, n_heads=d.heads, S=T, D=d.hd, scale=d.scale)
+    proj_t = ops.gemm(att_t, W[pre + "temporal_attn.proj.weight"], bias=W[pre + "temporal_attn.proj.bias"])
+    xt = torch.empty((RB, D), device=x.device, dtype=bf16)
+    ops.gemm(proj_t, W[pre + "temporal_fc.weight"], bias=W[pre + "temporal_fc.bias"], residual=x[:R], out=xt[:R])
+    xt[R:].copy_(x[R:])
+    # ---- spatial attention per frame, cls token shared by the T frames of a sample
+    ln_s, c.m_s, c.r_s = ops.layernorm_fwd(xt, W[pre + "norm1.weight"], W[pre + "norm1.bias"], d.eps)
+    qkv_s = ops.gemm(ln_s, W[pre + "attn.qkv.weight"], bias=_qkv_bias(W, pre + "attn."))
+    att_s = torch.empty((RB + B * T, D), device=x.device, dtype=bf16)  # tokens | cls mean | per-frame cls
+    m_in, m_out = _spatial_maps(d, R, RB)
+    q, k, v = (TView(qkv_s, i * D, d.hd, m_in) for i in range(3))
+    c.lse_s = ops.attn_fwd(q, k, v, TView(att_s, 0, d.hd, m_out), n_seq=B * T, n_heads=d.heads, head_dim=d.hd,
+                           s_q=d.N + 1, s_kv=d.N + 1, causal=False, scale=d.scale)
+    ops.group_reduce(att_s[RB:], B, T, att_s[R:RB], scale=1.0 / T)  # cls averaged over frames (:262)
+    y = ops.gemm(att_s[:RB], W[pre + "attn.proj.weight"], bias=W[pre + "attn.proj.bias"], residual=xt)
+    # ---- MLP
+    ln_m, c.m_m, c.r_m = ops.layernorm_fwd(y, W[pre + "norm2.weight"], W[pre + "norm2.bias"], d.eps)
+    pre_act = torch.empty((RB, d.hid), device=x.device, dtype=bf16)
+    h = ops.gemm(ln_m, W[pre + "mlp.fc1.weight"], bias=W[pre + "mlp.fc1.bias"], act=ACT_GELU_ERF, aux_out=pre_act)
+    out = ops.gemm(h, W[pre + "mlp.fc2.weight"], bias=W[pre + "mlp.fc2.bias"], residual=y)
+    if save:
+        c.update(x=x, ln_t=ln_t, qkv_t=qkv_t, att_t=att_t, proj_t=proj_t, xt=xt, ln_s=ln_s, qkv_s=qkv_s,
+                 att_s=att_s, y=y, ln_m=ln_m, pre_act=pre_act, h=h)
+    return out, c
+
+
+def vit_block_bwd(W, G, pre, c, dout, d):
+    """Backward of vit_block_fwd: dout [RB, D] -> dx [RB, D]; accumulates the block's weight grads."""
+    R, RB, D, B, T = d.R, d.RB, d.D, d.B, d.T
+    dev = dout.device
+    # ---- MLP
+    linear_wgrad(dout, c.h, pre + "mlp.fc2.weight", pre + "mlp.fc2.bias", G)
+    dpre = linear_dgrad(dout, W[pre + "mlp.fc2.weight"], act=ACT_GELU_ERF, aux_in=c.pre_act)
+    linear_wgrad(dpre, c.ln_m, pre + "mlp.fc1.weight", pre + "mlp.fc1.bias", G)
+    dln_m = linear_dgrad(dpre, W[pre + "mlp.fc1.weight"])
+    dy = ops.layernorm_bwd(dln_m, c.y, W[pre + "norm2.weight"], c.m_m, c.r_m, add=dout,
+                           dgamma=G.get(pre + "norm2.weight"), dbeta=G.get(pre + "norm2.bias"))
+    # ---- spatial attention
+    linear_wgrad(dy, c.att_s[:RB], pre + "attn.proj.weight", pre + "attn.proj.bias", G)
+    datt = torch.empty((RB + B * T, D), device=dev, dtype=bf16)
+    linear_dgrad(dy, W[pre + "attn.proj.weight"], out=datt[:RB])
+    ops.group_reduce(datt[R:RB], B, T, datt[RB:], scale=1.0 / T, broadcast=True)
+    dqkv = torch.empty((RB + B * T, 3 * D), device=dev, dtype=bf16)
+    m_in, m_out = _spatial_maps(d, R, RB)
+    q, k, v = (TView(c.qkv_s, i * D, d.hd, m_in) for i in range(3))
+    dq, dk, dv = (TView(dqkv, i * D, d.hd, m_out) for i in range(3))
+    ops.attn_bwd(q, k, v, TView(c.att_s, 0, d.hd, m_out), c.lse_s, TView(datt, 0, d.hd, m_out), dq, dk, dv,
+                 n_seq=B * T, n_heads=d.heads, head_dim=d.hd, s_q=d.N + 1, s_kv=d.N + 1, causal=False, scale=d.scale)
+    ops.group_reduce(dqkv[RB:], B, T, dqkv[R:RB], scale=1.0)  # the shared cls row collects all T frames
+    _qkv_wgrad(G, pre + "attn.", dqkv[:RB], c.ln_s, D, dev)
+    dln_s = linear_dgrad(dqkv[:RB], W[pre + "attn.qkv.weight"])
+    dxt = ops.layernorm_bwd(dln_s, c.xt, W[pre + "norm1.weight"], c.m_s, c.r_s, add=dy,
+                            dgamma=G.get(pre + "norm1.weight"), dbeta=G.get(pre + "norm1.bias"))
+    # ---- temporal attention
+    linear_wgrad(dxt[:R], c.proj_t, pre + "temporal_fc.weight", pre + "temporal_fc.bias", G)
+    dproj = linear_dgrad(dxt[:R], W[pre + "temporal_fc.weight"])
+    linear_wgrad(dproj, c.att_t, pre + "temporal_attn.proj.weight", pre + "temporal_attn.proj.bias", G)
+    datt_t = linear_dgrad(dproj, W[pre + "temporal_attn.proj.weight"])
+    dqkv_t = torch.empty((R, 3 * D), device=dev, dtype=bf16)
+    ops.attn_small_bwd(c.qkv_t, datt_t, dqkv_t, n_seq=R // T, n_heads=d.heads, S=T, D=d.hd, scale=d.scale)
+    _qkv_wgrad(G, pre + "temporal_attn.", dqkv_t, c.ln_t, D, dev)
+    dln_t = linear_dgrad(dqkv_t, W[pre + "temporal_attn.qkv.weight"])
+    dx = torch.empty((RB, D), device=dev, dtype=bf16)
+    ops.layernorm_bwd(dln_t, c.x[:R], W[pre + "temporal_ln.weight"], c.m_t, c.r_t, add=dxt[:R],
+                      dgamma=G.get(pre + "temporal_ln.weight"), dbeta=G.get(pre + "temporal_ln.bias"), dx=dx[:R])
+    dx[R:].copy_(dxt[R:])
+    return dx
+
+
+def _qkv_wgrad(G, apre, dqkv, x, D, dev):
+    linear_wgrad(dqkv, x, apre + "qkv.weight", None, G)
+    if apre + "q_bias" in G or apre + "v_bias" in G:
+        tmp = _zeros_f32(3 * D, dev)
+        ops.colsum(dqkv, tmp)
+        if apre + "q_bias" in G:
+            G[apre + "q_bias"] += tmp[:D]
+        if apre + "v_bias" in G:
+            G[apre + "v_bias"] += tmp[2 * D:]
+
+
+def vit_fwd(W, video, vcfg, save=True):
+    """TimeSformer.forward_features - models/vision_transformer.py:544-587.
+    video [B,3,T,H,W] bf16 -> image_embeds [B*(1+T*N), D] in the reference's (t n) order."""
+    B = video.shape[0]
+    d = VitDims(vcfg, B)
+    assert video.shape[2] == d.T, f"video has {video.shape[2]} frames, model expects {d.T}"
+    dev = video.device
+    c = Ctx(d=d, blocks=[])
+    patches = ops.im2col(video.contiguous(), d.P)
+    pos, temb = W[VE + "pos_embed"], W[VE + "temporal_embed"]
+    table = (pos[0, 1:, None, :] + temb[0, None, :, :]).reshape(d.N * d.T, d.D).contiguous()
+    x0 = torch.empty((d.RB, d.D), device=dev, dtype=bf16)
+    wp = W[VE + "patch_embed.proj.weight"].reshape(d.D, -1)
+    ops.gemm(patches, wp, bias=W.get(VE + "patch_embed.proj.bias"), residual=table, res_row_mod=d.N * d.T, out=x0[:d.R])
+    x0[d.R:] = (W[VE + "cls_token"][0, 0] + pos[0, 0])
+    if VE + "norm_pre.weight" in W:
+        x, c.m0, c.r0 = ops.layernorm_fwd(x0, W[VE + "norm_pre.weight"], W[VE + "norm_pre.bias"], d.eps)
+    else:
+        x = x0
+    for i in range(d.depth):
+        x, bc = vit_block_fwd(W, f"{VE}blocks.{i}.", x, d, save)
+        c.blocks.append(bc)
+    rows = _final_gather_rows(d, dev)
+    out, c.mf, c.rf = ops.layernorm_fwd(x, W[VE + "norm.weight"], W[VE + "norm.bias"], d.eps, in_rows=rows)
+    if save:
+        c.update(patches=patches, x0=x0, xL=x, rows=rows)
+    return out, c
+
+
+def vit_bwd(W, G, c, d_out):
+    """d_out [B*(1+T*N), D] (grad of image_embeds) -> accumulates all encoder weight grads."""
+    d = c.d
+    dev = d_out.device
+    dx = ops.layernorm_bwd(d_out, c.xL, W[VE + "norm.weight"], c.mf, c.rf, in_rows=c.rows,
+                           dgamma=G.get(VE + "norm.weight"), dbeta=G.get(VE + "norm.bias"))
+    for i in reversed(range(d.depth)):
+        dx = vit_block_bwd(W, G, f"{VE}blocks.{i}.", c.blocks[i], dx, d)
+        c.blocks[i] = None  # release activations as we go
+    if VE + "norm_pre.weight" in W:
+        dx0 = ops.layernorm_bwd(dx, c.x0, W[VE + "norm_pre.weight"], c.m0, c.r0,
+                                dgamma=G.get(VE + "norm_pre.weight"), dbeta=G.get(VE + "norm_pre.bias"))
+    else:
+        dx0 = dx
+    # cls_token + pos[0]
+    if VE + "cls_token" in G or VE + "pos_embed" in G:
+        dcls = _zeros_f32(d.D, dev)
+        ops.colsum(dx0[d.R:], dcls)
+        if VE + "cls_token" in G:
+            G[VE + "cls_token"].view(-1).add_(dcls)
+        if VE + "pos_embed" in G:
+            G[VE + "pos_embed"].view(d.N + 1, d.D)[0].add_(dcls)
+    # pos[1+n] + temporal[t] table: sum over the batch, then over t / n
+    if VE + "pos_embed" in G or VE + "temporal_embed" in G:
+        dtab = _zeros_f32(d.N * d.T * d.D, dev)
+        ops.colsum(dx0[:d.R].view(d.B, d.N * d.T * d.D), dtab)
+        dtab = dtab.view(d.N, d.T, d.D)
+        if VE + "pos_embed" in G:
+            G[VE + "pos_embed"].view(d.N + 1, d.D)[1:].add_(dtab.sum(1))
+        if VE + "temporal_embed" in G:
+            G[VE + "temporal_embed"].view(d.T, d.D).add_(dtab.sum(0))
+    linear_wgrad(dx0[:d.R], c.patches, VE + "patch_embed.proj.weight", VE + "patch_embed.proj.bias", G)
+
+
+# ------------------------------------------------------------------------------------------
+# visual abstractor (AttentionPool) + visual_fc
+# ------------------------------------------------------------------------------------------
+_pad_cache = {}
+
+
+def _kv_pad_rows(B, K1, dev):
+    """in_rows for the key LayerNorm: each sample gets K1 real rows plus one slot (-1) that the
+    learned bias_k / bias_v row (nn.MultiheadAttention add_bias_kv) is written into."""
+    key = (B, K1, str(dev))
+    if key not in _pad_cache:
+        r = torch.arange(B * K1).view(B, K1)
+        _pad_cache[key] = torch.cat([r, torch.full((B, 1), -1)], 1).reshape(-1).int().to(dev)
+    return _pad_cache[key]
+
+
+def attn_pool_fwd(W, image_embeds, B, heads, save=True):
+    """AttentionPool.forward - models/vision_transformer.py:368-374 on
+    learnable_queries.repeat(B) (models/distributed_gpt3.py:134).  image_embeds [B*K1, D] -> [B*Q, D]."""
+    dev = image_embeds.device
+    D = image_embeds.shape[1]
+    K1 = image_embeds.shape[0] // B
+    KP = K1 + 1
+    hd = D // heads
+    lq = W["learnable_queries"][0]
+    Q = lq.shape[0]
+    c = Ctx(B=B, Q=Q, K1=K1, D=D, heads=heads, hd=hd)
+    eps = 1e-6
+    # the query block is identical for every sample: normalise / project it once
+    xq, c.mq, c.rq = ops.layernorm_fwd(lq, W[AP + "norm1.weight"], W[AP + "norm1.bias"], eps)
+    rows = _kv_pad_rows(B, K1, dev)
+    kvn, c.mk, c.rk = ops.layernorm_fwd(image_embeds, W[AP + "normk.weight"], W[AP + "normk.bias"], eps, in_rows=rows)
+    w_in, b_in = W[AP + "attn.in_proj_weight"], W[AP + "attn.in_proj_bias"]
+    qp = ops.gemm(xq, w_in[:D], bias=b_in[:D])
+    kvp = ops.gemm(kvn, w_in[D:], bias=b_in[D:])                      # [B*KP, 2D]: k | v
+    kvp.view(B, KP, 2 * D)[:, K1] = torch.cat([W[AP + "attn.bias_k"].view(-1), W[AP + "attn.bias_v"].view(-1)])
+    att = torch.empty((B * Q, D), device=dev, dtype=bf16)
+    mq = ops.seqmap(seq_div=1, outer_stride=0, pos_stride=1)
+    mkv, mo = ops.dense_map(KP), ops.dense_map(Q)
+    c.lse = ops.attn_fwd(TView(qp, 0, hd, mq), TView(kvp, 0, hd, mkv), TView(kvp, D, hd, mkv), TView(att, 0, hd, mo),
+                         n_seq=B, n_heads=heads, head_dim=hd, s_q=Q, s_kv=KP, causal=False, scale=hd ** -0.5)
+    # residual from the *normalised* queries (:369-371)
+    x1 = ops.gemm(att, W[AP + "attn.out_proj.weight"], bias=W[AP + "attn.out_proj.bias"], residual=xq, res_row_mod=Q)
+    ln2, c.m2, c.r2 = ops.layernorm_fwd(x1, W[AP + "norm2.weight"], W[AP + "norm2.bias"], eps)
+    pre_act = torch.empty((B * Q, W[AP + "mlp.fc1.weight"].shape[0]), device=dev, dtype=bf16)
+    h = ops.gemm(ln2, W[AP + "mlp.fc1.weight"], bias=W[AP + "mlp.fc1.bias"], act=ACT_GELU_ERF, aux_out=pre_act)
+    out = ops.gemm(h, W[AP + "mlp.fc2.weight"], bias=W[AP + "mlp.fc2.bias"], residual=x1)
+    if save:
+        c.update(lq=lq, xq=xq, kvn=kvn, qp=qp, kvp=kvp, att=att, x1=x1, ln2=ln2, pre_act=pre_act, h=h,
+                 image_embeds=image_embeds, rows=rows)
+    return out, c
+
+
+def attn_pool_bwd(W, G, c, dout):
+    """dout [B*Q, D] -> d_image_embeds [B*K1, D]; accumulates abstractor + learnable_queries grads."""
+    B, Q, K1, D, hd, heads = c.B, c.Q, c.K1, c.D, c.hd, c.heads
+    KP = K1 + 1
+    dev = dout.device
+    linear_wgrad(dout, c.h, AP + "mlp.fc2.weight", AP + "mlp.fc2.bias", G)
+    dpre = linear_dgrad(dout, W[AP + "mlp.fc2.weight"], act=ACT_GELU_ERF, aux_in=c.pre_act)
+    linear_wgrad(dpre, c.ln2, AP + "mlp.fc1.weight", AP + "mlp.fc1.bias", G)
+    dln2 = linear_dgrad(dpre, W[AP + "mlp.fc1.weight"])
+    dx1 = ops.layernorm_bwd(dln2, c.x1, W[AP + "norm2.weight"], c.m2, c.r2, add=dout,
+                            dgamma=G.get(AP + "norm2.weight"), dbeta=G.get(AP + "norm2.bias"))
+    linear_wgrad(dx1, c.att, AP + "attn.out_proj.weight", AP + "attn.out_proj.bias", G)
+    datt = linear_dgrad(dx1, W[AP + "attn.out_proj.weight"])
+    dqp_b = torch.empty((B * Q, D), device=dev, dtype=bf16)
+    dkvp = torch.empty((B * KP, 2 * D), device=dev, dtype=bf16)
+    mq = ops.seqmap(seq_div=1, outer_stride=0, pos_stride=1)
+    mkv, mo = ops.dense_map(KP), ops.dense_map(Q)
+    ops.attn_bwd(TView(c.qp, 0, hd, mq), TView(c.kvp, 0, hd, mkv), TView(c.kvp, D, hd, mkv), TView(c.att, 0, hd, mo),
+                 c.lse, TView(datt, 0, hd, mo), TView(dqp_b, 0, hd, mo), TView(dkvp, 0, hd, mkv), TView(dkvp, D, hd, mkv),
+                 n_seq=B, n_heads=heads, head_dim=hd, s_q=Q, s_kv=KP, causal=False, scale=hd ** -0.5)
+    # learned bias_k / bias_v row, then zero it so it does not leak into the projection grads
+    dkv3 = dkvp.view(B, KP, 2 * D)
+    dbias = dkv3[:, K1].float().sum(0)
+    if AP + "attn.bias_k" in G:
+        G[AP + "attn.bias_k"].view(-1).add_(dbias[:D])
+    if AP + "attn.bias_v" in G:
+        G[AP + "attn.bias_v"].view(-1).add_(dbias[D:])
+    dkv3[:, K1].zero_()
+    # shared query block: sum the per-sample grads (query path + residual path)
+    dq_sum = _zeros_f32(Q * D, dev)
+    ops.colsum(dqp_b.view(B, Q * D), dq_sum)
+    dqp = dq_sum.view(Q, D).to(bf16)
+    dres = _zeros_f32(Q * D, dev)
+    ops.colsum(dx1.view(B, Q * D), dres)
+    w_in = W[AP + "attn.in_proj_weight"]
+    if AP + "attn.in_proj_weight" in G:
+        gw = G[AP + "attn.in_proj_weight"].view(3 * D, D)
+        ops.gemm(dqp, c.xq, a_t=True, b_t=True, out=gw[:D], accumulate=True)
+        ops.gemm(dkvp, c.kvn, a_t=True, b_t=True, out=gw[D:], accumulate=True)
+    if AP + "attn.in_proj_bias" in G:
+        gb = G[AP + "attn.in_proj_bias"]
+        ops.colsum(dqp, gb[:D])
+        ops.colsum(dkvp, gb[D:])
+    dxq = linear_dgrad(dqp, w_in[:D], out_dtype=torch.float32)
+    dxq = (dxq + dres.view(Q, D)).to(bf16)
+    dlq = ops.layernorm_bwd(dxq, c.lq, W[AP + "norm1.weight"], c.mq, c.rq,
+                            dgamma=G.get(AP + "norm1.weight"), dbeta=G.get(AP + "norm1.bias"))
+    if "learnable_queries" in G:
+        G["learnable_queries"].view(Q, D).add_(dlq.float())
+    dkvn = linear_dgrad(dkvp, w_in[D:])
+    d_img = torch.empty_like(c.image_embeds)
+    ops.layernorm_bwd(dkvn, c.image_embeds, W[AP + "normk.weight"], c.mk, c.rk, in_rows=c.rows,
+                      dgamma=G.get(AP + "normk.weight"), dbeta=G.get(AP + "normk.bias"), dx=d_img)
+    return d_img
+
+
+# ------------------------------------------------------------------------------------------
+# GPT-3 decoder
+# ------------------------------------------------------------------------------------------
+class GptDims:
+    def __init__(self, gcfg):
+        self.H = gcfg["hidden_size"]
+        self.heads = gcfg["num_attention_heads"]
+        self.hd = self.H // self.heads
+        self.layers = gcfg["num_hidden_layers"]
+        self.F = gcfg.get("ffn_hidden_size") or 4 * self.H
+        self.V = gcfg["vocab_size"]
+        self.eps = gcfg.get("layernorm_epsilon", 1e-12)
+        # q.k / (sqrt(hn)*layer) * layer == q.k / sqrt(hn)  (modeling_distributed_gpt3.py:718-762)
+        self.scale = 1.0 / math.sqrt(self.hd)
+
+
+def gpt_layer_fwd(W, pre, x, g, B, S, train_w=False):
+    """GPT3ParallelTransformerLayer.forward - models/modeling_distributed_gpt3.py:1034-1089
+    (dropout p=0; causal mask over the whole [prefix|text] sequence, :1329-1332)."""
+    H, hd = g.H, g.hd
+    c = Ctx()
+    ln1, c.m1, c.r1 = ops.layernorm_fwd(x, W[pre + "input_layernorm.weight"], W[pre + "input_layernorm.bias"], g.eps)
+    qkv = ops.gemm(ln1, W[pre + "self_attention.query_key_value.weight"], bias=W[pre + "self_attention.query_key_value.bias"])
+    att = torch.empty((B * S, H), device=x.device, dtype=bf16)
+    m = ops.dense_map(S)
+    q, k, v = (TView(qkv, i * hd, 3 * hd, m) for i in range(3))  # rows grouped per head as [q|k|v] (:894-902)
+    c.lse = ops.attn_fwd(q, k, v, TView(att, 0, hd, m), n_seq=B, n_heads=g.heads, head_dim=hd, s_q=S, s_kv=S,
+                         causal=True, scale=g.scale)
+    x1 = ops.gemm(att, W[pre + "self_attention.dense.weight"], bias=W[pre + "self_attention.dense.bias"], residual=x)
+    ln2, c.m2, c.r2 = ops.layernorm_fwd(x1, W[pre + "post_attention_layernorm.weight"], W[pre + "post_attention_layernorm.bias"], g.eps)
+    pre_act = torch.empty((B * S, g.F), device=x.device, dtype=bf16)
+    h = ops.gemm(ln2, W[pre + "mlp.dense_h_to_4h.weight"], bias=W[pre + "mlp.dense_h_to_4h.bias"], act=ACT_GELU_TANH, aux_out=pre_act)
+    out = ops.gemm(h, W[pre + "mlp.dense_4h_to_h.weight"], bias=W[pre + "mlp.dense_4h_to_h.bias"], residual=x1)
+    c.update(x=x, qkv=qkv, att=att, x1=x1, pre_act=pre_act)
+    if train_w:
+        c.update(ln1=ln1, ln2=ln2, h=h)
+    return out, c
+
+
+def gpt_layer_bwd(W, G, pre, c, dout, g, B, S):
+    hd = g.hd
+    dev = dout.device
+    if "h" in c:
+        linear_wgrad(dout, c.h, pre + "mlp.dense_4h_to_h.weight", pre + "mlp.dense_4h_to_h.bias", G)
+    dpre = linear_dgrad(dout, W[pre + "mlp.dense_4h_to_h.weight"], act=ACT_GELU_TANH, aux_in=c.pre_act)
+    if "ln2" in c:
+        linear_wgrad(dpre, c.ln2, pre + "mlp.dense_h_to_4h.weight", pre + "mlp.dense_h_to_4h.bias", G)
+    dln2 = linear_dgrad(dpre, W[pre + "mlp.dense_h_to_4h.weight"])
+    dx1 = ops.layernorm_bwd(dln2, c.x1, W[pre + "post_attention_layernorm.weight"], c.m2, c.r2, add=dout,
+                            dgamma=G.get(pre + "post_attention_layernorm.weight"), dbeta=G.get(pre + "post_attention_layernorm.bias"))
+    linear_wgrad(dx1, c.att, pre + "self_attention.dense.weight", pre + "self_attention.dense.bias", G)
+    datt = linear_dgrad(dx1, W[pre + "self_attention.dense.weight"])
+    dqkv = torch.empty_like(c.qkv)
+    m = ops.dense_map(S)
+    q, k, v = (TView(c.qkv, i * hd, 3 * hd, m) for i in range(3))
+    dq, dk, dv = (TView(dqkv, i * hd, 3 * hd, m) for i in range(3))
+    ops.attn_bwd(q, k, v, TView(c.att, 0, hd, m), c.lse, TView(datt, 0, hd, m), dq, dk, dv, n_seq=B, n_heads=g.heads,
+                 head_dim=hd, s_q=S, s_kv=S, causal=True, scale=g.scale)
+    if "ln1" in c:
+        linear_wgrad(dqkv, c.ln1, pre + "self_attention.query_key_value.weight", pre + "self_attention.query_key_value.bias", G)
+    dln1 = linear_dgrad(dqkv, W[pre + "self_attention.query_key_value.weight"])
+    return ops.layernorm_bwd(dln1, c.x, W[pre + "input_layernorm.weight"], c.m1, c.r1, add=dx1,
+                             dgamma=G.get(pre + "input_layernorm.weight"), dbeta=G.get(pre + "input_layernorm.bias"))
+
+
+def gpt_fwd(W, x, gcfg, B, S, train_w=False, save=True):
+    """x [B*S, H]: input embeddings with the learned position embeddings already added
+    (GPT3Embedding.forward, :640-666).  Returns final-LN hidden states [B*S, H]."""
+    g = GptDims(gcfg)
+    c = Ctx(g=g, B=B, S=S, layers=[])
+    for i in range(g.layers):
+        x, lc = gpt_layer_fwd(W, f"{GPT}encoder.layers.{i}.", x, g, B, S, train_w)
+        c.layers.append(lc if save else None)
+    hid, c.mf, c.rf = ops.layernorm_fwd(x, W[GPT + "encoder.final_layernorm.weight"], W[GPT + "encoder.final_layernorm.bias"], g.eps)
+    if save:
+        c.xL = x
+    return hid, c
+
+
+def gpt_bwd(W, G, c, dhid):
+    g, B, S = c.g, c.B, c.S
+    dx = ops.layernorm_bwd(dhid, c.xL, W[GPT + "encoder.final_layernorm.weight"], c.mf, c.rf,
+                           dgamma=G.get(GPT + "encoder.final_layernorm.weight"), dbeta=G.get(GPT + "encoder.final_layernorm.bias"))
+    for i in reversed(range(g.layers)):
+        dx = gpt_layer_bwd(W, G, f"{GPT}encoder.layers.{i}.", c.layers[i], dx, g, B, S)
+        c.layers[i] = None
+    return dx
+
+
+def lm_head_fwd(W, hid, labels):
+    """Tied LM head + per-token CE on fp32 math (modeling_distributed_gpt3.py:1348-1359).
+    Returns (logits [B*S, V] bf16, losses [B*S] fp32, lse)."""
+    logits = ops.gemm(hid, W[GPT + "embedding.word_embeddings.weight"])
+    losses, lse = ops.ce_fwd(logits, labels.reshape(-1).contiguous())
+    return logits, losses, lse
+
+
+def lm_head_bwd(W, G, hid, logits, labels, lse, grad_rows, keep_logits=False):
+    """grad_rows [B*S] fp32 = d loss / d losses.  Overwrites `logits` with dlogits unless keep_logits."""
+    dlogits = ops.ce_bwd(logits, labels.reshape(-1).contiguous(), lse, grad_rows.contiguous(),
+                         dlogits=torch.empty_like(logits) if keep_logits else None)
+    emb = GPT + "embedding.word_embeddings.weight"
+    if emb in G:
+        ops.gemm(dlogits, hid, a_t=True, b_t=True, out=G[emb].view(dlogits.shape[1], hid.shape[1]), accumulate=True)
+    return linear_dgrad(dlogits, W[emb])

@@ -121,6 +121,13 @@ class GroupArgs(C.Structure):
                 ("ld_out", c_i32), ("broadcast", c_i32), ("scale", C.c_float)]
 
 
+class AdamwArgs(C.Structure):
+    _fields_ = [("master", c_vp), ("param", c_vp), ("grad", c_vp), ("m", c_vp), ("v", c_vp), ("sumsq", c_vp),
+                ("n", C.c_int64), ("step", c_i32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("weight_decay", C.c_float), ("grad_scale", C.c_float),
+                ("max_grad_norm", C.c_float)]
+
+
 lib.ymp_last_error.restype = C.c_char_p
 lib.ymp_abi_version.restype = C.c_int
 lib.ymp_launch_count.restype = C.c_uint64
@@ -146,6 +153,10 @@ _ce_fwd = _declare("ymp_ce_fwd", CeArgs)
 _ce_bwd = _declare("ymp_ce_bwd", CeArgs)
 _colsum = _declare("ymp_colsum", ColsumArgs)
 _group = _declare("ymp_group_reduce", GroupArgs)
+_adamw = _declare("ymp_adamw", AdamwArgs)
+_sumsq = lib.ymp_sumsq
+_sumsq.restype = C.c_int
+_sumsq.argtypes = [c_vp, C.c_int64, c_vp, c_vp]
 
 
 def check(rc, what):

@@ -258,3 +258,22 @@ def group_reduce(x, G, T, out, scale=1.0, broadcast=False):
     a.ld_in, a.ld_out, a.broadcast, a.scale = x.stride(0), out.stride(0), int(broadcast), scale
     L.call(L._group, a, "ymp_group_reduce")
     return out
+
+
+# ---------------------------------------------------------------------------------- optimizer
+def sumsq(g, out):
+    """out (fp32 scalar tensor, accumulated) += sum(g^2)."""
+    assert g.dtype == torch.float32 and g.is_contiguous()
+    L.check(L._sumsq(g.data_ptr(), g.numel(), out.data_ptr(), L.cur_stream()), "ymp_sumsq")
+    return out
+
+
+def adamw(master, param, grad, m, v, *, step, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0,
+          max_grad_norm=0.0, sumsq_t=None):
+    a = L.AdamwArgs()
+    a.master, a.param, a.grad, a.m, a.v = master.data_ptr(), param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr()
+    a.sumsq = L.ptr(sumsq_t)
+    a.n, a.step = master.numel(), step
+    a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = lr, beta1, beta2, eps, weight_decay
+    a.grad_scale, a.max_grad_norm = grad_scale, max_grad_norm
+    L.call(L._adamw, a, "ymp_adamw")
