@@ -235,7 +235,7 @@ def run_ymp(args, rank, local_rank, world):
     pk = peaks()
     tf = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     ms_step = ms / args.steps
-    step_tf = GF_PER_SAMPLE * (B if (T, L, Q) == (8, 128, 128) else float("nan")) / ms_step / 1e3
+    step_tf = GF_PER_SAMPLE * (B if (T, L, Q) == (8, 128, 128) else float("nan")) / ms_step  # GFLOP/ms == TFLOP/s
     roofline = dict(bound="tensor", kernel="gemm_bf16_tcgen05_kernel", achieved=tf, peak=pk["tf_sustained"], unit="TFLOP/s",
                     frac=tf / pk["tf_sustained"], traffic=None, peak_source=pk["source"] + ", sustained figure",
                     launches_per_step=len(rec), gemm_ms_per_step=gemm_ms, gemm_share_of_step=gemm_ms / ms_step,
