@@ -146,6 +146,10 @@ int ymp_layernorm_bwd(const ymp_layernorm_bwd_args* a, void* stream);
  *   pos_stride=T, n_prefix=1, prefix_base=B*N*T, prefix_stride=1
  * lse: fp32 [n_seq, n_heads, s_q] (natural log), needed by the backward.
  * ------------------------------------------------------------------------------------------ */
+#define YMP_MASK_NONE 0
+#define YMP_MASK_CAUSAL 1
+#define YMP_MASK_BLOCK 2
+
 typedef struct ymp_seqmap {
   int32_t seq_div;
   int32_t n_prefix;
@@ -165,7 +169,12 @@ typedef struct ymp_attn_args {
   int32_t q_head_stride, k_head_stride, v_head_stride, o_head_stride;
   ymp_seqmap map_q, map_kv, map_o;
   int32_t n_seq, n_heads, head_dim, s_q, s_kv;
-  int32_t causal;
+  int32_t mask;        /* YMP_MASK_NONE | YMP_MASK_CAUSAL | YMP_MASK_BLOCK */
+  int32_t mask_block;  /* YMP_MASK_BLOCK: position i attends j iff i / mask_block == j / mask_block.
+                          Packs many short sequences (TimeSformer temporal attention over T frames,
+                          vision_transformer.py:246-248) into one tensor-core tile. */
+  int64_t total_rows;  /* >0 (dense packed sequences only): rows beyond total_rows do not exist, so
+                          the last sequence may be shorter than s_q */
   float scale;
 } ymp_attn_args;
 int ymp_attn_fwd(const ymp_attn_args* a, void* stream);
@@ -176,31 +185,12 @@ typedef struct ymp_attn_bwd_args {
   void* dq;               /* bf16 outputs; every addressed element is written exactly once */
   void* dk;
   void* dv;
+  float* delta_ws;        /* workspace fp32 [n_seq * n_heads * s_q] (rowsum(dO*O), written then read) */
   int32_t lddo, lddq, lddk, lddv;
   int32_t do_head_stride, dq_head_stride, dk_head_stride, dv_head_stride;
   ymp_seqmap map_do, map_dq, map_dkv;
 } ymp_attn_bwd_args;
 int ymp_attn_bwd(const ymp_attn_bwd_args* a, void* stream);
-
-/* TimeSformer temporal attention (sequence length = num_frames <= 16): dense sequences of S
- * consecutive rows, one warp per (sequence, head).  vision_transformer.py:246-248 via :179-204. */
-typedef struct ymp_attn_small_args {
-  const void* q;
-  const void* k;
-  const void* v;
-  void* o;
-  const void* dout;  /* backward only */
-  void* dq;
-  void* dk;
-  void* dv;
-  int32_t ld, head_stride;      /* q,k,v */
-  int32_t ldo, o_head_stride;   /* o and dout */
-  int32_t ldd, d_head_stride;   /* dq,dk,dv */
-  int32_t n_seq, n_heads, S, D;
-  float scale;
-} ymp_attn_small_args;
-int ymp_attn_small_fwd(const ymp_attn_small_args* a, void* stream);
-int ymp_attn_small_bwd(const ymp_attn_small_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Patch-embedding im2col: video [B,C,T,H,W] bf16 -> patches [(b,n,t), C*P*P] (the A operand of
@@ -282,6 +272,9 @@ typedef struct ymp_adamw_args {
   float lr, beta1, beta2, eps, weight_decay;
   float grad_scale;     /* e.g. 1/world_size after a summing all-reduce */
   float max_grad_norm;  /* <= 0: no clipping */
+  const float* hyper;   /* optional DEVICE array {lr, weight_decay, 1-beta1^t, 1-beta2^t}; when set it
+                           overrides lr / weight_decay / step so a captured CUDA graph can follow an
+                           lr schedule without re-capture */
 } ymp_adamw_args;
 int ymp_adamw(const ymp_adamw_args* a, void* stream);
 

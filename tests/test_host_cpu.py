@@ -31,7 +31,7 @@ def test_ctypes_structs_match_header_field_order():
     hdr = open(os.path.join(ROOT, "include", "ymp.h")).read()
     mirrors = {"ymp_gemm_args": L.GemmArgs, "ymp_layernorm_args": L.LayerNormArgs, "ymp_layernorm_bwd_args": L.LayerNormBwdArgs,
                "ymp_seqmap": L.SeqMap, "ymp_attn_args": L.AttnArgs, "ymp_attn_bwd_args": L.AttnBwdArgs,
-               "ymp_attn_small_args": L.AttnSmallArgs, "ymp_im2col_args": L.Im2colArgs, "ymp_embed_args": L.EmbedArgs,
+               "ymp_adamw_args": L.AdamwArgs, "ymp_im2col_args": L.Im2colArgs, "ymp_embed_args": L.EmbedArgs,
                "ymp_ce_args": L.CeArgs, "ymp_colsum_args": L.ColsumArgs, "ymp_group_args": L.GroupArgs}
     for name, cls in mirrors.items():
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)

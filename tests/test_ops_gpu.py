@@ -185,23 +185,25 @@ def test_attn_timesformer_spatial_map(cuda):
         assert _rel(d_cls, gr[:, :, :1]) < 3e-2, i
 
 
-@pytest.mark.parametrize("S,heads,hd", [(8, 8, 96), (4, 2, 96), (2, 2, 64), (16, 4, 80)])
-def test_attn_small(cuda, S, heads, hd):
+@pytest.mark.parametrize("S,heads,hd,n", [(8, 8, 96, 37), (4, 2, 96, 16), (2, 2, 64, 5), (16, 4, 80, 9), (12, 2, 64, 7)])
+def test_attn_temporal_packed(cuda, S, heads, hd, n):
+    """Short sequences packed into 64-row tiles with a block-diagonal mask (ragged last tile)."""
     from ymp import ops
     torch.manual_seed(5)
-    n, C = 37, heads * hd
-    qkv = (torch.randn(n * S, 3 * C, device=cuda) * 0.6).to(bf16)
-    out = torch.zeros(n * S, C, device=cuda, dtype=bf16)
+    C = heads * hd
+    R = n * S
+    qkv = (torch.randn(R, 3 * C, device=cuda) * 0.6).to(bf16)
+    out = torch.zeros(R, C, device=cuda, dtype=bf16)
     scale = hd ** -0.5
-    ops.attn_small_fwd(qkv, out, n_seq=n, n_heads=heads, S=S, D=hd, scale=scale)
+    lse = ops.attn_temporal_fwd(qkv, out, R=R, n_heads=heads, T=S, D=hd, scale=scale)
     q5 = qkv.float().view(n, S, 3, heads, hd)
     q, k, v = (q5[:, :, i].permute(0, 2, 1, 3).contiguous().requires_grad_() for i in range(3))
     ref = _attn_ref(q, k, v, scale, False)
     assert _rel(out.view(n, S, heads, hd).permute(0, 2, 1, 3), ref) < 2e-2
-    dout = torch.randn(n * S, C, device=cuda).to(bf16)
+    dout = torch.randn(R, C, device=cuda).to(bf16)
     ref.backward(dout.float().view(n, S, heads, hd).permute(0, 2, 1, 3))
     dqkv = torch.zeros_like(qkv)
-    ops.attn_small_bwd(qkv, dout, dqkv, n_seq=n, n_heads=heads, S=S, D=hd, scale=scale)
+    ops.attn_temporal_bwd(qkv, out, lse, dout, dqkv, R=R, n_heads=heads, T=S, D=hd, scale=scale)
     d5 = dqkv.float().view(n, S, 3, heads, hd)
     for i, gr in enumerate((q.grad, k.grad, v.grad)):
         assert _rel(d5[:, :, i].permute(0, 2, 1, 3), gr) < 3e-2, i

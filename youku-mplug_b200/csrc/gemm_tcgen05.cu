@@ -32,6 +32,7 @@ struct GemmKParams {
   int kb_per_split;
   int res_row_mod;                 // residual row = row % res_row_mod (0: plain)
   int d_row_block, d_row_stride;   // D row = (row / block) * stride + row % block (0: plain)
+  bool v32_d, v32_aux, v32_res, v32_bias;  // 32-byte aligned -> 256-bit accesses
   float alpha;
 };
 
@@ -55,6 +56,42 @@ __device__ __forceinline__ float apply_dact(float x, int act) {
   return 1.0f;
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per thread per
+// instruction, so the row-per-thread epilogue writes whole sectors instead of half sectors.
+__device__ __forceinline__ void ld_v8(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st_v8(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// 16 consecutive bf16 (32 bytes) <-> 16 floats
+__device__ __forceinline__ void load16(const __nv_bfloat16* p, bool v32, float (&f)[16]) {
+  uint32_t r[8];
+  if (v32) {
+    ld_v8(p, r);
+  } else {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { f[2 * i] = bf16_lo(r[i]); f[2 * i + 1] = bf16_hi(r[i]); }
+}
+__device__ __forceinline__ void store16(__nv_bfloat16* p, bool v32, const float* f) {
+  uint32_t r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+  if (v32) {
+    st_v8(p, r);
+  } else {
+    reinterpret_cast<uint4*>(p)[0] = make_uint4(r[0], r[1], r[2], r[3]);
+    reinterpret_cast<uint4*>(p)[1] = make_uint4(r[4], r[5], r[6], r[7]);
+  }
+}
+
 // Epilogue for one thread: 32 consecutive columns of one output row.
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint32_t (&r)[32],
                                                int row, int col0) {
@@ -68,70 +105,61 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
 
   if (full) {
     if (p.bias) {
-      const uint4* b4 = reinterpret_cast<const uint4*>(p.bias + col0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 b = __ldg(b4 + j);
-        v[8 * j + 0] += bf16_lo(b.x); v[8 * j + 1] += bf16_hi(b.x);
-        v[8 * j + 2] += bf16_lo(b.y); v[8 * j + 3] += bf16_hi(b.y);
-        v[8 * j + 4] += bf16_lo(b.z); v[8 * j + 5] += bf16_hi(b.z);
-        v[8 * j + 6] += bf16_lo(b.w); v[8 * j + 7] += bf16_hi(b.w);
+      for (int hh = 0; hh < 2; ++hh) {
+        float b[16];
+        load16(p.bias + col0 + 16 * hh, p.v32_bias, b);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[16 * hh + i] += b[i];
       }
     }
     const size_t off = (size_t)row * p.ldd + col0;          // aux tensors: plain rows
     const size_t doff = (size_t)drow * p.ldd + col0;        // D: optionally re-blocked rows
     if (p.aux_out) {
-      uint4* a4 = reinterpret_cast<uint4*>(p.aux_out + off);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-        o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-        o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-        o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-        a4[j] = o;
-      }
+      store16(p.aux_out + off, p.v32_aux, v);
+      store16(p.aux_out + off + 16, p.v32_aux, v + 16);
     }
     if (p.aux_in) {
-      const uint4* a4 = reinterpret_cast<const uint4*>(p.aux_in + off);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 a = __ldg(a4 + j);
-        v[8 * j + 0] *= apply_dact(bf16_lo(a.x), p.act); v[8 * j + 1] *= apply_dact(bf16_hi(a.x), p.act);
-        v[8 * j + 2] *= apply_dact(bf16_lo(a.y), p.act); v[8 * j + 3] *= apply_dact(bf16_hi(a.y), p.act);
-        v[8 * j + 4] *= apply_dact(bf16_lo(a.z), p.act); v[8 * j + 5] *= apply_dact(bf16_hi(a.z), p.act);
-        v[8 * j + 6] *= apply_dact(bf16_lo(a.w), p.act); v[8 * j + 7] *= apply_dact(bf16_hi(a.w), p.act);
+      for (int hh = 0; hh < 2; ++hh) {
+        float a[16];
+        load16(p.aux_in + off + 16 * hh, p.v32_aux, a);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[16 * hh + i] *= apply_dact(a[i], p.act);
       }
     } else if (p.act != YMP_ACT_NONE) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
     }
     if (p.residual) {
-      const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (size_t)rrow * p.ldr + col0);
+      const __nv_bfloat16* rp = p.residual + (size_t)rrow * p.ldr + col0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 a = __ldg(r4 + j);
-        v[8 * j + 0] += bf16_lo(a.x); v[8 * j + 1] += bf16_hi(a.x);
-        v[8 * j + 2] += bf16_lo(a.y); v[8 * j + 3] += bf16_hi(a.y);
-        v[8 * j + 4] += bf16_lo(a.z); v[8 * j + 5] += bf16_hi(a.z);
-        v[8 * j + 6] += bf16_lo(a.w); v[8 * j + 7] += bf16_hi(a.w);
+      for (int hh = 0; hh < 2; ++hh) {
+        float a[16];
+        load16(rp + 16 * hh, p.v32_res, a);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[16 * hh + i] += a[i];
       }
     }
     if (!p.out_f32) {
-      uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + doff);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-        o.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-        o.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-        o.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-        d4[j] = o;
-      }
+      __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + doff;
+      store16(dp, p.v32_d, v);
+      store16(dp + 16, p.v32_d, v + 16);
     } else if (!p.accumulate) {
-      float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + doff);
+      float* d = reinterpret_cast<float*>(p.D) + doff;
+      if (p.v32_d) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) {
+          uint32_t o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(v[8 * j + i]);
+          st_v8(d + 8 * j, o);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<float4*>(d)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
     } else {
       float* d = reinterpret_cast<float*>(p.D) + doff;
 #pragma unroll
@@ -451,6 +479,12 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
   kp.split_k = split; kp.kb_per_split = per;
   kp.alpha = a->alpha;
   kp.res_row_mod = a->res_row_mod; kp.d_row_block = a->d_row_block; kp.d_row_stride = a->d_row_stride;
+  auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+  const int esz = kp.out_f32 ? 4 : 2;
+  kp.v32_d = al32(a->D) && (a->ldd * esz) % 32 == 0;
+  kp.v32_aux = (a->ldd * 2) % 32 == 0 && (!a->aux_out || al32(a->aux_out)) && (!a->aux_in || al32(a->aux_in));
+  kp.v32_res = a->residual && al32(a->residual) && (a->ldr * 2) % 32 == 0;
+  kp.v32_bias = a->bias && al32(a->bias);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (bn == 256) return launch_gemm<256>(a, kp, st);
   return launch_gemm<128>(a, kp, st);

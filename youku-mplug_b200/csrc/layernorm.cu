@@ -228,8 +228,9 @@ extern "C" int ymp_layernorm_bwd(const ymp_layernorm_bwd_args* a, void* stream) 
   cudaStream_t st = (cudaStream_t)stream;
   const int vpl = (a->D / 8 + 31) / 32;
   const bool wg = a->dgamma != nullptr;
-  // with weight grads each block ends with D atomics: keep the grid at ~2 blocks per SM
-  const int cap = wg ? num_sms() * 2 : num_sms() * 8;
+  // with weight grads each block ends with 2*D atomics; 6 blocks per SM keeps enough warps in
+  // flight for HBM while bounding the atomic tail (~900 adds per address)
+  const int cap = wg ? num_sms() * 6 : num_sms() * 8;
   const int blocks = min((a->rows + LN_WARPS - 1) / LN_WARPS, cap);
   const int thr = LN_WARPS * 32;
   if (wg) {

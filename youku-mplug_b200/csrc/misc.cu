@@ -171,7 +171,18 @@ __global__ void __launch_bounds__(128) colsum_kernel(const __nv_bfloat16* __rest
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(R, r0 + rows_per_block);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int r = r0; r < r1; ++r) {
+  int r = r0;
+  for (; r + 8 <= r1; r += 8) {  // 8 independent 16-byte loads in flight per thread
+    uint4 u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)(r + j) * ld) + v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[0] += bf16_lo(u[j].x); acc[1] += bf16_hi(u[j].x); acc[2] += bf16_lo(u[j].y); acc[3] += bf16_hi(u[j].y);
+      acc[4] += bf16_lo(u[j].z); acc[5] += bf16_hi(u[j].z); acc[6] += bf16_lo(u[j].w); acc[7] += bf16_hi(u[j].w);
+    }
+  }
+  for (; r < r1; ++r) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + (size_t)r * ld) + v);
     acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
     acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);

@@ -34,6 +34,7 @@ struct AdamParams {
   float* m;
   float* v;
   const float* sumsq;  // device scalar: sum of squares of the (unscaled) global gradient, or NULL
+  const float* hyper;  // optional device array {lr, weight_decay, bc1, bc2}: overrides the by-value fields
   long n;
   float lr, beta1, beta2, eps, wd, grad_scale, max_norm, bc1, bc2;
 };
@@ -44,14 +45,16 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamParams p) {
     const float norm = sqrtf(*p.sumsq) * p.grad_scale;
     coef *= fminf(1.f, p.max_norm / (norm + 1e-6f));
   }
-  const float step = p.lr / p.bc1;
-  const float inv_bc2 = rsqrtf(p.bc2);
+  float lr = p.lr, wd = p.wd, bc1 = p.bc1, bc2 = p.bc2;
+  if (p.hyper) { lr = p.hyper[0]; wd = p.hyper[1]; bc1 = p.hyper[2]; bc2 = p.hyper[3]; }
+  const float step = lr / bc1;
+  const float inv_bc2 = rsqrtf(bc2);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long)gridDim.x * blockDim.x) {
     const float g = p.grad[i] * coef;
     const float m = p.beta1 * p.m[i] + (1.f - p.beta1) * g;
     const float v = p.beta2 * p.v[i] + (1.f - p.beta2) * g * g;
     float w = p.master[i];
-    w = w * (1.f - p.lr * p.wd) - step * m / (sqrtf(v) * inv_bc2 + p.eps);
+    w = w * (1.f - lr * wd) - step * m / (sqrtf(v) * inv_bc2 + p.eps);
     p.m[i] = m; p.v[i] = v; p.master[i] = w;
     p.param[i] = __float2bfloat16(w);
   }
@@ -72,10 +75,10 @@ extern "C" int ymp_sumsq(const float* g, int64_t n, float* out, void* stream) {
 
 extern "C" int ymp_adamw(const ymp_adamw_args* a, void* stream) {
   YMP_CHECK_ARG(a && a->master && a->param && a->grad && a->m && a->v && a->n > 0, "ymp_adamw: bad args");
-  YMP_CHECK_ARG(a->step >= 1, "ymp_adamw: step must be >= 1");
+  YMP_CHECK_ARG(a->step >= 1 || a->hyper, "ymp_adamw: step must be >= 1 (or pass hyper)");
   AdamParams p;
   p.master = a->master; p.param = (__nv_bfloat16*)a->param; p.grad = a->grad; p.m = a->m; p.v = a->v;
-  p.sumsq = a->sumsq; p.n = a->n;
+  p.sumsq = a->sumsq; p.hyper = a->hyper; p.n = a->n;
   p.lr = a->lr; p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps; p.wd = a->weight_decay;
   p.grad_scale = a->grad_scale; p.max_norm = a->max_grad_norm;
   p.bc1 = 1.f - powf(a->beta1, (float)a->step);

@@ -107,7 +107,7 @@ def vit_block_fwd(W, pre, x, d, save=True):
     ln_t, c.m_t, c.r_t = ops.layernorm_fwd(x[:R], W[pre + "temporal_ln.weight"], W[pre + "temporal_ln.bias"], d.eps)
     qkv_t = ops.gemm(ln_t, W[pre + "temporal_attn.qkv.weight"], bias=_qkv_bias(W, pre + "temporal_attn."))
     att_t = torch.empty((R, D), device=x.device, dtype=bf16)
-    ops.attn_small_fwd(qkv_t, att_t, n_seq=R // T, n_heads=d.heads, S=T, D=d.hd, scale=d.scale)
+    c.lse_t = ops.attn_temporal_fwd(qkv_t, att_t, R=R, n_heads=d.heads, T=T, D=d.hd, scale=d.scale)
     proj_t = ops.gemm(att_t, W[pre + "temporal_attn.proj.weight"], bias=W[pre + "temporal_attn.proj.bias"])
     xt = torch.empty((RB, D), device=x.device, dtype=bf16)
     ops.gemm(proj_t, W[pre + "temporal_fc.weight"], bias=W[pre + "temporal_fc.bias"], residual=x[:R], out=xt[:R])
@@ -166,7 +166,7 @@ def vit_block_bwd(W, G, pre, c, dout, d):
     linear_wgrad(dproj, c.att_t, pre + "temporal_attn.proj.weight", pre + "temporal_attn.proj.bias", G)
     datt_t = linear_dgrad(dproj, W[pre + "temporal_attn.proj.weight"])
     dqkv_t = torch.empty((R, 3 * D), device=dev, dtype=bf16)
-    ops.attn_small_bwd(c.qkv_t, datt_t, dqkv_t, n_seq=R // T, n_heads=d.heads, S=T, D=d.hd, scale=d.scale)
+    ops.attn_temporal_bwd(c.qkv_t, c.att_t, c.lse_t, datt_t, dqkv_t, R=R, n_heads=d.heads, T=T, D=d.hd, scale=d.scale)
     _qkv_wgrad(G, pre + "temporal_attn.", dqkv_t, c.ln_t, D, dev)
     dln_t = linear_dgrad(dqkv_t, W[pre + "temporal_attn.qkv.weight"])
     dx = torch.empty((RB, D), device=dev, dtype=bf16)

@@ -24,6 +24,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH = 0, 1, 2
+MASK_NONE, MASK_CAUSAL, MASK_BLOCK = 0, 1, 2
 DT_BF16, DT_F32 = 0, 1
 
 c_i32 = C.c_int32
@@ -75,25 +76,16 @@ class AttnArgs(C.Structure):
         ("q_head_stride", c_i32), ("k_head_stride", c_i32), ("v_head_stride", c_i32), ("o_head_stride", c_i32),
         ("map_q", SeqMap), ("map_kv", SeqMap), ("map_o", SeqMap),
         ("n_seq", c_i32), ("n_heads", c_i32), ("head_dim", c_i32), ("s_q", c_i32), ("s_kv", c_i32),
-        ("causal", c_i32), ("scale", C.c_float),
+        ("mask", c_i32), ("mask_block", c_i32), ("total_rows", C.c_int64), ("scale", C.c_float),
     ]
 
 
 class AttnBwdArgs(C.Structure):
     _fields_ = [
-        ("fwd", AttnArgs), ("dout", c_vp), ("dq", c_vp), ("dk", c_vp), ("dv", c_vp),
+        ("fwd", AttnArgs), ("dout", c_vp), ("dq", c_vp), ("dk", c_vp), ("dv", c_vp), ("delta_ws", c_vp),
         ("lddo", c_i32), ("lddq", c_i32), ("lddk", c_i32), ("lddv", c_i32),
         ("do_head_stride", c_i32), ("dq_head_stride", c_i32), ("dk_head_stride", c_i32), ("dv_head_stride", c_i32),
         ("map_do", SeqMap), ("map_dq", SeqMap), ("map_dkv", SeqMap),
-    ]
-
-
-class AttnSmallArgs(C.Structure):
-    _fields_ = [
-        ("q", c_vp), ("k", c_vp), ("v", c_vp), ("o", c_vp), ("dout", c_vp), ("dq", c_vp), ("dk", c_vp), ("dv", c_vp),
-        ("ld", c_i32), ("head_stride", c_i32), ("ldo", c_i32), ("o_head_stride", c_i32),
-        ("ldd", c_i32), ("d_head_stride", c_i32),
-        ("n_seq", c_i32), ("n_heads", c_i32), ("S", c_i32), ("D", c_i32), ("scale", C.c_float),
     ]
 
 
@@ -125,7 +117,7 @@ class AdamwArgs(C.Structure):
     _fields_ = [("master", c_vp), ("param", c_vp), ("grad", c_vp), ("m", c_vp), ("v", c_vp), ("sumsq", c_vp),
                 ("n", C.c_int64), ("step", c_i32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("eps", C.c_float), ("weight_decay", C.c_float), ("grad_scale", C.c_float),
-                ("max_grad_norm", C.c_float)]
+                ("max_grad_norm", C.c_float), ("hyper", c_vp)]
 
 
 lib.ymp_last_error.restype = C.c_char_p
@@ -145,8 +137,6 @@ _ln_fwd = _declare("ymp_layernorm_fwd", LayerNormArgs)
 _ln_bwd = _declare("ymp_layernorm_bwd", LayerNormBwdArgs)
 _attn_fwd = _declare("ymp_attn_fwd", AttnArgs)
 _attn_bwd = _declare("ymp_attn_bwd", AttnBwdArgs)
-_attn_small_fwd = _declare("ymp_attn_small_fwd", AttnSmallArgs)
-_attn_small_bwd = _declare("ymp_attn_small_bwd", AttnSmallArgs)
 _im2col = _declare("ymp_im2col", Im2colArgs)
 _embed = _declare("ymp_embed_gather", EmbedArgs)
 _ce_fwd = _declare("ymp_ce_fwd", CeArgs)

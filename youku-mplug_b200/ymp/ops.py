@@ -6,7 +6,8 @@ kernels of one ABI call on the current stream and returns the output tensor(s).
 import torch
 
 from . import lib as L
-from .lib import ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH, DT_BF16, DT_F32  # noqa: F401
+from .lib import (ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH, DT_BF16, DT_F32,  # noqa: F401
+                  MASK_NONE, MASK_CAUSAL, MASK_BLOCK)
 
 bf16 = torch.bfloat16
 
@@ -124,30 +125,35 @@ class TView:
         return self.t.stride(0)
 
 
-def _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale):
+def _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, mask_block=0, total_rows=0):
     a = L.AttnArgs()
     a.q, a.k, a.v, a.o, a.lse = q.p, k.p, v.p, o.p, L.ptr(lse)
     a.ldq, a.ldk, a.ldv, a.ldo = q.ld, k.ld, v.ld, o.ld
     a.q_head_stride, a.k_head_stride, a.v_head_stride, a.o_head_stride = q.hs, k.hs, v.hs, o.hs
     a.map_q, a.map_kv, a.map_o = q.m, k.m, o.m
     a.n_seq, a.n_heads, a.head_dim, a.s_q, a.s_kv = n_seq, n_heads, head_dim, s_q, s_kv
-    a.causal, a.scale = int(causal), scale
+    # `causal` may be a bool or one of MASK_NONE / MASK_CAUSAL / MASK_BLOCK
+    a.mask, a.mask_block, a.total_rows, a.scale = int(causal), mask_block, total_rows, scale
     return a
 
 
-def attn_fwd(q, k, v, o, *, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, lse=None):
+def attn_fwd(q, k, v, o, *, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, lse=None, mask_block=0,
+             total_rows=0):
     """q,k,v,o: TView.  Returns lse [n_seq, n_heads, s_q] fp32."""
     if lse is None:
         lse = torch.empty((n_seq, n_heads, s_q), device=q.t.device, dtype=torch.float32)
-    a = _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale)
+    a = _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, mask_block, total_rows)
     L.call(L._attn_fwd, a, "ymp_attn_fwd")
     return lse
 
 
-def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, *, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale):
+def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, *, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale,
+             mask_block=0, total_rows=0):
     """dout,dq,dk,dv: TView (dk and dv share dk's seqmap)."""
     b = L.AttnBwdArgs()
-    b.fwd = _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale)
+    b.fwd = _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, mask_block, total_rows)
+    delta = torch.empty_like(lse)
+    b.delta_ws = delta.data_ptr()
     b.dout, b.dq, b.dk, b.dv = dout.p, dq.p, dk.p, dv.p
     b.lddo, b.lddq, b.lddk, b.lddv = dout.ld, dq.ld, dk.ld, dv.ld
     b.do_head_stride, b.dq_head_stride, b.dk_head_stride, b.dv_head_stride = dout.hs, dq.hs, dk.hs, dv.hs
@@ -155,32 +161,31 @@ def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, *, n_seq, n_heads, head_dim, s_q
     L.call(L._attn_bwd, b, "ymp_attn_bwd")
 
 
-def _small_args(qkv, C, n_seq, n_heads, S, D, scale):
-    a = L.AttnSmallArgs()
-    base = qkv.data_ptr()
-    a.q, a.k, a.v = base, base + 2 * C, base + 4 * C
-    a.ld, a.head_stride = qkv.stride(0), D
-    a.n_seq, a.n_heads, a.S, a.D, a.scale = n_seq, n_heads, S, D, scale
-    return a
+def temporal_pack(R, T):
+    """Pack consecutive length-T sequences into <=64-row tiles: (n_seq, P) with P = (64 // T) * T."""
+    P = max(1, 64 // T) * T
+    return (R + P - 1) // P, P
 
 
-def attn_small_fwd(qkv, out, *, n_seq, n_heads, S, D, scale):
-    """qkv [n_seq*S, 3*C] in ViT layout [3, heads, D]; out [n_seq*S, C]."""
+def attn_temporal_fwd(qkv, out, *, R, n_heads, T, D, scale):
+    """TimeSformer temporal attention: rows are [.., T] consecutive frames of one patch; qkv [R, 3C] in ViT
+    layout [3, heads, D]; out [R, C].  Block-diagonal mask inside packed tiles.  Returns lse."""
     C = n_heads * D
-    a = _small_args(qkv, C, n_seq, n_heads, S, D, scale)
-    a.o, a.ldo, a.o_head_stride = out.data_ptr(), out.stride(0), D
-    L.call(L._attn_small_fwd, a, "ymp_attn_small_fwd")
-    return out
+    n_seq, P = temporal_pack(R, T)
+    m = dense_map(P)
+    q, k, v = (TView(qkv, i * C, D, m) for i in range(3))
+    return attn_fwd(q, k, v, TView(out, 0, D, m), n_seq=n_seq, n_heads=n_heads, head_dim=D, s_q=P, s_kv=P,
+                    causal=MASK_BLOCK, scale=scale, mask_block=T, total_rows=R)
 
 
-def attn_small_bwd(qkv, dout, dqkv, *, n_seq, n_heads, S, D, scale):
+def attn_temporal_bwd(qkv, out, lse, dout, dqkv, *, R, n_heads, T, D, scale):
     C = n_heads * D
-    a = _small_args(qkv, C, n_seq, n_heads, S, D, scale)
-    a.dout, a.ldo, a.o_head_stride = dout.data_ptr(), dout.stride(0), D
-    base = dqkv.data_ptr()
-    a.dq, a.dk, a.dv = base, base + 2 * C, base + 4 * C
-    a.ldd, a.d_head_stride = dqkv.stride(0), D
-    L.call(L._attn_small_bwd, a, "ymp_attn_small_bwd")
+    n_seq, P = temporal_pack(R, T)
+    m = dense_map(P)
+    q, k, v = (TView(qkv, i * C, D, m) for i in range(3))
+    dq, dk, dv = (TView(dqkv, i * C, D, m) for i in range(3))
+    attn_bwd(q, k, v, TView(out, 0, D, m), lse, TView(dout, 0, D, m), dq, dk, dv, n_seq=n_seq, n_heads=n_heads,
+             head_dim=D, s_q=P, s_kv=P, causal=MASK_BLOCK, scale=scale, mask_block=T, total_rows=R)
     return dqkv
 
 
@@ -269,8 +274,9 @@ def sumsq(g, out):
 
 
 def adamw(master, param, grad, m, v, *, step, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0,
-          max_grad_norm=0.0, sumsq_t=None):
+          max_grad_norm=0.0, sumsq_t=None, hyper=None):
     a = L.AdamwArgs()
+    a.hyper = L.ptr(hyper)
     a.master, a.param, a.grad, a.m, a.v = master.data_ptr(), param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr()
     a.sumsq = L.ptr(sumsq_t)
     a.n, a.step = master.numel(), step
