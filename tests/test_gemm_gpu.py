@@ -40,7 +40,8 @@ def _close(out, ref, tol=2e-2):
 
 @pytest.mark.parametrize("a_t,b_t", [(False, False), (False, True), (True, False), (True, True)])
 @pytest.mark.parametrize("M,N,K,tile_n", [(256, 256, 128, 256), (384, 512, 192, 128), (200, 328, 72, 0),
-                                          (1024, 768, 768, 256)])
+                                          (1024, 768, 768, 256), (512, 512, 256, 512), (1024, 768, 768, 512),
+                                          (300, 520, 136, 512), (2304, 768, 512, 512)])
 def test_gemm_layouts(cuda, a_t, b_t, M, N, K, tile_n):
     from ymp import ops
     torch.manual_seed(0)
@@ -51,8 +52,9 @@ def test_gemm_layouts(cuda, a_t, b_t, M, N, K, tile_n):
     _close(out, ref, 1e-2)
 
 
+@pytest.mark.parametrize("tile_n", [0, 512])
 @pytest.mark.parametrize("act", [0, 1, 2])
-def test_gemm_epilogue_fwd(cuda, act):
+def test_gemm_epilogue_fwd(cuda, act, tile_n):
     from ymp import ops
     torch.manual_seed(1)
     M, N, K = 512, 768, 256
@@ -61,7 +63,7 @@ def test_gemm_epilogue_fwd(cuda, act):
     bias = torch.randn(N, device=cuda).bfloat16()
     res = torch.randn(M, N, device=cuda).bfloat16()
     aux = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
-    out = ops.gemm(a, b, bias=bias, residual=res, act=act, aux_out=aux)
+    out = ops.gemm(a, b, bias=bias, residual=res, act=act, aux_out=aux, tile_n=tile_n)
     ref, pre = _ref(a, b, False, False, bias=bias, residual=res, act=act)
     _close(out, ref)
     _close(aux, pre)
@@ -95,6 +97,9 @@ def test_gemm_f32_out_and_splitk(cuda):
     acc2 = torch.zeros(M, N, device=cuda, dtype=torch.float32)
     ops.gemm(a, b, a_t=True, b_t=True, out=acc2, accumulate=True, split_k=0)
     _close(acc2, ref, 1e-3)
+    acc3 = torch.zeros(M, N, device=cuda, dtype=torch.float32)
+    ops.gemm(a, b, a_t=True, b_t=True, out=acc3, accumulate=True, split_k=4, tile_n=512)   # CTA-pair tiles
+    _close(acc3, ref, 1e-3)
 
 
 def test_gemm_large_persistent(cuda):
@@ -107,6 +112,10 @@ def test_gemm_large_persistent(cuda):
     out = ops.gemm(a, b)
     ref, _ = _ref(a, b, False, False)
     _close(out, ref, 1e-2)
+    out_p = ops.gemm(a, b, tile_n=512)   # CTA pairs: persistent loop + 6-stage ring + both TMEM stages
+    _close(out_p, ref, 1e-2)
+    big_m = torch.randn(20000, K, device=cuda).bfloat16()   # > 74 pairs: several tiles per pair
+    _close(ops.gemm(big_m, b, tile_n=512), big_m.float() @ b.float().t(), 1e-2)
     # strided views (ld > width) as produced by slicing packed QKV buffers
     big = torch.randn(M, 3 * K, device=cuda).bfloat16()
     out2 = ops.gemm(big[:, K:2 * K], b)

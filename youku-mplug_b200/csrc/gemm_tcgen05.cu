@@ -354,6 +354,173 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   }
 }
 
+// ------------------------------------------------------------------------------ 2-CTA variant
+// Tile 256(M) x 256(N) per CTA pair (tcgen05.mma cta_group::2): each CTA stages its own 128 rows of A
+// and HALF of the B tile, so per-SM shared-memory traffic (TMA writes + MMA reads) drops from
+// 192 to 128 B/clk - the 1-CTA kernel's limiter (B300_MICROARCH: smem crossbar 128 B/clk/SM) - and
+// L2->SM traffic per flop drops by a third.  The leader CTA issues all MMAs; completion is multicast
+// to both CTAs' mbarriers; both CTAs run their own producer and epilogue warps.
+constexpr int BN2 = 256;
+constexpr int NSTAGE2 = 6;
+constexpr int B2_STAGE_BYTES = (BN2 / 2) * BK * 2;
+constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;
+constexpr int SMEM2_BYTES = NSTAGE2 * STAGE2_BYTES + 256 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
+                              const __grid_constant__ CUtensorMap tma_b, const GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + NSTAGE2 * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGE2 * STAGE2_BYTES);
+  uint64_t* empty_bar = full_bar + NSTAGE2;
+  uint64_t* tfull_bar = empty_bar + NSTAGE2;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const int num_n = (p.N + BN2 - 1) / BN2;
+  const int num_units = num_m * num_n * p.split_k;
+  const int kb_total = (p.K + BK - 1) / BK;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < NSTAGE2; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * NUM_EPI_WARPS);  // epilogue warps of BOTH CTAs (used on the leader)
+    }
+    fence_mbar_init();
+  }
+  cluster_sync_all();
+  if (warp_idx == 2) tmem_alloc_cta2<2 * BN2>(tmem_ptr);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp_idx == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = pair; u < num_units; u += num_pairs) {
+        const int ks = u % p.split_k;
+        const int t = u / p.split_k;
+        const int m0 = (t % num_m) * 2 * BM + (int)rank * BM;
+        const int n0 = (t / num_m) * BN2 + (int)rank * (BN2 / 2);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);  // bytes of both CTAs land here
+          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * B2_STAGE_BYTES;
+          if (!p.a_mn) {
+            tma_load_2d_cta2(sa, &tma_a, &full_bar[stage], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)
+              tma_load_2d_cta2(sa + c * (64 * BK * 2), &tma_a, &full_bar[stage], m0 + c * 64, kb * BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_cta2(sb, &tma_b, &full_bar[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN2 / 2 / 64; ++c)
+              tma_load_2d_cta2(sb + c * (64 * BK * 2), &tma_b, &full_bar[stage], n0 + c * 64, kb * BK);
+          }
+          if (++stage == NSTAGE2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================================================== MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(2 * BM, BN2, p.a_mn, p.b_mn);
+      const uint32_t a_lbo = p.a_mn ? 64 * BK * 2 : 16, a_kstep = p.a_mn ? UMMA_K * 128 : UMMA_K * 2;
+      const uint32_t b_lbo = p.b_mn ? 64 * BK * 2 : 16, b_kstep = p.b_mn ? UMMA_K * 128 : UMMA_K * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int u = pair; u < num_units; u += num_pairs) {
+        const int ks = u % p.split_k;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN2;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * B2_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+            umma_bf16_cta2(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_cta2(&empty_bar[stage]);  // frees the slot in both CTAs
+          if (++stage == NSTAGE2) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_cta2(&tfull_bar[as]);  // accumulator halves complete in both CTAs
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================================================================== epilogue (both CTAs)
+    const int q = warp_idx & 3;
+    const int half = (warp_idx - 4) >> 2;
+    constexpr int CHUNKS = BN2 / 2 / 32;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int u = pair; u < num_units; u += num_pairs) {
+      const int t = u / p.split_k;
+      const int m0 = (t % num_m) * 2 * BM + (int)rank * BM;
+      const int n_blk = t / num_m;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int coff = half * (BN2 / 2) + c * 32;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN2 + coff), r);
+        tmem_ld_wait();
+        if (c == CHUNKS - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // always on the leader's barrier
+        }
+        epilogue_chunk(p, r, row, n_blk * BN2 + coff);
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be multicasting into our barriers / reading our smem
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc_cta2<2 * BN2>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -421,6 +588,28 @@ static int launch_gemm(const ymp_gemm_args* a, const GemmKParams& kp, cudaStream
   return YMP_OK;
 }
 
+static int launch_gemm_2cta(const ymp_gemm_args* a, const GemmKParams& kp, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a->a_mn_major) rc = make_map(&ta, a->A, a->K, a->M, a->lda, BK, BM);
+  else rc = make_map(&ta, a->A, a->M, a->K, a->lda, 64, BK);
+  if (rc) return rc;
+  if (!a->b_mn_major) rc = make_map(&tb, a->B, a->K, a->N, a->ldb, BK, BN2 / 2);
+  else rc = make_map(&tb, a->B, a->N, a->K, a->ldb, 64, BK);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    attr_set = true;
+  }
+  const int num_m = (a->M + 2 * BM - 1) / (2 * BM), num_n = (a->N + BN2 - 1) / BN2;
+  const int units = num_m * num_n * kp.split_k;
+  const int pairs = min(units, num_sms() / 2);
+  gemm_bf16_tcgen05_2cta_kernel<<<2 * pairs, GEMM_THREADS, SMEM2_BYTES, stream>>>(ta, tb, kp);
+  YMP_LAUNCH_CHECK();
+  return YMP_OK;
+}
+
 }  // namespace ymp
 
 extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
@@ -443,22 +632,28 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
                 "ymp_gemm: accumulate mode supports only alpha and bias-free linear epilogue");
   YMP_CHECK_ARG(a->res_row_mod >= 0 && a->d_row_block >= 0 && (a->d_row_block == 0 || a->d_row_stride >= a->d_row_block),
                 "ymp_gemm: bad res_row_mod / d_row_block / d_row_stride");
-  YMP_CHECK_ARG(a->tile_n == 0 || a->tile_n == 128 || a->tile_n == 256, "ymp_gemm: tile_n must be 0/128/256");
+  YMP_CHECK_ARG(a->tile_n == 0 || a->tile_n == 128 || a->tile_n == 256 || a->tile_n == 512,
+                "ymp_gemm: tile_n must be 0 (auto), 128, 256 (1-CTA tiles) or 512 (= 256x256 CTA-pair tile)");
 
   const int kb_total = (a->K + BK - 1) / BK;
   const int sms = num_sms();
   int bn = a->tile_n;
   if (bn == 0) {
-    // prefer the 128x256 tile unless it leaves most of the machine idle or N is narrow
+    // CTA-pair 256x256 tiles when there are enough of them to fill the machine; otherwise the
+    // 128x256 tile, or 128x128 when even that leaves most SMs idle or N is narrow
+    const long t2 = (long)((a->M + 2 * BM - 1) / (2 * BM)) * ((a->N + 255) / 256);
     const long t256 = (long)((a->M + BM - 1) / BM) * ((a->N + 255) / 256);
-    bn = (a->N <= 128 || (t256 < sms && a->split_k <= 1 && !a->accumulate)) ? 128 : 256;
+    if (a->N >= 256 && a->M >= 256 && (t2 >= sms || (a->accumulate && a->split_k != 1 && t2 * 4 >= sms / 2))) bn = 512;
+    else bn = (a->N <= 128 || (t256 < sms && a->split_k <= 1 && !a->accumulate)) ? 128 : 256;
   }
   int split = a->split_k;
   if (split <= 0) {
     split = 1;
     if (a->accumulate) {
-      const long tiles = (long)((a->M + BM - 1) / BM) * ((a->N + bn - 1) / bn);
-      while (tiles * split < 2L * sms && split * 8 <= kb_total) split *= 2;
+      const long tiles = bn == 512 ? (long)((a->M + 2 * BM - 1) / (2 * BM)) * ((a->N + 255) / 256)
+                                   : (long)((a->M + BM - 1) / BM) * ((a->N + bn - 1) / bn);
+      const long want = bn == 512 ? sms : 2L * sms;
+      while (tiles * split < want && split * 8 <= kb_total) split *= 2;
     }
   }
   YMP_CHECK_ARG(split == 1 || (a->accumulate && a->out_dtype == YMP_DT_F32), "ymp_gemm: split_k>1 needs accumulate=1 and fp32 output");
@@ -486,6 +681,7 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
   kp.v32_res = a->residual && al32(a->residual) && (a->ldr * 2) % 32 == 0;
   kp.v32_bias = a->bias && al32(a->bias);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (bn == 512) return launch_gemm_2cta(a, kp, st);
   if (bn == 256) return launch_gemm<256>(a, kp, st);
   return launch_gemm<128>(a, kp, st);
 }

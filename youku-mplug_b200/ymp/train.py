@@ -86,6 +86,7 @@ class TrainEngine:
         self.optimizer = _Optimizer(groups)
         self.micro_steps = 0
         self.global_steps = 0
+        self._graphs = {}
 
     # ---- nn.Module-like surface -----------------------------------------------------------
     def __call__(self, *args, **kwargs):
@@ -135,6 +136,47 @@ class TrainEngine:
                       max_grad_norm=self.clip_grad or 0.0, sumsq_t=self._sumsq if self.clip_grad else None)
         self.optimizer._global_grad_norm = _LazyNorm(self._sumsq.clone(), scale)
         self.flat_grad.zero_()
+
+    def train_step(self, video, text, use_graph=True, graph_warmup=2):
+        """One full iteration (forward + backward + step) and the loss tensor.
+
+        Shapes are static in pre-training (`padding='max_length'`, run_pretrain_distributed_gpt3.py:100),
+        so after `graph_warmup` eager iterations the ~900 kernel launches of forward+backward are
+        captured ONCE into a CUDA graph per input signature and replayed; the all-reduce and the
+        optimizer stay outside the graph.  Inputs are copied into the graph's static buffers (the copy
+        also casts fp32 frames to bf16), so callers may pass fresh tensors every step."""
+        key = (tuple(video.shape), tuple(text.input_ids.shape))
+        st = self._graphs.setdefault(key, dict(calls=0))
+        if not use_graph or st["calls"] < graph_warmup:
+            loss, _ = self.module(video, text)
+            self.backward(loss)
+            self.step()
+            st["calls"] += 1
+            return loss.detach()
+        if "graph" not in st:
+            from models.modeling_distributed_gpt3 import BatchEncoding
+            st["video"] = torch.empty(video.shape, device=video.device, dtype=torch.bfloat16)
+            st["ids"] = torch.empty_like(text.input_ids)
+            st["att"] = torch.empty_like(text.attention_mask)
+            st["video"].copy_(video)
+            st["ids"].copy_(text.input_ids)
+            st["att"].copy_(text.attention_mask)
+            static_text = BatchEncoding(dict(input_ids=st["ids"], attention_mask=st["att"]))
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                loss, _ = self.module(st["video"], static_text)
+                with YF.grad_sink(self._sink):
+                    loss.backward()
+            st["graph"], st["loss"] = g, loss.detach()
+        else:
+            st["video"].copy_(video, non_blocking=True)
+            st["ids"].copy_(text.input_ids, non_blocking=True)
+            st["att"].copy_(text.attention_mask, non_blocking=True)
+        st["graph"].replay()
+        self.micro_steps += 1
+        self.step()
+        return st["loss"]
 
     # ---- checkpointing (utils.py:476-480,441-455) ----------------------------------------------
     def save_checkpoint(self, save_dir, tag=None, client_state=None):
