@@ -48,6 +48,27 @@ __device__ __forceinline__ long rrow(const RSeq& r, int i) {
   return i < r.n_prefix ? r.prefix0 + i : r.base + (long)(i - r.n_prefix) * r.pos_stride;
 }
 
+// One operand matrix of one (sequence, head): element pointer of position i without any division
+// or 64-bit multiply chain on the load path.
+struct RMat {
+  const __nv_bfloat16* base;    // position n_prefix (first regular row), head/column offset applied
+  const __nv_bfloat16* prefix;  // position 0 when n_prefix > 0
+  long stride;                  // elements between consecutive regular positions
+  int ld, n_prefix;
+};
+__device__ __forceinline__ RMat rmat(const __nv_bfloat16* p, const RSeq& r, int ld, int col_off) {
+  RMat m;
+  m.base = p + r.base * ld + col_off;
+  m.prefix = p + r.prefix0 * ld + col_off;
+  m.stride = r.pos_stride * ld;
+  m.ld = ld;
+  m.n_prefix = r.n_prefix;
+  return m;
+}
+__device__ __forceinline__ const __nv_bfloat16* mrow(const RMat& m, int i) {
+  return i < m.n_prefix ? m.prefix + (long)i * m.ld : m.base + (long)(i - m.n_prefix) * m.stride;
+}
+
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -100,22 +121,43 @@ __device__ __forceinline__ void eff_len(const AttnKParams& p, int s, int& sq, in
     if (left < skv) skv = (int)left;
   }
 }
-__device__ __forceinline__ bool masked(const AttnKParams& p, int qi, int kj, int skv) {
-  if (kj >= skv) return true;
-  if (p.mask == MASK_CAUSAL) return kj > qi;
-  if (p.mask == MASK_BLOCK) return (qi / p.mask_block) != (kj / p.mask_block);
-  return false;
+// Warp-uniform test: does this 16-row x 64-col score tile need any masking at all?
+__device__ __forceinline__ bool tile_needs_mask(const AttnKParams& p, int row_lo, int col0, int skv) {
+  if (col0 + 64 > skv) return true;
+  if (p.mask == MASK_CAUSAL) return col0 + 63 > row_lo;
+  return p.mask == MASK_BLOCK;
+}
+// Set masked entries of a C-fragment tile to `fill`.  rows: row_lo + g (+8), cols: col0 + nb*8 + t4*2 (+1)
+__device__ __forceinline__ void apply_mask(const AttnKParams& p, float (&sc)[8][4], int row_lo, int col0, int skv,
+                                           int g, int t4, float fill) {
+  const int r0 = row_lo + g, r1 = r0 + 8;
+  int rb0 = 0, rb1 = 0;
+  if (p.mask == MASK_BLOCK) { rb0 = r0 / p.mask_block; rb1 = r1 / p.mask_block; }
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = col0 + nb * 8 + t4 * 2 + e;
+      bool m0 = col >= skv, m1 = m0;
+      if (p.mask == MASK_CAUSAL) { m0 |= col > r0; m1 |= col > r1; }
+      else if (p.mask == MASK_BLOCK) { const int cb = col / p.mask_block; m0 |= cb != rb0; m1 |= cb != rb1; }
+      if (m0) sc[nb][e] = fill;
+      if (m1) sc[nb][2 + e] = fill;
+    }
+  }
 }
 
 // Asynchronously load a [64 x D] bf16 tile (positions r0..r0+63 of the resolved sequence).
 template <int D>
-__device__ __forceinline__ void load_tile_async(__nv_bfloat16* dst, const __nv_bfloat16* src, const RSeq& m,
-                                                int r0, int n_valid, int ld, int col_off) {
+__device__ __forceinline__ void load_tile_async(__nv_bfloat16* dst, const RMat& m, int r0, int n_valid) {
   constexpr int CH = D / 8, LDS = D + 8;
-  for (int idx = threadIdx.x; idx < 64 * CH; idx += blockDim.x) {
+#pragma unroll
+  for (int it = 0; it < (64 * CH + 127) / 128; ++it) {
+    const int idx = threadIdx.x + it * 128;
+    if ((64 * CH) % 128 != 0 && idx >= 64 * CH) break;
     const int r = idx / CH, c = idx - r * CH;
     __nv_bfloat16* d = dst + r * LDS + c * 8;
-    if (r0 + r < n_valid) cp_async16(d, src + rrow(m, r0 + r) * ld + col_off + c * 8);
+    if (r0 + r < n_valid) cp_async16(d, mrow(m, r0 + r) + c * 8);
     else *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
   }
 }
@@ -133,7 +175,9 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
   int sq, skv;
   eff_len(p, s, sq, skv);
   if (q0 >= sq) return;
-  const RSeq mq = resolve(p.mq, s), mkv = resolve(p.mkv, s), mo = resolve(p.mo, s);
+  const RSeq mkv = resolve(p.mkv, s), mo = resolve(p.mo, s);
+  const RMat Mq = rmat(p.q, resolve(p.mq, s), p.ldq, h * p.hsq);
+  const RMat Mk = rmat(p.k, mkv, p.ldk, h * p.hsk), Mv = rmat(p.v, mkv, p.ldv, h * p.hsv);
 
   int kv_end = skv;
   if (p.mask == MASK_CAUSAL) kv_end = min(skv, q0 + 64);
@@ -144,9 +188,9 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
   }
   const int ntiles = (kv_end - kv_begin + 63) / 64;
 
-  load_tile_async<D>(Qs, p.q, mq, q0, sq, p.ldq, h * p.hsq);
-  load_tile_async<D>(KVs, p.k, mkv, kv_begin, skv, p.ldk, h * p.hsk);
-  load_tile_async<D>(KVs + TILE, p.v, mkv, kv_begin, skv, p.ldv, h * p.hsv);
+  load_tile_async<D>(Qs, Mq, q0, sq);
+  load_tile_async<D>(KVs, Mk, kv_begin, skv);
+  load_tile_async<D>(KVs + TILE, Mv, kv_begin, skv);
   cp_async_commit();
 
   uint32_t qf[KS][4];
@@ -162,8 +206,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
     __nv_bfloat16* Vs = Ks + TILE;
     if (t + 1 < ntiles) {
       __nv_bfloat16* Kn = KVs + ((t + 1) & 1) * 2 * TILE;
-      load_tile_async<D>(Kn, p.k, mkv, kv0 + 64, skv, p.ldk, h * p.hsk);
-      load_tile_async<D>(Kn + TILE, p.v, mkv, kv0 + 64, skv, p.ldv, h * p.hsv);
+      load_tile_async<D>(Kn, Mk, kv0 + 64, skv);
+      load_tile_async<D>(Kn + TILE, Mv, kv0 + 64, skv);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -194,27 +238,23 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
           }
         }
       }
+      // raw scores; the softmax scale is folded into one FFMA per element below
+      if (tile_needs_mask(p, q0 + warp * 16, kv0, skv))
+        apply_mask(p, sc, q0 + warp * 16, kv0, skv, g, t4, -CUDART_INF_F);
       float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int col = kv0 + nb * 8 + t4 * 2 + (e & 1);
-          const int row = q0 + warp * 16 + g + (e >> 1) * 8;
-          float v = sc[nb][e] * p.scale_log2;
-          if (masked(p, row, col, skv)) v = -CUDART_INF_F;
-          sc[nb][e] = v;
-          mx[e >> 1] = fmaxf(mx[e >> 1], v);
-        }
+        mx[0] = fmaxf(mx[0], fmaxf(sc[nb][0], sc[nb][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(sc[nb][2], sc[nb][3]));
       }
-      float alpha[2], msafe[2];
+      float alpha[2], ms[2];
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
         const float mnew = fmaxf(m_i[r], mx[r]);
-        msafe[r] = (mnew == -CUDART_INF_F) ? 0.f : mnew;
-        alpha[r] = exp2f(m_i[r] - msafe[r]);
+        ms[r] = (mnew == -CUDART_INF_F) ? 0.f : mnew * p.scale_log2;
+        alpha[r] = exp2f(m_i[r] * p.scale_log2 - ms[r]);
         m_i[r] = mnew;
         l_i[r] *= alpha[r];
       }
@@ -222,7 +262,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
       for (int nb = 0; nb < 8; ++nb) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float pv = exp2f(sc[nb][e] - msafe[e >> 1]);
+          const float pv = exp2f(fmaf(sc[nb][e], p.scale_log2, -ms[e >> 1]));
           sc[nb][e] = pv;
           l_i[e >> 1] += pv;
         }
@@ -269,7 +309,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
       *reinterpret_cast<uint32_t*>(orow + nb * 8 + t4 * 2) =
           pack_bf16(o_acc[nb][2 * r] * inv, o_acc[nb][2 * r + 1] * inv);
     if (p.lse && t4 == 0)
-      p.lse[((size_t)s * p.n_heads + h) * p.s_q + qi] = m_i[r] * 0.6931471805599453f + logf(l_i[r]);
+      p.lse[((size_t)s * p.n_heads + h) * p.s_q + qi] = m_i[r] * p.scale + logf(l_i[r]);
   }
 }
 
@@ -289,8 +329,9 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnKParams p) {
   int sq, skv;
   eff_len(p, s, sq, skv);
   if (q0 >= sq) return;
-  const RSeq mq = resolve(p.mq, s), mkv = resolve(p.mkv, s), mo = resolve(p.mo, s), mdo = resolve(p.mdo, s),
-             mdq = resolve(p.mdq, s);
+  const RSeq mkv = resolve(p.mkv, s), mo = resolve(p.mo, s), mdo = resolve(p.mdo, s), mdq = resolve(p.mdq, s);
+  const RMat Mq = rmat(p.q, resolve(p.mq, s), p.ldq, h * p.hsq), Mdo = rmat(p.dout, mdo, p.lddo, h * p.hsdo);
+  const RMat Mk = rmat(p.k, mkv, p.ldk, h * p.hsk), Mv = rmat(p.v, mkv, p.ldv, h * p.hsv);
   int kv_end = skv, kv_begin = 0;
   if (p.mask == MASK_CAUSAL) kv_end = min(skv, q0 + 64);
   if (p.mask == MASK_BLOCK) {
@@ -299,26 +340,30 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnKParams p) {
   }
   const int ntiles = (kv_end - kv_begin + 63) / 64;
 
-  load_tile_async<D>(Qs, p.q, mq, q0, sq, p.ldq, h * p.hsq);
-  load_tile_async<D>(dOs, p.dout, mdo, q0, sq, p.lddo, h * p.hsdo);
-  load_tile_async<D>(KVs, p.k, mkv, kv_begin, skv, p.ldk, h * p.hsk);
-  load_tile_async<D>(KVs + TILE, p.v, mkv, kv_begin, skv, p.ldv, h * p.hsv);
+  load_tile_async<D>(Qs, Mq, q0, sq);
+  load_tile_async<D>(dOs, Mdo, q0, sq);
+  load_tile_async<D>(KVs, Mk, kv_begin, skv);
+  load_tile_async<D>(KVs + TILE, Mv, kv_begin, skv);
   cp_async_commit();
-  // delta / lse for this warp's 16 rows, straight from global (O is not needed anywhere else)
-  for (int r = 0; r < 16; ++r) {
+  // delta / lse for this warp's 16 rows, straight from global (O is not needed anywhere else):
+  // lane -> (row = lane/2, half of the head dim = lane%2), all 16-byte loads independent
+  {
+    const int r = lane >> 1, hf = lane & 1;
     const int qi = q0 + warp * 16 + r;
     float acc = 0.f;
     if (qi < sq) {
-      const __nv_bfloat16* orow = p.o + rrow(mo, qi) * p.ldo + h * p.hso;
-      const __nv_bfloat16* drow = p.dout + rrow(mdo, qi) * p.lddo + h * p.hsdo;
-      for (int d = lane * 2; d < D; d += 64) {
-        const uint32_t a = *reinterpret_cast<const uint32_t*>(orow + d);
-        const uint32_t b = *reinterpret_cast<const uint32_t*>(drow + d);
-        acc += bf16_lo(a) * bf16_lo(b) + bf16_hi(a) * bf16_hi(b);
+      const uint4* orow = reinterpret_cast<const uint4*>(p.o + rrow(mo, qi) * p.ldo + h * p.hso + hf * (D / 2));
+      const uint4* drow = reinterpret_cast<const uint4*>(p.dout + rrow(mdo, qi) * p.lddo + h * p.hsdo + hf * (D / 2));
+#pragma unroll
+      for (int c = 0; c < D / 16; ++c) {
+        const uint4 a = __ldg(orow + c), b = __ldg(drow + c);
+        acc += bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) +
+               bf16_hi(a.y) * bf16_hi(b.y) + bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) +
+               bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
       }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (hf == 0) {
       const size_t li = ((size_t)s * p.n_heads + h) * p.s_q + qi;
       stat[64 + warp * 16 + r] = acc;
       stat[warp * 16 + r] = (qi < sq) ? p.lse[li] * 1.4426950408889634f : CUDART_INF_F;
@@ -339,8 +384,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnKParams p) {
     __nv_bfloat16* Vs = Ks + TILE;
     if (t + 1 < ntiles) {
       __nv_bfloat16* Kn = KVs + ((t + 1) & 1) * 2 * TILE;
-      load_tile_async<D>(Kn, p.k, mkv, kv0 + 64, skv, p.ldk, h * p.hsk);
-      load_tile_async<D>(Kn + TILE, p.v, mkv, kv0 + 64, skv, p.ldv, h * p.hsv);
+      load_tile_async<D>(Kn, Mk, kv0 + 64, skv);
+      load_tile_async<D>(Kn + TILE, Mv, kv0 + 64, skv);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -382,14 +427,13 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnKParams p) {
           }
         }
       }
+      if (tile_needs_mask(p, q0 + warp * 16, kv0, skv))
+        apply_mask(p, sc, q0 + warp * 16, kv0, skv, g, t4, -CUDART_INF_F);  // exp2(-inf) = 0
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int col = kv0 + nb * 8 + t4 * 2 + (e & 1);
-          const int row = q0 + warp * 16 + g + (e >> 1) * 8;
-          float pv = exp2f(sc[nb][e] * p.scale_log2 - lse_r[e >> 1]);
-          if (masked(p, row, col, skv)) pv = 0.f;
+          const float pv = exp2f(fmaf(sc[nb][e], p.scale_log2, -lse_r[e >> 1]));
           sc[nb][e] = pv * (dp[nb][e] - del_r[e >> 1]);  // dS
         }
       }
@@ -441,7 +485,9 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnKParams p)
   int sq, skv;
   eff_len(p, s, sq, skv);
   if (kv0 >= skv) return;
-  const RSeq mq = resolve(p.mq, s), mkv = resolve(p.mkv, s), mdo = resolve(p.mdo, s), mdkv = resolve(p.mdkv, s);
+  const RSeq mkv = resolve(p.mkv, s), mdkv = resolve(p.mdkv, s);
+  const RMat Mq = rmat(p.q, resolve(p.mq, s), p.ldq, h * p.hsq), Mdo = rmat(p.dout, resolve(p.mdo, s), p.lddo, h * p.hsdo);
+  const RMat Mk = rmat(p.k, mkv, p.ldk, h * p.hsk), Mv = rmat(p.v, mkv, p.ldv, h * p.hsv);
   int q_begin = 0, q_end = sq;
   if (p.mask == MASK_CAUSAL) q_begin = kv0;  // 64-aligned
   if (p.mask == MASK_BLOCK) {
@@ -453,8 +499,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnKParams p)
 
   auto load_stage = [&](int stage, int qi0) {
     __nv_bfloat16* Qn = QDs + stage * 2 * TILE;
-    load_tile_async<D>(Qn, p.q, mq, qi0, sq, p.ldq, h * p.hsq);
-    load_tile_async<D>(Qn + TILE, p.dout, mdo, qi0, sq, p.lddo, h * p.hsdo);
+    load_tile_async<D>(Qn, Mq, qi0, sq);
+    load_tile_async<D>(Qn + TILE, Mdo, qi0, sq);
     if (threadIdx.x < 64) {
       const int qi = qi0 + threadIdx.x;
       float* st = stat + stage * 128;
@@ -463,8 +509,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnKParams p)
     }
   };
 
-  load_tile_async<D>(Ks, p.k, mkv, kv0, skv, p.ldk, h * p.hsk);
-  load_tile_async<D>(Vs, p.v, mkv, kv0, skv, p.ldv, h * p.hsv);
+  load_tile_async<D>(Ks, Mk, kv0, skv);
+  load_tile_async<D>(Vs, Mv, kv0, skv);
   load_stage(0, q_begin);
   cp_async_commit();
 
@@ -520,14 +566,36 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnKParams p)
           }
         }
       }
+      {
+        // transposed tile: rows are keys, columns are queries
+        const int k_lo = kv0 + warp * 16;
+        bool need = (k_lo + 16 > skv);
+        if (p.mask == MASK_CAUSAL) need |= (k_lo + 15 > qi0);
+        if (p.mask == MASK_BLOCK) need = true;
+        if (need) {
+          const int k0 = k_lo + g, k1 = k0 + 8;
+          int kb0 = 0, kb1 = 0;
+          if (p.mask == MASK_BLOCK) { kb0 = k0 / p.mask_block; kb1 = k1 / p.mask_block; }
+#pragma unroll
+          for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int qc = qi0 + nb * 8 + t4 * 2 + e;
+              bool m0 = k0 >= skv, m1 = k1 >= skv;
+              if (p.mask == MASK_CAUSAL) { m0 |= k0 > qc; m1 |= k1 > qc; }
+              else if (p.mask == MASK_BLOCK) { const int qb = qc / p.mask_block; m0 |= qb != kb0; m1 |= qb != kb1; }
+              if (m0) st_[nb][e] = -CUDART_INF_F;
+              if (m1) st_[nb][2 + e] = -CUDART_INF_F;
+            }
+          }
+        }
+      }
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int kvr = kv0 + warp * 16 + g + (e >> 1) * 8;
           const int ql = nb * 8 + t4 * 2 + (e & 1);
-          float pv = exp2f(st_[nb][e] * p.scale_log2 - st[ql]);
-          if (masked(p, qi0 + ql, kvr, skv)) pv = 0.f;
+          const float pv = exp2f(fmaf(st_[nb][e], p.scale_log2, -st[ql]));  // lse=+inf for absent queries -> 0
           st_[nb][e] = pv;                              // P^T
           dpt[nb][e] = pv * (dpt[nb][e] - st[64 + ql]);  // dS^T
         }
