@@ -229,15 +229,28 @@ def run_ymp(args, rank, local_rank, world):
         e0.record()
         out = orig(a, b, **kw)
         e1.record()
-        rec.append((2.0 * M * N * K, e0, e1))
+        rec.append((2.0 * M * N * K, e0, e1, (M, N, K, int(bool(kw.get("a_t"))), int(bool(kw.get("b_t"))),
+                                              int(bool(kw.get("accumulate"))), int(kw.get("act", 0)),
+                                              int(kw.get("aux_out") is not None), int(kw.get("aux_in") is not None),
+                                              int(kw.get("residual") is not None))))
         return out
 
     ops.gemm = gemm_rec
     step_eager()
     torch.cuda.synchronize()
     ops.gemm = orig
-    gemm_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in rec)
-    gemm_flop = sum(f for f, _, _ in rec)
+    gemm_ms = sum(e0.elapsed_time(e1) for _, e0, e1, _ in rec)
+    gemm_flop = sum(f for f, _, _, _ in rec)
+    if args.gemm_report and rank == 0:
+        shapes = {}
+        for f, e0, e1, key in rec:
+            ent = shapes.setdefault(key, [0, 0.0, 0.0])
+            ent[0] += 1; ent[1] += e0.elapsed_time(e1); ent[2] += f
+        rows = sorted(([dict(M=k[0], N=k[1], K=k[2], a_t=k[3], b_t=k[4], acc=k[5], act=k[6], aux_out=k[7], aux_in=k[8],
+                             res=k[9], n=v[0], ms=v[1], tflops=v[2] / v[1] / 1e9) for k, v in shapes.items()]),
+                      key=lambda r: -r["ms"])
+        with open(args.gemm_report, "w") as fh:
+            json.dump(rows, fh, indent=1)
     pk = peaks()
     tf = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     ms_step = ms / args.steps
@@ -286,6 +299,7 @@ def main():
     ap.add_argument("--text-len", type=int, default=128)
     ap.add_argument("--queries", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-report", default=None, help="write per-shape GEMM timings of one step to this json file")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA graph replay)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

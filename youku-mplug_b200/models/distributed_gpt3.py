@@ -151,7 +151,7 @@ class DistributedGPT3_Pretrain(_PrefixModelBase):
                                                        self.visual_encoder.vcfg, self.text_decoder.config.engine_cfg(),
                                                        keys, *params)
             self.last_losses = losses
-            return loss_caption, torch.tensor(0.0, device=image.device)
+            return loss_caption, loss_caption.new_zeros(())   # device-side (CUDA-graph capturable)
 
         # ---- contrastive variant (:168-217): component path so that image_query is exposed
         _, image_embeds, image_query, query_features = self.visual_prefix(image)
