@@ -59,11 +59,37 @@ def bench():
             print("BENCH " + json.dumps(dict(impl=name, M=M, N=N, K=K, ms=ms, tflops=2 * M * N * K / ms / 1e9)))
 
 
+def ncu_shapes():
+    """A few hot-path GEMM launches (2 each) for `ncu --set full -k regex:gemm_bf16`."""
+    import torch
+    from ymp import ops
+    dev = "cuda"
+    a = torch.randn(50176, 768, device=dev).bfloat16()
+    w = torch.randn(2304, 768, device=dev).bfloat16()
+    for _ in range(2):
+        ops.gemm(a, w)                                         # ViT qkv forward
+    dy = torch.randn(50208, 768, device=dev).bfloat16()
+    w2 = torch.randn(768, 3072, device=dev).bfloat16()
+    pre = torch.randn(50208, 3072, device=dev).bfloat16()
+    for _ in range(2):
+        ops.gemm(dy, w2, b_t=True, act=1, aux_in=pre)         # fc2 dgrad with GELU'(erf) epilogue
+    x = torch.randn(8192, 2048, device=dev).bfloat16()
+    w3 = torch.randn(8192, 2048, device=dev).bfloat16()
+    for _ in range(2):
+        ops.gemm(x, w3)                                        # GPT h->4h
+    g = torch.zeros(768, 768, device=dev)
+    for _ in range(2):
+        ops.gemm(dy[:50176], a, a_t=True, b_t=True, out=g, accumulate=True)   # wgrad, split-K atomics
+    torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "case":
         one(CASES[int(sys.argv[2])])
     elif len(sys.argv) > 1 and sys.argv[1] == "bench":
         bench()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ncu":
+        ncu_shapes()
     else:
         for i in range(len(CASES)):
             try:

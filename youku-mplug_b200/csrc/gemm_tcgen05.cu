@@ -100,8 +100,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
   const int drow = p.d_row_block ? (row / p.d_row_block) * p.d_row_stride + row % p.d_row_block : row;
   const int rrow = p.res_row_mod ? row % p.res_row_mod : row;
   float v[32];
+  if (p.alpha == 1.0f) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+  }
 
   if (full) {
     if (p.bias) {
@@ -119,17 +124,26 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
       store16(p.aux_out + off, p.v32_aux, v);
       store16(p.aux_out + off + 16, p.v32_aux, v + 16);
     }
+    // activation switches are hoisted out of the element loops (warp-uniform branches)
     if (p.aux_in) {
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float a[16];
         load16(p.aux_in + off + 16 * hh, p.v32_aux, a);
+        if (p.act == YMP_ACT_GELU_ERF) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[16 * hh + i] *= apply_dact(a[i], p.act);
+          for (int i = 0; i < 16; ++i) v[16 * hh + i] *= dgelu_erf(a[i]);
+        } else if (p.act == YMP_ACT_GELU_TANH) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[16 * hh + i] *= dgelu_tanh(a[i]);
+        }
       }
-    } else if (p.act != YMP_ACT_NONE) {
+    } else if (p.act == YMP_ACT_GELU_ERF) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    } else if (p.act == YMP_ACT_GELU_TANH) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
     }
     if (p.residual) {
       const __nv_bfloat16* rp = p.residual + (size_t)rrow * p.ldr + col0;
@@ -643,7 +657,7 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
     // 128x256 tile, or 128x128 when even that leaves most SMs idle or N is narrow
     const long t2 = (long)((a->M + 2 * BM - 1) / (2 * BM)) * ((a->N + 255) / 256);
     const long t256 = (long)((a->M + BM - 1) / BM) * ((a->N + 255) / 256);
-    if (a->N >= 256 && a->M >= 256 && (t2 >= sms || (a->accumulate && a->split_k != 1 && t2 * 4 >= sms / 2))) bn = 512;
+    if (a->N >= 256 && a->M >= 256 && (t2 >= sms || (a->accumulate && a->split_k != 1))) bn = 512;
     else bn = (a->N <= 128 || (t256 < sms && a->split_k <= 1 && !a->accumulate)) ? 128 : 256;
   }
   int split = a->split_k;

@@ -234,14 +234,26 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// exact-erf GELU (nn.GELU default) and its derivative
+// exact-erf GELU (nn.GELU default) and its derivative.  erf(x/sqrt2) by Abramowitz-Stegun 7.1.26
+// (|err| < 1.5e-7); its exponential exp(-x^2/2) is the same one the normal pdf needs, so the
+// derivative costs one MUFU.EX2 + one MUFU.RCP in total.
+__device__ __forceinline__ float norm_cdf_pdf(float x, float& e) {
+  const float ax = fabsf(x) * 0.70710678118f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  e = exp2f(-0.72134752044f * x * x);  // exp(-x^2/2)
+  const float poly =
+      fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
+  const float half_tail = 0.5f * poly * e;            // 0.5 * (1 - erf(|x|/sqrt2))
+  return x >= 0.f ? 1.0f - half_tail : half_tail;     // Phi(x)
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118f));
+  float e;
+  return x * norm_cdf_pdf(x, e);
 }
 __device__ __forceinline__ float dgelu_erf(float x) {
-  float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118f));
-  float pdf = 0.3989422804f * __expf(-0.5f * x * x);
-  return fmaf(x, pdf, cdf);
+  float e;
+  const float cdf = norm_cdf_pdf(x, e);
+  return fmaf(x * 0.3989422804f, e, cdf);
 }
 // tanh-approximation GELU (Megatron bias_gelu) and its derivative
 __device__ __forceinline__ float gelu_tanh(float x) {
