@@ -53,10 +53,11 @@ uint64_t ymp_launch_count(void);
  *   All leading dimensions must be multiples of 8 elements and base pointers 16-byte aligned.
  * Epilogue, applied in this order to v = alpha * acc:
  *   v += bias[n]                         (bias: bf16 [N], optional)
- *   if aux_out: aux_out[m,n] = bf16(v)   (pre-activation saved for backward, ld = ldd)
- *   v = act(v)                           (YMP_ACT_*)
- *   if aux_in:  v *= act'(aux_in[m,n])   (backward of an activation; act selects which GELU;
- *                                          with aux_in set, act() itself is NOT applied)
+ *   if aux_out: aux_out[m,n] = bf16(act'(v)) when act != NONE (what the backward pass multiplies by),
+ *                            = bf16(v)       when act == NONE                       (ld = ldd)
+ *   v = act(v)                           (YMP_ACT_*; skipped when aux_in is set)
+ *   if aux_in:  v *= aux_in[m,n]         (backward of an activation: aux_in is the act' saved above,
+ *                                          so the backward epilogue needs no transcendental)
  *   v += residual[m,n]                   (bf16 [M,N], row stride ldr, optional)
  *   D[m,n] = v  (bf16 or fp32) ; or atomically D[m,n] += v (fp32, accumulate=1, used by split-K)
  * ------------------------------------------------------------------------------------------ */
@@ -78,8 +79,8 @@ typedef struct ymp_gemm_args {
   const void* residual; /* bf16 [M,N] or NULL */
   int32_t ldr;
   int32_t act;          /* YMP_ACT_* */
-  void* aux_out;        /* bf16 [M,N] (ld = ldd) or NULL */
-  const void* aux_in;   /* bf16 [M,N] (ld = ldd) or NULL */
+  void* aux_out;        /* bf16 [M,N] (ld = ldd) or NULL: act'(pre-activation) (or the value if act=NONE) */
+  const void* aux_in;   /* bf16 [M,N] (ld = ldd) or NULL: element-wise multiplier */
   int32_t out_dtype;    /* YMP_DT_BF16 | YMP_DT_F32 */
   int32_t accumulate;   /* 1: D (fp32) += result using atomics */
   int32_t split_k;      /* >=1; >1 requires accumulate=1 and out_dtype=F32; 0 = library picks */

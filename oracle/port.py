@@ -326,3 +326,64 @@ VCFG_TINY = dict(img_size=32, patch_size=16, embed_dim=192, depth=2, num_heads=2
 GCFG_TINY = dict(vocab_size=512, hidden_size=128, ffn_hidden_size=512, num_hidden_layers=2,
                  num_attention_heads=2, max_position_embeddings=64, layernorm_epsilon=1e-5,
                  init_method_std=0.02)
+
+
+# ------------------------------------------------------------------------------------------
+# Downstream forwards, restated on the same primitives
+# ------------------------------------------------------------------------------------------
+def visual_prefix(video, sd, vcfg):
+    """image -> (pooled cls feature, image_embeds, image_query, query_features)
+    (models/distributed_gpt3.py:532-537 and the identical preambles of the other task models)."""
+    image_embeds = timesformer(video, sd, vcfg)
+    B = video.shape[0]
+    image_query = attention_pool(sd["learnable_queries"].expand(B, -1, -1), image_embeds, sd, vcfg["num_heads"])
+    query_features = F.linear(image_query, sd["visual_fc.weight"], sd["visual_fc.bias"])
+    return image_embeds[:, 0], image_embeds, image_query, query_features
+
+
+def prefix_decoder_pass(query_features, input_ids, attention_mask, prompt_lengths, sd, gcfg):
+    """Decoder over [prefix | text] with prompt tokens masked out of the loss
+    (models/distributed_gpt3.py:540-567).  Returns dict(loss, losses [B,S-1], loss_mask, hidden)."""
+    Q = query_features.shape[1]
+    att = attention_mask.clone()
+    text_loss_atts = att[:, 1:].clone()
+    if prompt_lengths is not None:
+        for i, ln in enumerate(prompt_lengths.tolist()):
+            text_loss_atts[i, :ln] = 0
+    targets, _ = build_targets(input_ids, att, Q)
+    loss_mask = torch.cat([torch.zeros((att.shape[0], Q), dtype=torch.long), text_loss_atts], dim=1)
+    emb_w = sd[GPT_PRE + "embedding.word_embeddings.weight"]
+    hidden = gpt3_decoder(torch.cat([query_features, emb_w[input_ids]], dim=1), sd, gcfg)
+    logits, losses = lm_head_losses(hidden, emb_w, targets)
+    return dict(loss=masked_mean_loss(losses, loss_mask), losses=losses[:, :-1], loss_mask=loss_mask, hidden=hidden,
+                logits=logits)
+
+
+def cls_eval_scores(query_features, input_ids, attention_mask, prompt_lengths, sd, gcfg, num_cls):
+    """DistributedGPT3_Cls eval branch - models/distributed_gpt3.py:598-625: prefix repeated per class,
+    generation_logits = softmax(-sum(losses * loss_mask))."""
+    B, Q, H = query_features.shape
+    qf = query_features.unsqueeze(1).repeat(1, num_cls, 1, 1).reshape(B * num_cls, Q, H)
+    out = prefix_decoder_pass(qf, input_ids, attention_mask, prompt_lengths, sd, gcfg)
+    return (-(out["losses"] * out["loss_mask"]).sum(-1)).view(B, num_cls).softmax(-1)
+
+
+def retrieval_features(video, input_ids, attention_mask, sd, vcfg, gcfg):
+    """DistributedGPT3_Retrieval.extract_{vision,text}_feature - models/distributed_gpt3.py:909-945:
+    CLS-pooled ViT feature -> vision_proj -> L2 ; GPT hidden at the last valid token -> text_proj -> L2."""
+    pooled = timesformer(video, sd, vcfg)[:, 0]
+    vfeat = F.normalize(F.linear(pooled, sd["vision_proj.weight"], sd["vision_proj.bias"]), dim=-1)
+    emb_w = sd[GPT_PRE + "embedding.word_embeddings.weight"]
+    hidden = gpt3_decoder(emb_w[input_ids], sd, gcfg)
+    last = hidden[torch.arange(hidden.shape[0]), attention_mask.sum(-1) - 1]
+    tfeat = F.normalize(F.linear(last, sd["text_proj.weight"], sd["text_proj.bias"]), dim=-1)
+    return vfeat, tfeat
+
+
+def retrieval_loss(vfeat, tfeat, idx, temp):
+    """models/distributed_gpt3.py:966-980 (single process: the gathered features are the local ones)."""
+    sim_i2t = vfeat @ tfeat.t() / temp
+    sim_t2i = tfeat @ vfeat.t() / temp
+    pos = torch.eq(idx.view(-1, 1), idx.view(1, -1)).float()
+    tgt = pos / pos.sum(1, keepdim=True)
+    return (-(F.log_softmax(sim_i2t, 1) * tgt).sum(1).mean() - (F.log_softmax(sim_t2i, 1) * tgt).sum(1).mean()) / 2

@@ -1,0 +1,112 @@
+"""GPU: the downstream task models on the B200 kernels against the
+oracle composed from the same reference-pinned primitives (oracle/port.py)."""
+import pytest
+import torch
+
+from oracle import port
+from oracle.make_golden import make_inputs
+from helpers import build_pretrain
+
+pytestmark = pytest.mark.gpu
+VC, GC, Q = port.VCFG_TINY, port.GCFG_TINY, 8
+
+
+def _rel(a, b):
+    return ((a.float().cpu() - b.float().cpu()).abs().max() / (b.float().abs().max() + 1e-12)).item()
+
+
+def _enc(dev, **kw):
+    import models.modeling_distributed_gpt3 as G
+    return G.BatchEncoding({k: v.to(dev) for k, v in kw.items()})
+
+
+def _sd(extra=None, seed=21):
+    sd = port.init_state_dict(VC, GC, Q, seed=seed, randomize=True)
+    g = torch.Generator().manual_seed(seed + 1)
+    for k, shape in (extra or {}).items():
+        sd[k] = 0.05 * torch.randn(shape, generator=g)
+    return sd
+
+
+def test_cls_train_and_eval(cuda):
+    sd = _sd({"cls_head.0.weight": (128, 128), "cls_head.0.bias": (128,), "cls_head.2.weight": (5, 128), "cls_head.2.bias": (5,)})
+    m = build_pretrain(VC, GC, Q, sd=sd, device=cuda, dtype=torch.bfloat16, cls_name="DistributedGPT3_Cls",
+                       num_frames=VC["num_frames"], use_cls=True, num_classes=5)
+    B, L, ncls = 2, 8, 3
+    video, ids, att = make_inputs(B, VC, L, GC["vocab_size"], 31)
+    pl = torch.tensor([2, 3])
+    rsd = {k: v.bfloat16().float() for k, v in sd.items()}
+    _, _, _, qf = port.visual_prefix(video.bfloat16().float(), rsd, VC)
+    # ---- training branch: generation loss with the prompt masked + cls_head CE on the prompt pass
+    _, pids, patt = make_inputs(B, VC, L, GC["vocab_size"], 32)
+    labels = torch.tensor([1, 4])
+    loss_cap, loss_cls = m(video.to(cuda).bfloat16(), _enc(cuda, input_ids=ids, attention_mask=att, prompt_lengths=pl),
+                           _enc(cuda, input_ids=pids, attention_mask=patt), labels.to(cuda), train=True)
+    ref = port.prefix_decoder_pass(qf, ids, att, pl, rsd, GC)
+    assert abs(loss_cap.item() - ref["loss"].item()) < 1e-2 * ref["loss"].item()
+    refp = port.prefix_decoder_pass(qf, pids, patt, None, rsd, GC)
+    pooled = refp["hidden"][torch.arange(B), Q + patt.sum(-1) - 1]
+    h = torch.relu(torch.nn.functional.linear(pooled, rsd["cls_head.0.weight"], rsd["cls_head.0.bias"]))
+    ref_cls = torch.nn.functional.cross_entropy(torch.nn.functional.linear(h, rsd["cls_head.2.weight"], rsd["cls_head.2.bias"]), labels)
+    assert abs(loss_cls.item() - ref_cls.item()) < 3e-2 * ref_cls.item()
+    (loss_cap + loss_cls).backward()
+    assert m.cls_head[0].weight.grad is not None and m.visual_fc.weight.grad is not None
+    # ---- eval branch: num_cls prompts per video
+    _, cids, catt = make_inputs(B * ncls, VC, L, GC["vocab_size"], 33)
+    cpl = torch.randint(1, 4, (B * ncls,), generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        gen, cls_logits = m(video.to(cuda).bfloat16(), _enc(cuda, input_ids=cids, attention_mask=catt, prompt_lengths=cpl),
+                            _enc(cuda, input_ids=pids, attention_mask=patt), train=False)
+    ref_gen = port.cls_eval_scores(qf, cids, catt, cpl, rsd, GC, ncls)
+    assert gen.shape == (B, ncls) and cls_logits.shape == (B, 5)
+    assert _rel(gen, ref_gen) < 3e-2
+
+
+def test_retrieval_features_and_loss(cuda):
+    sd = _sd({"vision_proj.weight": (32, 192), "vision_proj.bias": (32,), "text_proj.weight": (32, 128),
+              "text_proj.bias": (32,)})
+    sd["temp"] = torch.tensor(0.07)
+    m = build_pretrain(VC, GC, Q, sd=sd, device=cuda, dtype=torch.bfloat16, cls_name="DistributedGPT3_Retrieval",
+                       num_frames=VC["num_frames"], contrastive_embed_dim=32)
+    B, L = 3, 8
+    video, ids, att = make_inputs(B, VC, L, GC["vocab_size"], 41)
+    idx = torch.tensor([7, 9, 7])
+    rsd = {k: v.bfloat16().float() for k, v in sd.items()}
+    rv, rt = port.retrieval_features(video.bfloat16().float(), ids, att, rsd, VC, GC)
+    text = _enc(cuda, input_ids=ids, attention_mask=att)
+    with torch.no_grad():
+        v = m.extract_vision_feature(video.to(cuda).bfloat16())
+        t = m.extract_text_feature(text)
+    assert _rel(v, rv) < 2e-2 and _rel(t, rt) < 2e-2
+    loss = m(video.to(cuda).bfloat16(), text, idx.to(cuda))
+    ref = port.retrieval_loss(rv, rt, idx, 0.07)
+    assert abs(loss.item() - ref.item()) < 3e-2 * abs(ref.item())
+    loss.backward()
+    assert m.vision_proj.weight.grad is not None and m.visual_encoder.cls_token.grad is not None
+    assert all(p.grad is None for p in m.text_decoder.parameters())
+
+
+def test_retrieval_cls_shapes_and_negatives(cuda):
+    sd = _sd({"cls_head.0.weight": (128, 128), "cls_head.0.bias": (128,), "cls_head.2.weight": (2, 128), "cls_head.2.bias": (2,)})
+    m = build_pretrain(VC, GC, Q, sd=sd, device=cuda, dtype=torch.bfloat16, cls_name="DistributedGPT3_Retrieval_Cls",
+                       num_frames=VC["num_frames"], use_cls=True)
+    B, L = 2, 8
+    video, _, _ = make_inputs(B, VC, L, GC["vocab_size"], 51)
+    _, ids, att = make_inputs(2 * B, VC, L, GC["vocab_size"], 52)       # positives then negatives
+    pl = torch.tensor([2, 2, 3, 1])
+    neg = torch.tensor([1, 0])
+    labels = torch.tensor([1, 1, 0, 0])
+    text = _enc(cuda, input_ids=ids, attention_mask=att, prompt_lengths=pl)
+    prompt = _enc(cuda, input_ids=ids, attention_mask=att)
+    lc, lcls = m(video.to(cuda).bfloat16(), text, prompt, neg.to(cuda), labels.to(cuda), train=True)
+    rsd = {k: v.bfloat16().float() for k, v in sd.items()}
+    _, _, _, qf = port.visual_prefix(video.bfloat16().float(), rsd, VC)
+    ref = port.prefix_decoder_pass(torch.cat([qf, qf[neg]], 0), ids, att, pl, rsd, GC)
+    assert abs(lc.item() - ref["loss"].item()) < 1e-2 * ref["loss"].item()
+    assert torch.isfinite(lcls)
+    with torch.no_grad():
+        gen, cls = m(video.to(cuda).bfloat16(), text, prompt, train=False)
+    assert gen.shape == (B, 2) and cls.shape == (B, 2)
+    ref_eval = port.prefix_decoder_pass(qf.repeat_interleave(2, 0), ids, att, pl, rsd, GC)
+    ref_gen = (-(ref_eval["losses"] * ref_eval["loss_mask"]).sum(-1)).view(B, 2)
+    assert _rel(gen, ref_gen) < 2e-2

@@ -5,31 +5,33 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _dact(x, act):
+    if act == 1:
+        return 0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * torch.pi) ** 0.5
+    if act == 2:
+        u = 0.79788456 * x * (1 + 0.044715 * x * x)
+        t = torch.tanh(u)
+        return 0.5 * (1 + t) + 0.5 * x * (1 - t * t) * 0.79788456 * (1 + 3 * 0.044715 * x * x)
+    return torch.ones_like(x)
+
+
 def _ref(a, b, a_t, b_t, bias=None, residual=None, act=0, aux_in=None, alpha=1.0):
+    """Returns (D, aux_out) where aux_out = act'(pre-activation) when act != 0, else the pre-activation."""
     A = a.float().t() if a_t else a.float()
     B = b.float() if b_t else b.float().t()
     v = alpha * (A @ B)
     if bias is not None:
         v = v + bias.float()
-    pre = v
+    aux = _dact(v, act) if act else v
     if aux_in is not None:
-        x = aux_in.float()
-        if act == 1:
-            g = 0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * torch.pi) ** 0.5
-        elif act == 2:
-            u = 0.79788456 * x * (1 + 0.044715 * x * x)
-            t = torch.tanh(u)
-            g = 0.5 * (1 + t) + 0.5 * x * (1 - t * t) * 0.79788456 * (1 + 3 * 0.044715 * x * x)
-        else:
-            g = torch.ones_like(x)
-        v = v * g
+        v = v * aux_in.float()
     elif act == 1:
         v = torch.nn.functional.gelu(v)
     elif act == 2:
         v = torch.nn.functional.gelu(v, approximate="tanh")
     if residual is not None:
         v = v + residual.float()
-    return v, pre
+    return v, aux
 
 
 def _close(out, ref, tol=2e-2):
@@ -69,16 +71,17 @@ def test_gemm_epilogue_fwd(cuda, act, tile_n):
     _close(aux, pre)
 
 
-@pytest.mark.parametrize("act", [1, 2])
-def test_gemm_epilogue_dact(cuda, act):
+@pytest.mark.parametrize("tile_n", [0, 512])
+def test_gemm_epilogue_multiplier(cuda, tile_n):
+    """Backward of an activation: D = (dY @ W) * aux_in, aux_in = act'(pre) saved by the forward GEMM."""
     from ymp import ops
     torch.manual_seed(2)
     M, N, K = 256, 512, 320
     a = torch.randn(M, K, device=cuda).bfloat16()
     b = (torch.randn(K, N, device=cuda) * 0.1).bfloat16()
-    pre = torch.randn(M, N, device=cuda).bfloat16()
-    out = ops.gemm(a, b, b_t=True, act=act, aux_in=pre)
-    ref, _ = _ref(a, b, False, True, act=act, aux_in=pre)
+    mul = torch.randn(M, N, device=cuda).bfloat16()
+    out = ops.gemm(a, b, b_t=True, act=1, aux_in=mul, tile_n=tile_n)
+    ref, _ = _ref(a, b, False, True, aux_in=mul)
     _close(out, ref)
 
 

@@ -32,6 +32,7 @@ struct GemmKParams {
   int kb_per_split;
   int res_row_mod;                 // residual row = row % res_row_mod (0: plain)
   int d_row_block, d_row_stride;   // D row = (row / block) * stride + row % block (0: plain)
+  int n_fast;                      // tile order: consecutive units walk N first (A streamed once) or M first
   bool v32_d, v32_aux, v32_res, v32_bias;  // 32-byte aligned -> 256-bit accesses
   float alpha;
 };
@@ -44,17 +45,6 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512 (power of two)
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 256 + 1024;
 };
-
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == YMP_ACT_GELU_ERF) return gelu_erf(v);
-  if (act == YMP_ACT_GELU_TANH) return gelu_tanh(v);
-  return v;
-}
-__device__ __forceinline__ float apply_dact(float x, int act) {
-  if (act == YMP_ACT_GELU_ERF) return dgelu_erf(x);
-  if (act == YMP_ACT_GELU_TANH) return dgelu_tanh(x);
-  return 1.0f;
-}
 
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per thread per
 // instruction, so the row-per-thread epilogue writes whole sectors instead of half sectors.
@@ -120,30 +110,41 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
     }
     const size_t off = (size_t)row * p.ldd + col0;          // aux tensors: plain rows
     const size_t doff = (size_t)drow * p.ldd + col0;        // D: optionally re-blocked rows
-    if (p.aux_out) {
-      store16(p.aux_out + off, p.v32_aux, v);
-      store16(p.aux_out + off + 16, p.v32_aux, v + 16);
-    }
-    // activation switches are hoisted out of the element loops (warp-uniform branches)
+    // aux_out: with an activation it receives act'(v) (what the backward epilogue multiplies by),
+    // without one the value itself.  aux_in: a plain multiplier.  Switches are warp-uniform.
     if (p.aux_in) {
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float a[16];
         load16(p.aux_in + off + 16 * hh, p.v32_aux, a);
-        if (p.act == YMP_ACT_GELU_ERF) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[16 * hh + i] *= dgelu_erf(a[i]);
-        } else if (p.act == YMP_ACT_GELU_TANH) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[16 * hh + i] *= dgelu_tanh(a[i]);
-        }
+        for (int i = 0; i < 16; ++i) v[16 * hh + i] *= a[i];
       }
     } else if (p.act == YMP_ACT_GELU_ERF) {
+      if (p.aux_out) {
+        float d[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf_both(v[i], d[i]);
+        store16(p.aux_out + off, p.v32_aux, d);
+        store16(p.aux_out + off + 16, p.v32_aux, d + 16);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+      }
     } else if (p.act == YMP_ACT_GELU_TANH) {
+      if (p.aux_out) {
+        float d[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+        for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_both(v[i], d[i]);
+        store16(p.aux_out + off, p.v32_aux, d);
+        store16(p.aux_out + off + 16, p.v32_aux, d + 16);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
+      }
+    } else if (p.aux_out) {
+      store16(p.aux_out + off, p.v32_aux, v);
+      store16(p.aux_out + off + 16, p.v32_aux, v + 16);
     }
     if (p.residual) {
       const __nv_bfloat16* rp = p.residual + (size_t)rrow * p.ldr + col0;
@@ -192,9 +193,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
         float x = v[i];
         if (p.bias) x += __bfloat162float(p.bias[col]);
         const size_t off = (size_t)row * p.ldd + col, doff = (size_t)drow * p.ldd + col;
-        if (p.aux_out) p.aux_out[off] = __float2bfloat16(x);
-        if (p.aux_in) x *= apply_dact(__bfloat162float(p.aux_in[off]), p.act);
-        else x = apply_act(x, p.act);
+        if (p.aux_in) {
+          x *= __bfloat162float(p.aux_in[off]);
+        } else if (p.act == YMP_ACT_GELU_ERF) {
+          float d; x = gelu_erf_both(x, d);
+          if (p.aux_out) p.aux_out[off] = __float2bfloat16(d);
+        } else if (p.act == YMP_ACT_GELU_TANH) {
+          float d; x = gelu_tanh_both(x, d);
+          if (p.aux_out) p.aux_out[off] = __float2bfloat16(d);
+        } else if (p.aux_out) {
+          p.aux_out[off] = __float2bfloat16(x);
+        }
         if (p.residual) x += __bfloat162float(p.residual[(size_t)rrow * p.ldr + col]);
         if (!p.out_f32) reinterpret_cast<__nv_bfloat16*>(p.D)[doff] = __float2bfloat16(x);
         else if (!p.accumulate) reinterpret_cast<float*>(p.D)[doff] = x;
@@ -261,8 +270,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
         const int ks = u % p.split_k;
         const int t = u / p.split_k;
-        const int m_blk = t % num_m;
-        const int n_blk = t / num_m;
+        const int m_blk = p.n_fast ? t / num_n : t % num_m;
+        const int n_blk = p.n_fast ? t % num_n : t / num_m;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -337,8 +346,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     uint32_t aphase = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       const int t = u / p.split_k;
-      const int m_blk = t % num_m;
-      const int n_blk = t / num_m;
+      const int m_blk = p.n_fast ? t / num_n : t % num_m;
+      const int n_blk = p.n_fast ? t % num_n : t / num_m;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int row = m_blk * BM + q * 32 + lane;
@@ -434,8 +443,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
       for (int u = pair; u < num_units; u += num_pairs) {
         const int ks = u % p.split_k;
         const int t = u / p.split_k;
-        const int m0 = (t % num_m) * 2 * BM + (int)rank * BM;
-        const int n0 = (t / num_m) * BN2 + (int)rank * (BN2 / 2);
+        const int m0 = (p.n_fast ? t / num_n : t % num_m) * 2 * BM + (int)rank * BM;
+        const int n0 = (p.n_fast ? t % num_n : t / num_m) * BN2 + (int)rank * (BN2 / 2);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -505,8 +514,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
     uint32_t aphase = 0;
     for (int u = pair; u < num_units; u += num_pairs) {
       const int t = u / p.split_k;
-      const int m0 = (t % num_m) * 2 * BM + (int)rank * BM;
-      const int n_blk = t / num_m;
+      const int m0 = (p.n_fast ? t / num_n : t % num_m) * 2 * BM + (int)rank * BM;
+      const int n_blk = p.n_fast ? t % num_n : t / num_m;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
@@ -687,6 +696,8 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
   kp.act = a->act; kp.out_f32 = (a->out_dtype == YMP_DT_F32); kp.accumulate = a->accumulate ? 1 : 0;
   kp.split_k = split; kp.kb_per_split = per;
   kp.alpha = a->alpha;
+  // keep the larger operand streaming once from HBM: the smaller one is the re-read (L2-resident) side
+  kp.n_fast = ((long)a->M >= (long)a->N) ? 1 : 0;
   kp.res_row_mod = a->res_row_mod; kp.d_row_block = a->d_row_block; kp.d_row_stride = a->d_row_stride;
   auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
   const int esz = kp.out_f32 ? 4 : 2;

@@ -250,6 +250,22 @@ __device__ __forceinline__ float gelu_erf(float x) {
   float e;
   return x * norm_cdf_pdf(x, e);
 }
+// GELU and its derivative together (the derivative is what backward needs; it is stored in bf16 by the
+// forward epilogue so that the backward epilogue is a plain multiply)
+__device__ __forceinline__ float gelu_erf_both(float x, float& d) {
+  float e;
+  const float cdf = norm_cdf_pdf(x, e);
+  d = fmaf(x * 0.3989422804f, e, cdf);
+  return x * cdf;
+}
+__device__ __forceinline__ float gelu_tanh_both(float x, float& d) {
+  const float u = 0.79788456f * x * fmaf(0.044715f * x, x, 1.0f);
+  const float t = tanh_fast(u);
+  const float du = 0.79788456f * fmaf(0.134145f * x, x, 1.0f);
+  const float hp = 0.5f * (1.0f + t);
+  d = fmaf(0.5f * x * (1.0f - t * t), du, hp);
+  return x * hp;
+}
 __device__ __forceinline__ float dgelu_erf(float x) {
   float e;
   const float cdf = norm_cdf_pdf(x, e);

@@ -187,11 +187,14 @@ class DistributedGPT3_Caption(_PrefixModelBase):
         self._build(config, tokenizer, config.get('num_frames', None))
 
     def forward(self, image, text=None):
+        """Caption loss over [prefix | prompt+caption]; prompt tokens (text.prompt_lengths, :760-766) carry
+        no loss."""
         _, _, _, query_features = self.visual_prefix(image)
         Q = query_features.shape[1]
         text_loss_atts = text.attention_mask[:, 1:].clone()
-        if self.prompt != "":
-            for i, ln in enumerate(text.prompt_lengths.tolist()):
+        prompt_lengths = getattr(text, "prompt_lengths", None)
+        if prompt_lengths is not None:
+            for i, ln in enumerate(prompt_lengths.cpu().tolist()):
                 text_loss_atts[i, :ln] = 0
         targets, loss_mask = build_targets(text.input_ids, text_loss_atts, Q)
         input_embeds = torch.cat([query_features, self._word_embedding()(text.input_ids).to(query_features.dtype)], dim=1)
@@ -201,9 +204,40 @@ class DistributedGPT3_Caption(_PrefixModelBase):
         raise NotImplementedError("generation (KV-cache beam search) is SURVEY.md section 8f row N2")
 
 
-class DistributedGPT3_Cls(_PrefixModelBase):
-    """Video category prediction (:431-657).  Training: caption-style loss on [prompt+label] (+
-    optional cls_head); eval: every class prompt scored by softmax(-sum(losses * mask))."""
+class _PromptClsBase(_PrefixModelBase):
+    """Shared forward pieces of DistributedGPT3_Cls (:431-657) and DistributedGPT3_Retrieval_Cls (:988-1218):
+    a caption-style generation loss over `text` ([prompt+answer] pairs, prompt tokens masked out of the
+    loss via text.prompt_lengths) and an optional cls_head on the decoder state at the last valid token of
+    `prompt_text`."""
+
+    def _gen_pass(self, query_features, text):
+        """Decoder pass over [visual prefix | text]; returns (outputs, loss_mask [B, S-1])."""
+        Q = query_features.shape[1]
+        text_loss_atts = text.attention_mask[:, 1:].clone()
+        for i, ln in enumerate(text.prompt_lengths.cpu().tolist()):
+            text_loss_atts[i, :ln] = 0
+        targets, loss_mask = build_targets(text.input_ids, text_loss_atts, Q)
+        emb = self._word_embedding()(text.input_ids).to(query_features.dtype)
+        out = self.text_decoder(input_embeds=torch.cat([query_features, emb], dim=1), loss_mask=loss_mask, labels=targets)
+        return out, loss_mask
+
+    def _cls_pass(self, query_features, prompt_text, train):
+        """cls_head(last_hidden_state at the last valid position of [prefix | prompt])."""
+        Q = query_features.shape[1]
+        att = prompt_text.attention_mask
+        # the reference's (unused) loss of this pass masks with 1-att in training and att in eval
+        text_loss_atts = (1 - att[:, 1:]) if train else att[:, 1:].clone()
+        targets, loss_mask = build_targets(prompt_text.input_ids, text_loss_atts, Q)
+        emb = self._word_embedding()(prompt_text.input_ids).to(query_features.dtype)
+        out = self.text_decoder(input_embeds=torch.cat([query_features, emb], dim=1), loss_mask=loss_mask, labels=targets)
+        hid = out.last_hidden_state
+        pooled = hid[torch.arange(hid.shape[0], device=hid.device), Q + att.sum(dim=-1) - 1]
+        return self.cls_head(pooled)
+
+
+class DistributedGPT3_Cls(_PromptClsBase):
+    """Video category prediction (:431-657).  Training: generation loss on [prompt+label] (+ optional
+    cls_head CE); eval: every class prompt of every video scored by softmax(-sum(losses * mask))."""
 
     def __init__(self, config=None, tokenizer=None):
         super().__init__()
@@ -214,38 +248,55 @@ class DistributedGPT3_Cls(_PrefixModelBase):
             self.cls_head = nn.Sequential(_Linear(self.text_width, self.text_width), nn.ReLU(),
                                           _Linear(self.text_width, self.num_classes))
 
-    def _caption_pass(self, query_features, text):
-        Q = query_features.shape[1]
-        text_loss_atts = text.attention_mask[:, 1:].clone()
-        if getattr(text, "prompt_lengths", None) is not None:
-            for i, ln in enumerate(text.prompt_lengths.tolist()):
-                text_loss_atts[i, :ln] = 0
-        targets, loss_mask = build_targets(text.input_ids, text_loss_atts, Q)
-        input_embeds = torch.cat([query_features, self._word_embedding()(text.input_ids).to(query_features.dtype)], dim=1)
-        return self.text_decoder(input_embeds=input_embeds, loss_mask=loss_mask, labels=targets), loss_mask
-
     def forward(self, image, text=None, prompt_text=None, labels=None, train=True):
         _, _, _, query_features = self.visual_prefix(image)
         B, Q, _ = query_features.shape
         if train:
-            out, _ = self._caption_pass(query_features, prompt_text if prompt_text is not None else text)
-            loss_cls = torch.tensor(0.0, device=image.device)
+            out, _ = self._gen_pass(query_features, text)
             if self.use_cls:
-                out_t, _ = self._caption_pass(query_features, text)
-                last = out_t.last_hidden_state[torch.arange(B), Q + text.attention_mask.sum(-1) - 1]
-                loss_cls = F.cross_entropy(self.cls_head(last).float(), labels)
+                loss_cls = F.cross_entropy(self._cls_pass(query_features, prompt_text, True).float(), labels)
+            else:
+                loss_cls = out.loss.new_zeros(())
             return out.loss, loss_cls
-        # eval: prompt_text holds num_cls prompts per video, flattened [B*num_cls, L]
-        num_cls = prompt_text.input_ids.shape[0] // B
-        qf = query_features.unsqueeze(1).expand(B, num_cls, Q, -1).reshape(B * num_cls, Q, -1)
-        out, loss_mask = self._caption_pass(qf, prompt_text)
-        scores = -(out.losses * loss_mask.float()).sum(-1).view(B, num_cls)
-        generation_logits = scores.softmax(-1)
+        num_cls = text.input_ids.shape[0] // B
+        qf = query_features.unsqueeze(1).repeat(1, num_cls, 1, 1).reshape(B * num_cls, Q, -1)
+        out, loss_mask = self._gen_pass(qf, text)
+        generation_logits = (-(out.losses * loss_mask).sum(dim=-1)).view(B, num_cls).softmax(dim=-1)
+        cls_logits = self._cls_pass(query_features, prompt_text, False) if self.use_cls else None
+        return generation_logits, cls_logits
+
+
+class DistributedGPT3_Retrieval_Cls(_PromptClsBase):
+    """Video-text matching used by downstream/run_retrieval_distributed_gpt3_itm.py (:988-1218): the B
+    prefixes are extended with `negative_indices` (hard negatives), a generation loss plus a 2-way
+    match/no-match cls_head; eval scores every (video, text) pair."""
+
+    def __init__(self, config=None, tokenizer=None):
+        super().__init__()
+        self._build(config, tokenizer, config.get('num_frames', None))
+        self.use_cls = config.get('use_cls', False)
+        if self.use_cls:
+            self.cls_head = nn.Sequential(_Linear(self.text_width, self.text_width), nn.ReLU(),
+                                          _Linear(self.text_width, 2))
+
+    def forward(self, image, text=None, prompt_text=None, negative_indices=None, labels=None, train=True):
+        _, _, _, query_features = self.visual_prefix(image)
+        if train:
+            qf = torch.cat([query_features, query_features[negative_indices]], dim=0)
+            out, _ = self._gen_pass(qf, text)
+            if self.use_cls:
+                loss_cls = F.cross_entropy(self._cls_pass(qf, prompt_text, True).float(), labels)
+            else:
+                loss_cls = out.loss.new_zeros(())
+            return out.loss, loss_cls
+        V = query_features.shape[0]
+        t = text.input_ids.shape[0] // V
+        qf = query_features.repeat_interleave(t, dim=0)
+        out, loss_mask = self._gen_pass(qf, text)
+        generation_logits = (-(out.losses * loss_mask).sum(dim=-1)).view(V, t)
         cls_logits = None
-        if self.use_cls and text is not None:
-            out_t, _ = self._caption_pass(query_features, text)
-            last = out_t.last_hidden_state[torch.arange(B), Q + text.attention_mask.sum(-1) - 1]
-            cls_logits = self.cls_head(last).float()
+        if self.use_cls:
+            cls_logits = self._cls_pass(qf, prompt_text, False).float().softmax(dim=-1)[:, 1].view(V, t)
         return generation_logits, cls_logits
 
 
@@ -256,7 +307,7 @@ class DistributedGPT3_Retrieval(_PrefixModelBase):
     def __init__(self, config=None, tokenizer=None):
         super().__init__()
         self._build(config, tokenizer, config.get('num_frames', None))
-        embed_dim = config.get('embed_dim', 256)
+        embed_dim = config.get('contrastive_embed_dim', 256)
         self.vision_proj = _Linear(self.vision_width, embed_dim)
         self.text_proj = _Linear(self.text_width, embed_dim)
         self.temp = nn.Parameter(torch.ones([]) * config.get('temp', 0.07))

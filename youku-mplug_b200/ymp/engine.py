@@ -124,12 +124,12 @@ def vit_block_fwd(W, pre, x, d, save=True):
     y = ops.gemm(att_s[:RB], W[pre + "attn.proj.weight"], bias=W[pre + "attn.proj.bias"], residual=xt)
     # ---- MLP
     ln_m, c.m_m, c.r_m = ops.layernorm_fwd(y, W[pre + "norm2.weight"], W[pre + "norm2.bias"], d.eps)
-    pre_act = torch.empty((RB, d.hid), device=x.device, dtype=bf16)
-    h = ops.gemm(ln_m, W[pre + "mlp.fc1.weight"], bias=W[pre + "mlp.fc1.bias"], act=ACT_GELU_ERF, aux_out=pre_act)
+    dact = torch.empty((RB, d.hid), device=x.device, dtype=bf16)
+    h = ops.gemm(ln_m, W[pre + "mlp.fc1.weight"], bias=W[pre + "mlp.fc1.bias"], act=ACT_GELU_ERF, aux_out=dact)
     out = ops.gemm(h, W[pre + "mlp.fc2.weight"], bias=W[pre + "mlp.fc2.bias"], residual=y)
     if save:
         c.update(x=x, ln_t=ln_t, qkv_t=qkv_t, att_t=att_t, proj_t=proj_t, xt=xt, ln_s=ln_s, qkv_s=qkv_s,
-                 att_s=att_s, y=y, ln_m=ln_m, pre_act=pre_act, h=h)
+                 att_s=att_s, y=y, ln_m=ln_m, dact=dact, h=h)
     return out, c
 
 
@@ -139,7 +139,7 @@ def vit_block_bwd(W, G, pre, c, dout, d):
     dev = dout.device
     # ---- MLP
     linear_wgrad(dout, c.h, pre + "mlp.fc2.weight", pre + "mlp.fc2.bias", G)
-    dpre = linear_dgrad(dout, W[pre + "mlp.fc2.weight"], act=ACT_GELU_ERF, aux_in=c.pre_act)
+    dpre = linear_dgrad(dout, W[pre + "mlp.fc2.weight"], act=ACT_GELU_ERF, aux_in=c.dact)
     linear_wgrad(dpre, c.ln_m, pre + "mlp.fc1.weight", pre + "mlp.fc1.bias", G)
     dln_m = linear_dgrad(dpre, W[pre + "mlp.fc1.weight"])
     dy = ops.layernorm_bwd(dln_m, c.y, W[pre + "norm2.weight"], c.m_m, c.r_m, add=dout,
@@ -294,11 +294,11 @@ def attn_pool_fwd(W, image_embeds, B, heads, save=True):
     # residual from the *normalised* queries (:369-371)
     x1 = ops.gemm(att, W[AP + "attn.out_proj.weight"], bias=W[AP + "attn.out_proj.bias"], residual=xq, res_row_mod=Q)
     ln2, c.m2, c.r2 = ops.layernorm_fwd(x1, W[AP + "norm2.weight"], W[AP + "norm2.bias"], eps)
-    pre_act = torch.empty((B * Q, W[AP + "mlp.fc1.weight"].shape[0]), device=dev, dtype=bf16)
-    h = ops.gemm(ln2, W[AP + "mlp.fc1.weight"], bias=W[AP + "mlp.fc1.bias"], act=ACT_GELU_ERF, aux_out=pre_act)
+    dact = torch.empty((B * Q, W[AP + "mlp.fc1.weight"].shape[0]), device=dev, dtype=bf16)
+    h = ops.gemm(ln2, W[AP + "mlp.fc1.weight"], bias=W[AP + "mlp.fc1.bias"], act=ACT_GELU_ERF, aux_out=dact)
     out = ops.gemm(h, W[AP + "mlp.fc2.weight"], bias=W[AP + "mlp.fc2.bias"], residual=x1)
     if save:
-        c.update(lq=lq, xq=xq, kvn=kvn, qp=qp, kvp=kvp, att=att, x1=x1, ln2=ln2, pre_act=pre_act, h=h,
+        c.update(lq=lq, xq=xq, kvn=kvn, qp=qp, kvp=kvp, att=att, x1=x1, ln2=ln2, dact=dact, h=h,
                  image_embeds=image_embeds, rows=rows)
     return out, c
 
@@ -309,7 +309,7 @@ def attn_pool_bwd(W, G, c, dout):
     KP = K1 + 1
     dev = dout.device
     linear_wgrad(dout, c.h, AP + "mlp.fc2.weight", AP + "mlp.fc2.bias", G)
-    dpre = linear_dgrad(dout, W[AP + "mlp.fc2.weight"], act=ACT_GELU_ERF, aux_in=c.pre_act)
+    dpre = linear_dgrad(dout, W[AP + "mlp.fc2.weight"], act=ACT_GELU_ERF, aux_in=c.dact)
     linear_wgrad(dpre, c.ln2, AP + "mlp.fc1.weight", AP + "mlp.fc1.bias", G)
     dln2 = linear_dgrad(dpre, W[AP + "mlp.fc1.weight"])
     dx1 = ops.layernorm_bwd(dln2, c.x1, W[AP + "norm2.weight"], c.m2, c.r2, add=dout,
@@ -389,10 +389,10 @@ def gpt_layer_fwd(W, pre, x, g, B, S, train_w=False):
                          causal=True, scale=g.scale)
     x1 = ops.gemm(att, W[pre + "self_attention.dense.weight"], bias=W[pre + "self_attention.dense.bias"], residual=x)
     ln2, c.m2, c.r2 = ops.layernorm_fwd(x1, W[pre + "post_attention_layernorm.weight"], W[pre + "post_attention_layernorm.bias"], g.eps)
-    pre_act = torch.empty((B * S, g.F), device=x.device, dtype=bf16)
-    h = ops.gemm(ln2, W[pre + "mlp.dense_h_to_4h.weight"], bias=W[pre + "mlp.dense_h_to_4h.bias"], act=ACT_GELU_TANH, aux_out=pre_act)
+    dact = torch.empty((B * S, g.F), device=x.device, dtype=bf16)
+    h = ops.gemm(ln2, W[pre + "mlp.dense_h_to_4h.weight"], bias=W[pre + "mlp.dense_h_to_4h.bias"], act=ACT_GELU_TANH, aux_out=dact)
     out = ops.gemm(h, W[pre + "mlp.dense_4h_to_h.weight"], bias=W[pre + "mlp.dense_4h_to_h.bias"], residual=x1)
-    c.update(x=x, qkv=qkv, att=att, x1=x1, pre_act=pre_act)
+    c.update(x=x, qkv=qkv, att=att, x1=x1, dact=dact)
     if train_w:
         c.update(ln1=ln1, ln2=ln2, h=h)
     return out, c
@@ -403,7 +403,7 @@ def gpt_layer_bwd(W, G, pre, c, dout, g, B, S):
     dev = dout.device
     if "h" in c:
         linear_wgrad(dout, c.h, pre + "mlp.dense_4h_to_h.weight", pre + "mlp.dense_4h_to_h.bias", G)
-    dpre = linear_dgrad(dout, W[pre + "mlp.dense_4h_to_h.weight"], act=ACT_GELU_TANH, aux_in=c.pre_act)
+    dpre = linear_dgrad(dout, W[pre + "mlp.dense_4h_to_h.weight"], act=ACT_GELU_TANH, aux_in=c.dact)
     if "ln2" in c:
         linear_wgrad(dpre, c.ln2, pre + "mlp.dense_h_to_4h.weight", pre + "mlp.dense_h_to_4h.bias", G)
     dln2 = linear_dgrad(dpre, W[pre + "mlp.dense_h_to_4h.weight"])
