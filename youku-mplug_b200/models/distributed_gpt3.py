@@ -25,6 +25,10 @@ class _Linear(nn.Linear):
     """nn.Linear whose forward runs on the tcgen05 GEMM (same parameters / state_dict keys)."""
 
     def forward(self, x):
+        if self.weight.shape[0] % 8 or self.weight.shape[1] % 8:
+            # classifier heads with 2 / 5 / 45 outputs: a few kFLOP, below the GEMM kernel's 16-byte
+            # row-alignment requirement - left to the library GEMM
+            return F.linear(x, self.weight, self.bias)
         return YF.LinearFn.apply(x, self.weight, self.bias)
 
 
