@@ -58,7 +58,7 @@ uint64_t ymp_launch_count(void);
  *   v = act(v)                           (YMP_ACT_*; skipped when aux_in is set)
  *   if aux_in:  v *= aux_in[m,n]         (backward of an activation: aux_in is the act' saved above,
  *                                          so the backward epilogue needs no transcendental)
- *   v += residual[m,n]                   (bf16 [M,N], row stride ldr, optional)
+ *   v += residual[m,n]                   (bf16 or fp32 [M,N], row stride ldr, optional)
  *   D[m,n] = v  (bf16 or fp32) ; or atomically D[m,n] += v (fp32, accumulate=1, used by split-K)
  * ------------------------------------------------------------------------------------------ */
 #define YMP_ACT_NONE 0
@@ -76,7 +76,7 @@ typedef struct ymp_gemm_args {
   int32_t lda, ldb, ldd;
   int32_t a_mn_major, b_mn_major;
   const void* bias;     /* bf16 [N] or NULL */
-  const void* residual; /* bf16 [M,N] or NULL */
+  const void* residual; /* bf16 or fp32 (residual_dtype) [M,N] or NULL */
   int32_t ldr;
   int32_t act;          /* YMP_ACT_* */
   void* aux_out;        /* bf16 [M,N] (ld = ldd) or NULL: act'(pre-activation) (or the value if act=NONE) */
@@ -89,6 +89,7 @@ typedef struct ymp_gemm_args {
   int32_t res_row_mod;  /* >0: residual row = m % res_row_mod (broadcast tables: position embeddings) */
   int32_t d_row_block;  /* >0: D row = (m / d_row_block) * d_row_stride + m % d_row_block           */
   int32_t d_row_stride; /*     (writes [B*Q] rows into a [B, S>=Q] buffer without a copy)           */
+  int32_t residual_dtype; /* YMP_DT_BF16 (default) | YMP_DT_F32: the residual streams are kept in fp32 */
 } ymp_gemm_args;
 
 int ymp_gemm(const ymp_gemm_args* a, void* stream);
@@ -111,6 +112,8 @@ typedef struct ymp_layernorm_args {
   const int32_t* in_rows;
   int32_t rows, D, ldx, ldy;
   float eps;
+  int32_t x_dtype;    /* YMP_DT_BF16 | YMP_DT_F32 (fp32 residual stream in) */
+  int32_t y_dtype;    /* YMP_DT_BF16 | YMP_DT_F32 */
 } ymp_layernorm_args;
 int ymp_layernorm_fwd(const ymp_layernorm_args* a, void* stream);
 
@@ -126,6 +129,7 @@ typedef struct ymp_layernorm_bwd_args {
   float* dbeta;
   const int32_t* in_rows;
   int32_t rows, D, ldx, lddy, ldadd;
+  int32_t x_dtype;    /* dtype of x (dx is always bf16, same row stride in elements) */
 } ymp_layernorm_bwd_args;
 int ymp_layernorm_bwd(const ymp_layernorm_bwd_args* a, void* stream);
 
@@ -215,6 +219,7 @@ typedef struct ymp_embed_args {
   const void* pos;     /* bf16 [max_pos, hidden] or NULL */
   void* out;           /* bf16 [B*S, hidden] rows of stride ldo */
   int32_t B, L, S, row_offset, hidden, vocab, ldo;
+  int32_t out_dtype;   /* YMP_DT_BF16 | YMP_DT_F32 */
 } ymp_embed_args;
 int ymp_embed_gather(const ymp_embed_args* a, void* stream);
 

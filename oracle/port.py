@@ -214,7 +214,7 @@ def pretrain_forward(video, input_ids, attention_mask, sd, vcfg, gcfg, return_al
 # ------------------------------------------------------------------------------------------
 # Random-init state dicts with the reference's keys / shapes / init laws (for benches & tests)
 # ------------------------------------------------------------------------------------------
-def init_state_dict(vcfg, gcfg, num_query, seed=0, dtype=torch.float32, randomize=False):
+def init_state_dict(vcfg, gcfg, num_query, seed=0, dtype=torch.float32, randomize=False, fast=False):
     """Same parameter names, shapes and init distributions as the reference constructors
     (TimeSformer.__init__ models/vision_transformer.py:441-519, DistributedGPT3_Pretrain.__init__
     models/distributed_gpt3.py:96-116, GPT3 init_method_normal / scaled models/
@@ -227,9 +227,13 @@ def init_state_dict(vcfg, gcfg, num_query, seed=0, dtype=torch.float32, randomiz
     sd = {}
 
     def tn(*shape, std=0.015):
+        if fast:  # timing-only weights: same scale, vectorised fill (not reproducible across runs)
+            return torch.empty(*shape).uniform_(-1.7 * std, 1.7 * std)
         return torch.nn.init.trunc_normal_(torch.empty(*shape), std=std, generator=g)
 
     def nrm(*shape, std):
+        if fast:
+            return torch.empty(*shape).uniform_(-1.7 * std, 1.7 * std)
         return torch.empty(*shape).normal_(0.0, std, generator=g)
 
     ve = "visual_encoder."

@@ -37,6 +37,31 @@ def test_layernorm_fwd_bwd(cuda, rows, D):
     assert _rel(dx2, xf.grad) < 1e-2
 
 
+@pytest.mark.parametrize("D", [768, 2048])
+def test_layernorm_fp32_stream(cuda, D):
+    """fp32 residual-stream input (and optionally fp32 output), bf16 gradients."""
+    from ymp import ops
+    torch.manual_seed(11)
+    rows = 77
+    x = torch.randn(rows, D, device=cuda) * 3 + 1
+    g = (1 + 0.1 * torch.randn(D, device=cuda)).to(bf16)
+    b = (0.1 * torch.randn(D, device=cuda)).to(bf16)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-5)
+    assert y.dtype == bf16
+    xf = x.clone().requires_grad_()
+    ref = torch.nn.functional.layer_norm(xf, (D,), g.float(), b.float(), 1e-5)
+    assert _rel(y, ref) < 5e-3
+    y32, _, _ = ops.layernorm_fwd(x, g, b, 1e-5, out_dtype=torch.float32)
+    assert y32.dtype == torch.float32 and _rel(y32, ref) < 1e-5
+    dy = torch.randn(rows, D, device=cuda).to(bf16)
+    ref.backward(dy.float())
+    dg, db = torch.zeros(D, device=cuda), torch.zeros(D, device=cuda)
+    dx = ops.layernorm_bwd(dy, x, g, mean, rstd, dgamma=dg, dbeta=db)
+    assert dx.dtype == bf16 and _rel(dx, xf.grad) < 1e-2
+    xh = (x - x.mean(-1, keepdim=True)) * torch.rsqrt(x.var(-1, unbiased=False, keepdim=True) + 1e-5)
+    assert _rel(dg, (dy.float() * xh).sum(0)) < 5e-3 and _rel(db, dy.float().sum(0)) < 5e-3
+
+
 def test_layernorm_row_gather(cuda):
     from ymp import ops
     torch.manual_seed(1)
@@ -262,6 +287,27 @@ def test_cross_entropy(cuda, V):
     assert _rel(d, lf.grad) < 1e-2
     d2 = ops.ce_bwd(logits.clone(), labels, lse, g)  # in place
     assert torch.equal(d2, d)
+
+
+def test_fp32_stream_epilogues(cuda):
+    """fp32 residual in / fp32 out of the GEMM epilogue and fp32 rows from the embedding gather."""
+    from ymp import ops
+    torch.manual_seed(12)
+    M, N, K = 300, 256, 128
+    a = torch.randn(M, K, device=cuda).to(bf16)
+    w = (torch.randn(N, K, device=cuda) * 0.1).to(bf16)
+    res = torch.randn(M, N, device=cuda)
+    out = ops.gemm(a, w, residual=res, out_dtype=torch.float32)
+    assert out.dtype == torch.float32
+    assert _rel(out, a.float() @ w.float().t() + res) < 1e-5
+    out_bf = ops.gemm(a, w, residual=res)
+    assert out_bf.dtype == bf16 and _rel(out_bf, a.float() @ w.float().t() + res) < 1e-2
+    table = torch.randn(100, 256, device=cuda).to(bf16)
+    pos = torch.randn(32, 256, device=cuda).to(bf16)
+    ids = torch.randint(0, 100, (2, 5), device=cuda)
+    o = torch.zeros(2 * 9, 256, device=cuda)
+    ops.embed_gather(ids, table, pos, o, 9, 4)
+    assert torch.equal(o.view(2, 9, 256)[:, 4:], table[ids].float() + pos[4:9].float()[None])
 
 
 def test_colsum_and_group(cuda):

@@ -22,7 +22,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 struct GemmKParams {
   void* D;
   const __nv_bfloat16* bias;
-  const __nv_bfloat16* residual;
+  const void* residual;            // bf16 or fp32 (res_f32)
   __nv_bfloat16* aux_out;
   const __nv_bfloat16* aux_in;
   int M, N, K;
@@ -32,6 +32,7 @@ struct GemmKParams {
   int kb_per_split;
   int res_row_mod;                 // residual row = row % res_row_mod (0: plain)
   int d_row_block, d_row_stride;   // D row = (row / block) * stride + row % block (0: plain)
+  int res_f32;
   int n_fast;                      // tile order: consecutive units walk N first (A streamed once) or M first
   bool v32_d, v32_aux, v32_res, v32_bias;  // 32-byte aligned -> 256-bit accesses
   float alpha;
@@ -147,13 +148,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
       store16(p.aux_out + off + 16, p.v32_aux, v + 16);
     }
     if (p.residual) {
-      const __nv_bfloat16* rp = p.residual + (size_t)rrow * p.ldr + col0;
+      if (p.res_f32) {  // fp32 residual stream
+        const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + (size_t)rrow * p.ldr + col0);
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        float a[16];
-        load16(rp + 16 * hh, p.v32_res, a);
+        for (int j = 0; j < 8; ++j) {
+          const float4 a = __ldg(rp + j);
+          v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+        }
+      } else {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)rrow * p.ldr + col0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[16 * hh + i] += a[i];
+        for (int hh = 0; hh < 2; ++hh) {
+          float a[16];
+          load16(rp + 16 * hh, p.v32_res, a);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[16 * hh + i] += a[i];
+        }
       }
     }
     if (!p.out_f32) {
@@ -204,7 +214,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
         } else if (p.aux_out) {
           p.aux_out[off] = __float2bfloat16(x);
         }
-        if (p.residual) x += __bfloat162float(p.residual[(size_t)rrow * p.ldr + col]);
+        if (p.residual)
+          x += p.res_f32 ? reinterpret_cast<const float*>(p.residual)[(size_t)rrow * p.ldr + col]
+                         : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[(size_t)rrow * p.ldr + col]);
         if (!p.out_f32) reinterpret_cast<__nv_bfloat16*>(p.D)[doff] = __float2bfloat16(x);
         else if (!p.accumulate) reinterpret_cast<float*>(p.D)[doff] = x;
         else atomicAdd(reinterpret_cast<float*>(p.D) + doff, x);
@@ -647,6 +659,7 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
   YMP_CHECK_ARG(a->ldd >= a->N && a->ldd % 8 == 0, "ymp_gemm: ldd must be >= N and a multiple of 8 (ldd=%d)", a->ldd);
   YMP_CHECK_ARG(a->act >= 0 && a->act <= 2, "ymp_gemm: bad act %d", a->act);
   YMP_CHECK_ARG(!a->residual || (a->ldr >= a->N && a->ldr % 8 == 0 && aligned16(a->residual)), "ymp_gemm: bad residual ld/alignment");
+  YMP_CHECK_ARG(a->residual_dtype == YMP_DT_BF16 || a->residual_dtype == YMP_DT_F32, "ymp_gemm: bad residual_dtype");
   YMP_CHECK_ARG(!a->bias || aligned16(a->bias), "ymp_gemm: bias must be 16-byte aligned");
   YMP_CHECK_ARG(!a->aux_out || aligned16(a->aux_out), "ymp_gemm: aux_out alignment");
   YMP_CHECK_ARG(!a->aux_in || aligned16(a->aux_in), "ymp_gemm: aux_in alignment");
@@ -687,7 +700,8 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
   GemmKParams kp;
   kp.D = a->D;
   kp.bias = reinterpret_cast<const __nv_bfloat16*>(a->bias);
-  kp.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+  kp.residual = a->residual;
+  kp.res_f32 = (a->residual_dtype == YMP_DT_F32) ? 1 : 0;
   kp.aux_out = reinterpret_cast<__nv_bfloat16*>(a->aux_out);
   kp.aux_in = reinterpret_cast<const __nv_bfloat16*>(a->aux_in);
   kp.M = a->M; kp.N = a->N; kp.K = a->K;

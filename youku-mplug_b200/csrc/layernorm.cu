@@ -8,10 +8,11 @@ namespace ymp {
 constexpr int LN_WARPS = 8;
 
 struct LnParams {
-  const __nv_bfloat16* x;
+  const void* x;  // bf16 or fp32 (XF32)
   const __nv_bfloat16* gamma;
   const __nv_bfloat16* beta;
-  __nv_bfloat16* y;
+  void* y;        // bf16 or fp32 (y_f32)
+  int y_f32;
   float* mean;
   float* rstd;
   const int32_t* in_rows;
@@ -30,8 +31,20 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return u;
 }
 
-// VPL = 16-byte vectors per lane (D <= VPL*256)
-template <int VPL>
+// 8 consecutive elements of row `row` (vector index vi) as floats, from bf16 or fp32 storage
+template <bool XF32>
+__device__ __forceinline__ void load8(const void* base, size_t row, int ld, int vi, float (&f)[8]) {
+  if (XF32) {
+    const float4* p4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + row * ld) + 2 * vi;
+    const float4 a = __ldg(p4), b = __ldg(p4 + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + row * ld) + vi), f);
+  }
+}
+
+// VPL = 8-element vectors per lane (D <= VPL*256)
+template <int VPL, bool XF32>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnParams p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -39,22 +52,21 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnParams p)
   for (int row = blockIdx.x * LN_WARPS + warp; row < p.rows; row += gridDim.x * LN_WARPS) {
     const int irow = p.in_rows ? p.in_rows[row] : row;
     if (irow < 0) {  // padding slot: emit a zero row (the caller overwrites it), no statistics
-      uint4* yz = reinterpret_cast<uint4*>(p.y + (size_t)row * p.ldy);
-      for (int vi = lane; vi < nvec; vi += 32) yz[vi] = make_uint4(0, 0, 0, 0);
+      uint4* yz = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)row * p.ldy);
+      for (int vi = lane; vi < nvec; vi += 32) yz[vi] = make_uint4(0, 0, 0, 0);  // (bf16 outputs only)
       if (lane == 0) {
         if (p.mean) p.mean[row] = 0.f;
         if (p.rstd) p.rstd[row] = 0.f;
       }
       continue;
     }
-    const uint4* xr = reinterpret_cast<const uint4*>(p.x + (size_t)irow * p.ldx);
     float v[VPL][8];
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       const int vi = j * 32 + lane;
       if (vi < nvec) {
-        unpack8(__ldg(xr + vi), v[j]);
+        load8<XF32>(p.x, (size_t)irow, p.ldx, vi, v[j]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) s += v[j][e];
       } else {
@@ -76,7 +88,6 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnParams p)
       if (p.mean) p.mean[row] = mu;
       if (p.rstd) p.rstd[row] = rs;
     }
-    uint4* yr = reinterpret_cast<uint4*>(p.y + (size_t)row * p.ldy);
     const uint4* g4 = reinterpret_cast<const uint4*>(p.gamma);
     const uint4* b4 = reinterpret_cast<const uint4*>(p.beta);
 #pragma unroll
@@ -88,7 +99,13 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnParams p)
         unpack8(__ldg(b4 + vi), b);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = fmaf((v[j][e] - mu) * rs, g[e], b[e]);
-        yr[vi] = pack8(o);
+        if (p.y_f32) {
+          float4* yr = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + (size_t)row * p.ldy) + 2 * vi;
+          yr[0] = make_float4(o[0], o[1], o[2], o[3]);
+          yr[1] = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+          reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)row * p.ldy)[vi] = pack8(o);
+        }
       }
     }
   }
@@ -96,7 +113,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnParams p)
 
 struct LnBwdParams {
   const __nv_bfloat16* dy;
-  const __nv_bfloat16* x;
+  const void* x;  // bf16 or fp32 (XF32)
   const __nv_bfloat16* gamma;
   const float* mean;
   const float* rstd;
@@ -108,7 +125,7 @@ struct LnBwdParams {
   int rows, D, ldx, lddy, ldadd;
 };
 
-template <int VPL, bool WGRAD>
+template <int VPL, bool WGRAD, bool XF32>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -124,7 +141,6 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
   for (int row = blockIdx.x * LN_WARPS + warp; row < p.rows; row += gridDim.x * LN_WARPS) {
     const int irow = p.in_rows ? p.in_rows[row] : row;
     if (irow < 0) continue;  // padding slot of the forward: no input row behind it
-    const uint4* xr = reinterpret_cast<const uint4*>(p.x + (size_t)irow * p.ldx);
     const uint4* dyr = reinterpret_cast<const uint4*>(p.dy + (size_t)row * p.lddy);
     const float mu = p.mean[row], rs = p.rstd[row];
     float xh[VPL][8], gy[VPL][8];
@@ -134,7 +150,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
       const int vi = j * 32 + lane;
       if (vi < nvec) {
         float xv[8], dyv[8], g[8];
-        unpack8(__ldg(xr + vi), xv);
+        load8<XF32>(p.x, (size_t)irow, p.ldx, vi, xv);
         unpack8(__ldg(dyr + vi), dyv);
         unpack8(__ldg(g4 + vi), g);
 #pragma unroll
@@ -180,12 +196,21 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
 #pragma unroll
         for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = pass == 0 ? dg[j][e] : db[j][e];
         __syncthreads();
-        for (int c = threadIdx.x; c < 256; c += LN_WARPS * 32) {
-          float s = 0.f;
+        // 256 columns per (j, pass): thread t < 64 owns 4 consecutive columns -> one 16-byte reduction
+        if (threadIdx.x < 64) {
+          float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int w = 0; w < LN_WARPS; ++w) s += red[w][c];
-          const int col = j * 256 + c;
-          if (col < p.D) atomicAdd((pass == 0 ? p.dgamma : p.dbeta) + col, s);
+          for (int w = 0; w < LN_WARPS; ++w)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s[e] += red[w][threadIdx.x * 4 + e];
+          const int col = j * 256 + threadIdx.x * 4;
+          float* dst = (pass == 0 ? p.dgamma : p.dbeta) + col;
+          if (col + 3 < p.D) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]) : "memory");
+          } else {
+            for (int e = 0; e < 4; ++e)
+              if (col + e < p.D) atomicAdd(dst + e, s[e]);
+          }
         }
       }
     }
@@ -200,16 +225,24 @@ extern "C" int ymp_layernorm_fwd(const ymp_layernorm_args* a, void* stream) {
   YMP_CHECK_ARG(a->rows > 0 && a->D > 0 && a->D % 8 == 0 && a->D <= 4096, "ymp_layernorm_fwd: D=%d must be a multiple of 8 and <= 4096", a->D);
   YMP_CHECK_ARG(a->ldx % 8 == 0 && a->ldy % 8 == 0 && a->ldx >= a->D && a->ldy >= a->D, "ymp_layernorm_fwd: bad ld");
   YMP_CHECK_ARG(aligned16(a->x) && aligned16(a->y) && aligned16(a->gamma) && aligned16(a->beta), "ymp_layernorm_fwd: 16-byte alignment required");
+  YMP_CHECK_ARG(!(a->in_rows && a->y_dtype == YMP_DT_F32), "ymp_layernorm_fwd: row gather supports bf16 outputs only");
   LnParams p;
-  p.x = (const __nv_bfloat16*)a->x; p.gamma = (const __nv_bfloat16*)a->gamma; p.beta = (const __nv_bfloat16*)a->beta;
-  p.y = (__nv_bfloat16*)a->y; p.mean = a->mean; p.rstd = a->rstd; p.in_rows = a->in_rows;
+  p.x = a->x; p.gamma = (const __nv_bfloat16*)a->gamma; p.beta = (const __nv_bfloat16*)a->beta;
+  p.y = a->y; p.y_f32 = (a->y_dtype == YMP_DT_F32); p.mean = a->mean; p.rstd = a->rstd; p.in_rows = a->in_rows;
   p.rows = a->rows; p.D = a->D; p.ldx = a->ldx; p.ldy = a->ldy; p.eps = a->eps;
   const int blocks = min((a->rows + LN_WARPS - 1) / LN_WARPS, num_sms() * 8);
   cudaStream_t st = (cudaStream_t)stream;
   const int vpl = (a->D / 8 + 31) / 32;
-  if (vpl <= 3) ln_fwd_kernel<3><<<blocks, LN_WARPS * 32, 0, st>>>(p);
-  else if (vpl <= 8) ln_fwd_kernel<8><<<blocks, LN_WARPS * 32, 0, st>>>(p);
-  else ln_fwd_kernel<16><<<blocks, LN_WARPS * 32, 0, st>>>(p);
+  const int thr = LN_WARPS * 32;
+  if (a->x_dtype == YMP_DT_F32) {
+    if (vpl <= 3) ln_fwd_kernel<3, true><<<blocks, thr, 0, st>>>(p);
+    else if (vpl <= 8) ln_fwd_kernel<8, true><<<blocks, thr, 0, st>>>(p);
+    else ln_fwd_kernel<16, true><<<blocks, thr, 0, st>>>(p);
+  } else {
+    if (vpl <= 3) ln_fwd_kernel<3, false><<<blocks, thr, 0, st>>>(p);
+    else if (vpl <= 8) ln_fwd_kernel<8, false><<<blocks, thr, 0, st>>>(p);
+    else ln_fwd_kernel<16, false><<<blocks, thr, 0, st>>>(p);
+  }
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }
@@ -219,9 +252,10 @@ extern "C" int ymp_layernorm_bwd(const ymp_layernorm_bwd_args* a, void* stream) 
   YMP_CHECK_ARG(a && a->dy && a->x && a->gamma && a->mean && a->rstd && a->dx, "ymp_layernorm_bwd: null pointer");
   YMP_CHECK_ARG(a->rows > 0 && a->D > 0 && a->D % 8 == 0 && a->D <= 4096, "ymp_layernorm_bwd: bad D=%d", a->D);
   YMP_CHECK_ARG((a->dgamma == nullptr) == (a->dbeta == nullptr), "ymp_layernorm_bwd: dgamma/dbeta must both be set or both NULL");
+  YMP_CHECK_ARG(!a->dgamma || (aligned16(a->dgamma) && aligned16(a->dbeta)), "ymp_layernorm_bwd: dgamma/dbeta must be 16-byte aligned");
   YMP_CHECK_ARG(a->ldx % 8 == 0 && a->lddy % 8 == 0 && (!a->add || a->ldadd % 8 == 0), "ymp_layernorm_bwd: bad ld");
   LnBwdParams p;
-  p.dy = (const __nv_bfloat16*)a->dy; p.x = (const __nv_bfloat16*)a->x; p.gamma = (const __nv_bfloat16*)a->gamma;
+  p.dy = (const __nv_bfloat16*)a->dy; p.x = a->x; p.gamma = (const __nv_bfloat16*)a->gamma;
   p.mean = a->mean; p.rstd = a->rstd; p.add = (const __nv_bfloat16*)a->add; p.dx = (__nv_bfloat16*)a->dx;
   p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.in_rows = a->in_rows;
   p.rows = a->rows; p.D = a->D; p.ldx = a->ldx; p.lddy = a->lddy; p.ldadd = a->ldadd;
@@ -230,18 +264,16 @@ extern "C" int ymp_layernorm_bwd(const ymp_layernorm_bwd_args* a, void* stream) 
   const bool wg = a->dgamma != nullptr;
   // with weight grads each block ends with 2*D atomics; 6 blocks per SM keeps enough warps in
   // flight for HBM while bounding the atomic tail (~900 adds per address)
-  const int cap = wg ? num_sms() * 6 : num_sms() * 8;
+  const int cap = wg ? num_sms() * 4 : num_sms() * 8;
   const int blocks = min((a->rows + LN_WARPS - 1) / LN_WARPS, cap);
   const int thr = LN_WARPS * 32;
-  if (wg) {
-    if (vpl <= 3) ln_bwd_kernel<3, true><<<blocks, thr, 0, st>>>(p);
-    else if (vpl <= 8) ln_bwd_kernel<8, true><<<blocks, thr, 0, st>>>(p);
-    else ln_bwd_kernel<16, true><<<blocks, thr, 0, st>>>(p);
-  } else {
-    if (vpl <= 3) ln_bwd_kernel<3, false><<<blocks, thr, 0, st>>>(p);
-    else if (vpl <= 8) ln_bwd_kernel<8, false><<<blocks, thr, 0, st>>>(p);
-    else ln_bwd_kernel<16, false><<<blocks, thr, 0, st>>>(p);
-  }
+  const bool xf = (a->x_dtype == YMP_DT_F32);
+#define YMP_LN_BWD(V, W, X) ln_bwd_kernel<V, W, X><<<blocks, thr, 0, st>>>(p)
+#define YMP_LN_BWD_V(W, X) do { if (vpl <= 3) YMP_LN_BWD(3, W, X); else if (vpl <= 8) YMP_LN_BWD(8, W, X); else YMP_LN_BWD(16, W, X); } while (0)
+  if (wg) { if (xf) YMP_LN_BWD_V(true, true); else YMP_LN_BWD_V(true, false); }
+  else { if (xf) YMP_LN_BWD_V(false, true); else YMP_LN_BWD_V(false, false); }
+#undef YMP_LN_BWD_V
+#undef YMP_LN_BWD
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }

@@ -39,8 +39,8 @@ __global__ void __launch_bounds__(256) im2col_kernel(const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256) embed_gather_kernel(const int64_t* __restrict__ ids,
                                                            const __nv_bfloat16* __restrict__ table,
                                                            const __nv_bfloat16* __restrict__ pos,
-                                                           __nv_bfloat16* __restrict__ out, int B, int L,
-                                                           int S, int off, int Hd, int vocab, int ldo) {
+                                                           void* __restrict__ out_, int B, int L,
+                                                           int S, int off, int Hd, int vocab, int ldo, int out_f32) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nvec = Hd >> 3;
@@ -50,17 +50,24 @@ __global__ void __launch_bounds__(256) embed_gather_kernel(const int64_t* __rest
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
     const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)id * Hd);
     const uint4* ps = pos ? reinterpret_cast<const uint4*>(pos + (size_t)(off + l) * Hd) : nullptr;
-    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(b * S + off + l) * ldo);
+    const size_t orow = (size_t)(b * S + off + l) * ldo;
     for (int v = lane; v < nvec; v += 32) {
-      uint4 a = __ldg(src + v);
+      const uint4 a = __ldg(src + v);
+      float f[8] = {bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y), bf16_lo(a.z), bf16_hi(a.z), bf16_lo(a.w), bf16_hi(a.w)};
       if (ps) {
         const uint4 c = __ldg(ps + v);
-        a.x = pack_bf16(bf16_lo(a.x) + bf16_lo(c.x), bf16_hi(a.x) + bf16_hi(c.x));
-        a.y = pack_bf16(bf16_lo(a.y) + bf16_lo(c.y), bf16_hi(a.y) + bf16_hi(c.y));
-        a.z = pack_bf16(bf16_lo(a.z) + bf16_lo(c.z), bf16_hi(a.z) + bf16_hi(c.z));
-        a.w = pack_bf16(bf16_lo(a.w) + bf16_lo(c.w), bf16_hi(a.w) + bf16_hi(c.w));
+        f[0] += bf16_lo(c.x); f[1] += bf16_hi(c.x); f[2] += bf16_lo(c.y); f[3] += bf16_hi(c.y);
+        f[4] += bf16_lo(c.z); f[5] += bf16_hi(c.z); f[6] += bf16_lo(c.w); f[7] += bf16_hi(c.w);
       }
-      dst[v] = a;
+      if (out_f32) {
+        float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_) + orow) + 2 * v;
+        d[0] = make_float4(f[0], f[1], f[2], f[3]);
+        d[1] = make_float4(f[4], f[5], f[6], f[7]);
+      } else {
+        uint4 o;
+        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+        reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_) + orow)[v] = o;
+      }
     }
   }
 }
@@ -162,34 +169,56 @@ __global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const __nv_bfloat16*
 }
 
 // ------------------------------------------------------------------------------ column sum
-// out[c] += sum_r in[r, c]   (fp32 atomics; the caller zeroes or carries `out`)
-__global__ void __launch_bounds__(128) colsum_kernel(const __nv_bfloat16* __restrict__ in,
-                                                     float* __restrict__ out, int R, int C, int ld,
-                                                     int rows_per_block) {
-  const int v = blockIdx.x * 128 + threadIdx.x;  // 8-column vector index
-  if (v * 8 >= C) return;
+// out[c] += sum_r in[r, c]   (fp32; the caller zeroes or carries `out`).
+// Block = 8 warps x 32 lanes: a warp reads 512 contiguous bytes of one row (8 columns per lane, 8 rows
+// in flight per lane), the 8 warps of a block take interleaved rows and are reduced through shared
+// memory, so a block issues ONE 16-byte vector reduction per 4 columns: same-address atomic traffic
+// (the limiter of the first version at C=768) drops by 32x.
+constexpr int CS_WARPS = 8;
+__device__ __forceinline__ void acc8(float (&acc)[8], const uint4& u) {
+  acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
+  acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
+}
+__global__ void __launch_bounds__(CS_WARPS * 32) colsum_kernel(const __nv_bfloat16* __restrict__ in,
+                                                               float* __restrict__ out, int R, int C, int ld,
+                                                               int rows_per_block) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v = blockIdx.x * 32 + lane;  // 8-column vector index
+  const bool active = v * 8 < C;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(R, r0 + rows_per_block);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int r = r0;
-  for (; r + 8 <= r1; r += 8) {  // 8 independent 16-byte loads in flight per thread
-    uint4 u[8];
+  if (active) {
+    int r = r0 + warp;
+    for (; r + 7 * CS_WARPS < r1; r += 8 * CS_WARPS) {
+      uint4 u[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)(r + j) * ld) + v);
+      for (int j = 0; j < 8; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)(r + j * CS_WARPS) * ld) + v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[0] += bf16_lo(u[j].x); acc[1] += bf16_hi(u[j].x); acc[2] += bf16_lo(u[j].y); acc[3] += bf16_hi(u[j].y);
-      acc[4] += bf16_lo(u[j].z); acc[5] += bf16_hi(u[j].z); acc[6] += bf16_lo(u[j].w); acc[7] += bf16_hi(u[j].w);
+      for (int j = 0; j < 8; ++j) acc8(acc, u[j]);
+    }
+    for (; r < r1; r += CS_WARPS) acc8(acc, __ldg(reinterpret_cast<const uint4*>(in + (size_t)r * ld) + v));
+  }
+  __shared__ float red[CS_WARPS][32][9];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[warp][lane][e] = acc[e];
+  __syncthreads();
+  // 256 columns per block: thread t < 64 owns 4 consecutive columns
+  if (threadIdx.x < 64) {
+    const int l = threadIdx.x >> 1, e0 = (threadIdx.x & 1) * 4;
+    float s[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int w = 0; w < CS_WARPS; ++w)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[e] += red[w][l][e0 + e];
+    const int col = (blockIdx.x * 32 + l) * 8 + e0;
+    if (col + 3 < C) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + col), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]) : "memory");
+    } else {
+      for (int e = 0; e < 4; ++e)
+        if (col + e < C) atomicAdd(out + col + e, s[e]);
     }
   }
-  for (; r < r1; ++r) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + (size_t)r * ld) + v);
-    acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
-    acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
-  }
-#pragma unroll
-  for (int e = 0; e < 8; ++e)
-    if (v * 8 + e < C) atomicAdd(out + v * 8 + e, acc[e]);
 }
 
 // ------------------------------------------------------------------------------ group reduce
@@ -257,8 +286,8 @@ extern "C" int ymp_embed_gather(const ymp_embed_args* a, void* stream) {
   const int rows = a->B * a->L;
   const int blocks = min((rows + 7) / 8, num_sms() * 8);
   embed_gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      a->ids, (const __nv_bfloat16*)a->table, (const __nv_bfloat16*)a->pos, (__nv_bfloat16*)a->out, a->B, a->L,
-      a->S, a->row_offset, a->hidden, a->vocab, a->ldo);
+      a->ids, (const __nv_bfloat16*)a->table, (const __nv_bfloat16*)a->pos, a->out, a->B, a->L,
+      a->S, a->row_offset, a->hidden, a->vocab, a->ldo, a->out_dtype == YMP_DT_F32 ? 1 : 0);
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }
@@ -284,11 +313,12 @@ extern "C" int ymp_ce_bwd(const ymp_ce_args* a, void* stream) {
 extern "C" int ymp_colsum(const ymp_colsum_args* a, void* stream) {
   YMP_CHECK_ARG(a && a->in && a->out, "ymp_colsum: null pointer");
   YMP_CHECK_ARG(a->R > 0 && a->C > 0 && a->C % 8 == 0 && a->ld % 8 == 0 && a->ld >= a->C && aligned16(a->in), "ymp_colsum: bad shape/alignment");
-  const int gx = (a->C / 8 + 127) / 128;
-  int splits = max(1, min((a->R + 63) / 64, (num_sms() * 8 + gx - 1) / gx));
+  YMP_CHECK_ARG(aligned16(a->out), "ymp_colsum: out must be 16-byte aligned");
+  const int gx = (a->C / 8 + 31) / 32;
+  int splits = max(1, min((a->R + 63) / 64, (num_sms() * 4 + gx - 1) / gx));
   const int rpb = (a->R + splits - 1) / splits;
   splits = (a->R + rpb - 1) / rpb;
-  colsum_kernel<<<dim3(gx, splits), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a->in, a->out, a->R, a->C, a->ld, rpb);
+  colsum_kernel<<<dim3(gx, splits), CS_WARPS * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a->in, a->out, a->R, a->C, a->ld, rpb);
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }

@@ -97,7 +97,7 @@ class PretrainFn(torch.autograd.Function):
         S = Q + L
         H = gcfg["hidden_size"]
         pos = W[engine.GPT + "embedding.position_embeddings.weight"]
-        x_in = torch.empty((B * S, H), device=video.device, dtype=bf16)
+        x_in = torch.empty((B * S, H), device=video.device, dtype=torch.float32)  # fp32 residual stream
         # visual_fc (+ optional visual_norm is Identity without connect_ln) written straight into the
         # decoder input rows [b*S, b*S+Q) with the learned positions added (:136,:155-156; GPT3Embedding :646-650)
         ops.gemm(q, W["visual_fc.weight"], bias=W["visual_fc.bias"], residual=pos, res_row_mod=Q, out=x_in,
@@ -235,7 +235,7 @@ class GptFn(torch.autograd.Function):
         W = {k: as_bf16(p) for k, p in zip(keys, params)}
         B, S, H = input_embeds.shape
         pos = W[engine.GPT + "embedding.position_embeddings.weight"]
-        x_in = (input_embeds.to(bf16) + pos[:S][None]).reshape(B * S, H).contiguous()
+        x_in = (input_embeds.float() + pos[:S][None].float()).reshape(B * S, H).contiguous()  # fp32 stream
         need_bwd = any(ctx.needs_input_grad)
         train_gpt = any(n for k, n in zip(keys, ctx.needs_input_grad[5:]) if k.startswith(engine.GPT + "encoder.layers"))
         hid, cg = engine.gpt_fwd(W, x_in, gcfg, B, S, train_w=train_gpt, save=need_bwd)

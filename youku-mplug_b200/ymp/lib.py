@@ -41,7 +41,7 @@ class GemmArgs(C.Structure):
         ("act", c_i32), ("aux_out", c_vp), ("aux_in", c_vp),
         ("out_dtype", c_i32), ("accumulate", c_i32), ("split_k", c_i32),
         ("alpha", C.c_float), ("tile_n", c_i32),
-        ("res_row_mod", c_i32), ("d_row_block", c_i32), ("d_row_stride", c_i32),
+        ("res_row_mod", c_i32), ("d_row_block", c_i32), ("d_row_stride", c_i32), ("residual_dtype", c_i32),
     ]
 
 
@@ -49,7 +49,7 @@ class LayerNormArgs(C.Structure):
     _fields_ = [
         ("x", c_vp), ("gamma", c_vp), ("beta", c_vp), ("y", c_vp), ("mean", c_vp), ("rstd", c_vp),
         ("in_rows", c_vp), ("rows", c_i32), ("D", c_i32), ("ldx", c_i32), ("ldy", c_i32),
-        ("eps", C.c_float),
+        ("eps", C.c_float), ("x_dtype", c_i32), ("y_dtype", c_i32),
     ]
 
 
@@ -57,7 +57,7 @@ class LayerNormBwdArgs(C.Structure):
     _fields_ = [
         ("dy", c_vp), ("x", c_vp), ("gamma", c_vp), ("mean", c_vp), ("rstd", c_vp), ("add", c_vp),
         ("dx", c_vp), ("dgamma", c_vp), ("dbeta", c_vp), ("in_rows", c_vp),
-        ("rows", c_i32), ("D", c_i32), ("ldx", c_i32), ("lddy", c_i32), ("ldadd", c_i32),
+        ("rows", c_i32), ("D", c_i32), ("ldx", c_i32), ("lddy", c_i32), ("ldadd", c_i32), ("x_dtype", c_i32),
     ]
 
 
@@ -96,7 +96,8 @@ class Im2colArgs(C.Structure):
 
 class EmbedArgs(C.Structure):
     _fields_ = [("ids", c_vp), ("table", c_vp), ("pos", c_vp), ("out", c_vp), ("B", c_i32), ("L", c_i32),
-                ("S", c_i32), ("row_offset", c_i32), ("hidden", c_i32), ("vocab", c_i32), ("ldo", c_i32)]
+                ("S", c_i32), ("row_offset", c_i32), ("hidden", c_i32), ("vocab", c_i32), ("ldo", c_i32),
+                ("out_dtype", c_i32)]
 
 
 class CeArgs(C.Structure):

@@ -44,6 +44,9 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, 
     g.bias = L.ptr(bias)
     g.residual = L.ptr(residual)
     g.ldr = residual.stride(0) if residual is not None else 0
+    if residual is not None:
+        assert residual.dtype in (bf16, torch.float32) and residual.stride(1) == 1
+        g.residual_dtype = DT_F32 if residual.dtype == torch.float32 else DT_BF16
     g.act = act
     if aux_out is not None:
         assert aux_out.dtype == bf16 and aux_out.shape == (M, N) and aux_out.stride(0) == out.stride(0)
@@ -61,19 +64,21 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, 
 
 
 # ---------------------------------------------------------------------------------- LayerNorm
-def layernorm_fwd(x, gamma, beta, eps, out=None, in_rows=None, rows=None, stats=True):
-    """y = LN(x) row-wise (fp32 statistics).  Returns (y, mean, rstd)."""
+def layernorm_fwd(x, gamma, beta, eps, out=None, in_rows=None, rows=None, stats=True, out_dtype=bf16):
+    """y = LN(x) row-wise (fp32 statistics); x and y may each be bf16 or fp32.  Returns (y, mean, rstd)."""
     _chk2d(x, "x")
     D = x.shape[1]
     rows = rows if rows is not None else (in_rows.numel() if in_rows is not None else x.shape[0])
     if out is None:
-        out = torch.empty((rows, D), device=x.device, dtype=bf16)
+        out = torch.empty((rows, D), device=x.device, dtype=out_dtype)
     mean = torch.empty(rows, device=x.device, dtype=torch.float32) if stats else None
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if stats else None
     a = L.LayerNormArgs()
     a.x, a.gamma, a.beta, a.y = x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr()
     a.mean, a.rstd, a.in_rows = L.ptr(mean), L.ptr(rstd), L.ptr(in_rows)
     a.rows, a.D, a.ldx, a.ldy, a.eps = rows, D, x.stride(0), out.stride(0), eps
+    a.x_dtype = DT_F32 if x.dtype == torch.float32 else DT_BF16
+    a.y_dtype = DT_F32 if out.dtype == torch.float32 else DT_BF16
     L.call(L._ln_fwd, a, "ymp_layernorm_fwd")
     return out, mean, rstd
 
@@ -90,6 +95,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, add=None, dgamma=None, dbeta=None, i
     a.add, a.dx, a.dgamma, a.dbeta, a.in_rows = L.ptr(add), dx.data_ptr(), L.ptr(dgamma), L.ptr(dbeta), L.ptr(in_rows)
     a.rows, a.D, a.ldx, a.lddy = rows, D, x.stride(0), dy.stride(0)
     a.ldadd = add.stride(0) if add is not None else 0
+    a.x_dtype = DT_F32 if x.dtype == torch.float32 else DT_BF16
+    assert dx.dtype == bf16 and dy.dtype == bf16
     L.call(L._ln_bwd, a, "ymp_layernorm_bwd")
     return dx
 
@@ -212,6 +219,7 @@ def embed_gather(ids, table, pos, out, S, row_offset):
     a.ids, a.table, a.pos, a.out = ids.data_ptr(), table.data_ptr(), L.ptr(pos), out.data_ptr()
     a.B, a.L, a.S, a.row_offset = B, Ln, S, row_offset
     a.hidden, a.vocab, a.ldo = table.shape[1], table.shape[0], out.stride(0)
+    a.out_dtype = DT_F32 if out.dtype == torch.float32 else DT_BF16
     L.call(L._embed, a, "ymp_embed_gather")
     return out
 
