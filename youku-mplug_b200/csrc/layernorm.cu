@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
     if (irow < 0) continue;  // padding slot of the forward: no input row behind it
     const uint4* dyr = reinterpret_cast<const uint4*>(p.dy + (size_t)row * p.lddy);
     const float mu = p.mean[row], rs = p.rstd[row];
-    float xh[VPL][8], gy[VPL][8];
+    // Two passes over the row keep the register footprint small (high occupancy for an HBM-bound
+    // kernel); the second pass re-reads the 3-8 KB row from L1/L2, not from HBM.
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
@@ -155,15 +156,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
         unpack8(__ldg(g4 + vi), g);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          xh[j][e] = (xv[e] - mu) * rs;
-          gy[j][e] = dyv[e] * g[e];
-          s1 += gy[j][e];
-          s2 += gy[j][e] * xh[j][e];
-          if (WGRAD) { dg[j][e] += dyv[e] * xh[j][e]; db[j][e] += dyv[e]; }
+          const float xh = (xv[e] - mu) * rs, gy = dyv[e] * g[e];
+          s1 += gy;
+          s2 += gy * xh;
+          if (WGRAD) { dg[j][e] += dyv[e] * xh; db[j][e] += dyv[e]; }
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { xh[j][e] = 0.f; gy[j][e] = 0.f; }
       }
     }
     s1 = warp_sum(s1) / (float)p.D;
@@ -174,9 +171,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams
     for (int j = 0; j < VPL; ++j) {
       const int vi = j * 32 + lane;
       if (vi < nvec) {
-        float o[8];
+        float xv[8], dyv[8], g[8], o[8];
+        load8<XF32>(p.x, (size_t)irow, p.ldx, vi, xv);
+        unpack8(__ldg(dyr + vi), dyv);
+        unpack8(__ldg(g4 + vi), g);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = rs * (gy[j][e] - s1 - xh[j][e] * s2);
+        for (int e = 0; e < 8; ++e) o[e] = rs * (dyv[e] * g[e] - s1 - (xv[e] - mu) * rs * s2);
         if (ar) {
           float a[8];
           unpack8(__ldg(ar + vi), a);
