@@ -12,6 +12,7 @@
 // cls row, abstractor cross attention).  Mask modes: none, causal, block-diagonal (packs many
 // short TimeSformer temporal sequences into one 64-row tile).
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -222,7 +223,14 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
     if (warp_active) {
       // number of key columns of this tile this warp actually needs (warp-uniform)
       int nv = min(64, skv - kv0);
+      int nb_lo = 0;  // first 16-column group this warp needs (block mask: only its own diagonal blocks)
       if (p.mask == MASK_CAUSAL) nv = min(nv, q0 + warp * 16 + 16 - kv0);
+      if (p.mask == MASK_BLOCK) {
+        const int r_lo = q0 + warp * 16;
+        const int c_lo = (r_lo / p.mask_block) * p.mask_block, c_hi = ((r_lo + 15) / p.mask_block + 1) * p.mask_block;
+        nb_lo = max(0, (c_lo - kv0) / 16);
+        nv = min(nv, c_hi - kv0);
+      }
       float sc[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i) { sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f; }
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
       for (int kk = 0; kk < KS; ++kk) {
 #pragma unroll
         for (int nbp = 0; nbp < 4; ++nbp) {
-          if (nbp * 16 < nv) {
+          if (nbp * 16 < nv && nbp >= nb_lo) {
             uint32_t b[4];
             ldsm_x4(b, smem_u32(Ks + (nbp * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + kk * 16 + ((lane >> 3) & 1) * 8));
             mma16816(sc[2 * nbp], qf[kk], b[0], b[1]);
@@ -274,7 +282,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
       }
 #pragma unroll
       for (int kk2 = 0; kk2 < 4; ++kk2) {
-        if (kk2 * 16 < nv) {
+        if (kk2 * 16 < nv && kk2 >= nb_lo) {
           uint32_t pa[4];
           pa[0] = pack_bf16(sc[2 * kk2][0], sc[2 * kk2][1]);
           pa[1] = pack_bf16(sc[2 * kk2][2], sc[2 * kk2][3]);
@@ -404,7 +412,14 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnKParams p) {
     }
     if (warp_active) {
       int nv = min(64, skv - kv0);
+      int nb_lo = 0;  // first 16-column group this warp needs (block mask: only its own diagonal blocks)
       if (p.mask == MASK_CAUSAL) nv = min(nv, q0 + warp * 16 + 16 - kv0);
+      if (p.mask == MASK_BLOCK) {
+        const int r_lo = q0 + warp * 16;
+        const int c_lo = (r_lo / p.mask_block) * p.mask_block, c_hi = ((r_lo + 15) / p.mask_block + 1) * p.mask_block;
+        nb_lo = max(0, (c_lo - kv0) / 16);
+        nv = min(nv, c_hi - kv0);
+      }
       float sc[8][4], dp[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -415,7 +430,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnKParams p) {
       for (int kk = 0; kk < KS; ++kk) {
 #pragma unroll
         for (int nbp = 0; nbp < 4; ++nbp) {
-          if (nbp * 16 < nv) {
+          if (nbp * 16 < nv && nbp >= nb_lo) {
             uint32_t b[4];
             const int off = (nbp * 16 + (lane & 7) + (lane >> 4) * 8) * LDS + kk * 16 + ((lane >> 3) & 1) * 8;
             ldsm_x4(b, smem_u32(Ks + off));
@@ -439,7 +454,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnKParams p) {
       }
 #pragma unroll
       for (int kk2 = 0; kk2 < 4; ++kk2) {
-        if (kk2 * 16 < nv) {
+        if (kk2 * 16 < nv && kk2 >= nb_lo) {
           uint32_t da[4];
           da[0] = pack_bf16(sc[2 * kk2][0], sc[2 * kk2][1]);
           da[1] = pack_bf16(sc[2 * kk2][2], sc[2 * kk2][3]);
@@ -537,9 +552,15 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnKParams p)
     __syncthreads();
     if (warp_active) {
       // query columns of this tile this warp needs (warp-uniform)
-      const int nv = min(64, sq - qi0);
+      int nv = min(64, sq - qi0);
       int nb_lo = 0;  // causal: queries below the first key row of this warp contribute nothing
       if (p.mask == MASK_CAUSAL) nb_lo = max(0, (kv0 + warp * 16 - qi0) / 16);
+      if (p.mask == MASK_BLOCK) {  // only the query blocks on this warp's diagonal
+        const int k_lo = kv0 + warp * 16;
+        const int c_lo = (k_lo / p.mask_block) * p.mask_block, c_hi = ((k_lo + 15) / p.mask_block + 1) * p.mask_block;
+        nb_lo = max(0, (c_lo - qi0) / 16);
+        nv = min(nv, c_hi - qi0);
+      }
       float st_[8][4], dpt[8][4];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -697,6 +718,8 @@ static int launch_bwd(const AttnKParams& p, cudaStream_t st) {
 
 }  // namespace ymp
 
+namespace ymp { int attn_tc_fwd_try(const ymp_attn_args* a, cudaStream_t st); }
+
 extern "C" int ymp_attn_fwd(const ymp_attn_args* a, void* stream) {
   using namespace ymp;
   AttnKParams p = {};
@@ -704,6 +727,12 @@ extern "C" int ymp_attn_fwd(const ymp_attn_args* a, void* stream) {
   if (rc) return rc;
   YMP_CHECK_ARG(a->o && aligned16(a->o), "ymp_attn_fwd: bad o");
   cudaStream_t st = (cudaStream_t)stream;
+  // short key ranges run on the tcgen05 kernel (attention_tc.cu); YMP_ATTN_LEGACY=1 forces mma.sync
+  static const bool legacy = [] { const char* e = getenv("YMP_ATTN_LEGACY"); return e && e[0] == '1'; }();
+  if (!legacy) {
+    rc = attn_tc_fwd_try(a, st);
+    if (rc != YMP_ENOSUP) return rc;
+  }
   switch (a->head_dim) {
     case 64: return launch_fwd<64>(p, st);
     case 80: return launch_fwd<80>(p, st);

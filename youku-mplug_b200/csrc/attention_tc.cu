@@ -1,0 +1,351 @@
+// tcgen05 attention forward for short key ranges (s_kv <= 256): ViT spatial (197), packed temporal,
+// GPT causal (256).  One CTA = 128 query rows of one (sequence, head):
+//   1. cp.async gathers Q [128 x HD], K, V [Nkv x HD] through the seqmap into shared memory laid out
+//      exactly as the UMMA canonical SWIZZLE_128B (first 64 head-dim columns) / SWIZZLE_64B (columns
+//      64..95 when HD = 96) tiles
+//   2. one elected thread issues S[128 x Nkv] = Q K^T  (tcgen05.mma, K-major A and B, fp32 in TMEM)
+//   3. 128 threads (thread = row = TMEM lane) do the exact softmax over the whole row with two passes of
+//      tcgen05.ld, and write P as packed bf16 back into the same TMEM columns (tcgen05.st)
+//   4. O[128 x HD] = P V  with A = P read from TMEM and B = V as an MN-major smem operand
+//   5. tcgen05.ld O, scale by 1/l, 16-byte row stores + lse
+// No online-softmax rescaling, no KV loop, no register-resident accumulators.  TMEM use is 256 columns
+// (S/P in [0,256), O aliased onto [128,224) once S is consumed), shared memory ~80-105 KB, so two CTAs
+// share an SM and overlap each other's load / MMA / softmax phases.
+#include <math_constants.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ymp {
+
+struct TcSeqMap {
+  int seq_div, n_prefix, prefix_per_seq;
+  long outer_stride, inner_stride, pos_stride, prefix_base, prefix_stride;
+};
+struct TcMat {
+  const __nv_bfloat16* base;
+  const __nv_bfloat16* prefix;
+  long stride;
+  int ld, n_prefix;
+};
+__device__ __forceinline__ TcMat tc_mat(const __nv_bfloat16* p, const TcSeqMap& m, int s, int ld, int col_off) {
+  const int outer = s / m.seq_div, inner = s - outer * m.seq_div;
+  TcMat r;
+  r.base = p + ((long)outer * m.outer_stride + (long)inner * m.inner_stride) * ld + col_off;
+  r.prefix = p + (m.prefix_base + (long)(m.prefix_per_seq ? s : outer) * m.prefix_stride) * ld + col_off;
+  r.stride = m.pos_stride * ld;
+  r.ld = ld;
+  r.n_prefix = m.n_prefix;
+  return r;
+}
+__device__ __forceinline__ const __nv_bfloat16* tc_row(const TcMat& m, int i) {
+  return i < m.n_prefix ? m.prefix + (long)i * m.ld : m.base + (long)(i - m.n_prefix) * m.stride;
+}
+
+struct AttnTcParams {
+  const __nv_bfloat16 *q, *k, *v;
+  __nv_bfloat16* o;
+  float* lse;
+  int ldq, ldk, ldv, ldo, hsq, hsk, hsv, hso;
+  TcSeqMap mq, mkv, mo;
+  int n_seq, n_heads, s_q, s_kv, mask, mask_block;
+  long total_rows;
+  float scale_log2, scale;
+  int kv_rows;  // rows of the K/V smem tiles = round32(s_kv)
+};
+
+__device__ __forceinline__ void cp16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+// byte offset of 16-byte chunk c16 of row r inside a SWIZZLE_128B block ([rows][64 bf16]) / SWIZZLE_64B
+// block ([rows][32 bf16])
+__device__ __forceinline__ uint32_t sw128_off(int r, int c16) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ uint32_t sw64_off(int r, int c16) {
+  return (uint32_t)((r >> 3) * 512 + (r & 7) * 64 + ((c16 ^ ((r >> 1) & 3)) << 4));
+}
+// smem descriptors: K-major / MN-major both use (SBO = one 8-row group, layout type)
+__device__ __forceinline__ uint64_t desc_sw(uint32_t saddr, uint32_t sbo, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;  // LBO (unused: single swizzle atom along the leading dimension)
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr int TC_MASK_CAUSAL = 1, TC_MASK_BLOCK = 2;
+constexpr int LAYOUT_SW128 = 2, LAYOUT_SW64 = 4;
+
+// Load `rows` rows x HD columns into the swizzled blocks (rows beyond n_valid are zero-filled).
+// thread -> (row = tid/4 within a 32-row pass, 16-byte chunks tid%4 + 4j): one row pointer per thread and
+// pass, 4 consecutive lanes fetch 64 contiguous bytes.
+template <int HD>
+__device__ __forceinline__ void tc_load(uint8_t* blk0, uint8_t* blk1, const TcMat& m, int r0, int rows, int n_valid) {
+  constexpr int CPT = HD / 32;  // chunks per thread per row
+  const int rl = threadIdx.x >> 2, c0 = threadIdx.x & 3;
+  for (int rb = 0; rb < rows; rb += 32) {
+    const int r = rb + rl;
+    if (r >= rows) break;
+    if (r0 + r < n_valid) {
+      const __nv_bfloat16* g = tc_row(m, r0 + r);
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = c0 + 4 * j;
+        cp16((c < 8) ? blk0 + sw128_off(r, c) : blk1 + sw64_off(r, c - 8), g + c * 8);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = c0 + 4 * j;
+        *reinterpret_cast<uint4*>((c < 8) ? blk0 + sw128_off(r, c) : blk1 + sw64_off(r, c - 8)) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) {
+  static_assert(HD == 64 || HD == 96, "head_dim 64 or 96");
+  constexpr bool TWO = (HD == 96);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  const int kvr = p.kv_rows;
+  uint8_t* q0s = smem;                                  // 128 x 128 B
+  uint8_t* k0s = q0s + 128 * 128;                       // kvr x 128 B
+  uint8_t* v0s = k0s + kvr * 128;                       // kvr x 128 B
+  uint8_t* q1s = v0s + kvr * 128;                       // 128 x 64 B   (HD = 96 only)
+  uint8_t* k1s = q1s + (TWO ? 128 * 64 : 0);
+  uint8_t* v1s = k1s + (TWO ? kvr * 64 : 0);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(v1s + (TWO ? kvr * 64 : 0));  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, s = blockIdx.z;
+  int sq = p.s_q, skv = p.s_kv;
+  if (p.total_rows > 0) {
+    const long left = p.total_rows - (long)s * p.s_q;
+    if (left < sq) sq = (int)left;
+    if (left < skv) skv = (int)left;
+  }
+  if (q0 >= sq) return;
+  // key range this tile needs
+  int kv_end = skv;
+  if (p.mask == TC_MASK_CAUSAL) kv_end = min(skv, q0 + 128);
+  const int nkv = (kv_end + 31) & ~31;  // MMA N / K extent (multiple of 32, <= 256)
+
+  if (warp == 0) tmem_alloc<256>(tmem_ptr);
+  if (threadIdx.x == 32) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  {
+    const TcMat Mq = tc_mat(p.q, p.mq, s, p.ldq, h * p.hsq);
+    const TcMat Mk = tc_mat(p.k, p.mkv, s, p.ldk, h * p.hsk);
+    const TcMat Mv = tc_mat(p.v, p.mkv, s, p.ldv, h * p.hsv);
+    tc_load<HD>(q0s, q1s, Mq, q0, 128, sq);
+    tc_load<HD>(k0s, k1s, Mk, 0, nkv, kv_end);
+    tc_load<HD>(v0s, v1s, Mv, 0, nkv, kv_end);
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  fence_proxy_async();  // smem written through the generic proxy is read by the tensor core's async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+
+  // ---- S = Q K^T
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, nkv, 0, 0);
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      uint64_t ad, bd;
+      if (ks < 4) {
+        ad = desc_sw(smem_u32(q0s) + ks * 32, 1024, LAYOUT_SW128);
+        bd = desc_sw(smem_u32(k0s) + ks * 32, 1024, LAYOUT_SW128);
+      } else {
+        ad = desc_sw(smem_u32(q1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
+        bd = desc_sw(smem_u32(k1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
+      }
+      umma_bf16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(&bar[0]);
+  }
+  mbar_wait(&bar[0], 0);
+  tc_fence_after();
+
+  // ---- exact softmax: thread = query row = TMEM lane
+  const int row = q0 + warp * 32 + lane;
+  const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+  // valid key columns of this row form one interval [lo, hi): bounds + causal + block-diagonal masks
+  int lo = 0, hi = kv_end;
+  if (p.mask == TC_MASK_CAUSAL) hi = min(hi, row + 1);
+  if (p.mask == TC_MASK_BLOCK) { lo = (row / p.mask_block) * p.mask_block; hi = min(hi, lo + p.mask_block); }
+  float mx = -CUDART_INF_F;
+  const int nch = nkv / 32;
+  for (int c = 0; c < nch; ++c) {
+    // tcgen05.ld is .sync.aligned: the skip decision must be warp-uniform
+    if (__all_sync(0xffffffffu, c * 32 >= hi || c * 32 + 32 <= lo)) continue;
+    uint32_t r[32];
+    tmem_ld32(tl + c * 32, r);
+    tmem_ld_wait();
+    if (c * 32 >= lo && c * 32 + 32 <= hi) {           // fully valid: no per-element masking
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int col = c * 32 + i;
+        if (col >= lo && col < hi) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+    }
+  }
+  const float ms = (mx == -CUDART_INF_F) ? 0.f : mx * p.scale_log2;
+  float lsum = 0.f;
+  for (int c = 0; c < nch; ++c) {
+    uint32_t pk[16];
+    if (__all_sync(0xffffffffu, c * 32 >= hi || c * 32 + 32 <= lo)) {   // warp-uniform
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = 0u;
+    } else {
+      uint32_t r[32];
+      tmem_ld32(tl + c * 32, r);
+      tmem_ld_wait();
+      float pv[32];
+      if (c * 32 >= lo && c * 32 + 32 <= hi) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pv[i] = exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -ms));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = c * 32 + i;
+          pv[i] = (col >= lo && col < hi) ? exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -ms)) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) lsum += pv[i];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+    }
+    tmem_st16(tl + c * 16, pk);  // P (bf16 pairs) overwrites S columns that are already consumed
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // ---- O = P V   (A = P from TMEM, B = V MN-major)
+  constexpr uint32_t O_COL = 128;
+  if (threadIdx.x == 0) {
+    const uint32_t id64 = make_idesc_bf16(128, 64, 0, 1);
+    const uint32_t id32 = make_idesc_bf16(128, 32, 0, 1);
+    const int nks = nkv / 16;
+    for (int ks = 0; ks < nks; ++ks) {
+      umma_ts(tmem + O_COL, tmem + ks * 8, desc_sw(smem_u32(v0s) + ks * 2048, 1024, LAYOUT_SW128), id64, ks > 0 ? 1u : 0u);
+      if (TWO)
+        umma_ts(tmem + O_COL + 64, tmem + ks * 8, desc_sw(smem_u32(v1s) + ks * 1024, 512, LAYOUT_SW64), id32, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(&bar[1]);
+  }
+  mbar_wait(&bar[1], 0);
+  tc_fence_after();
+
+  // ---- epilogue
+  const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+  const bool valid = row < sq;
+  __nv_bfloat16* orow = nullptr;
+  if (valid) {
+    const TcMat Mo = tc_mat(p.o, p.mo, s, p.ldo, h * p.hso);
+    orow = const_cast<__nv_bfloat16*>(tc_row(Mo, row));
+  }
+#pragma unroll
+  for (int c = 0; c < HD / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(tl + O_COL + c * 32, r);
+    tmem_ld_wait();
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+        o.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+        o.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+        o.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + c * 32 + j * 8) = o;
+      }
+    }
+  }
+  if (valid && p.lse) p.lse[((size_t)s * p.n_heads + h) * p.s_q + row] = mx * p.scale + logf(lsum);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
+static TcSeqMap tc_map(const ymp_seqmap& m) {
+  TcSeqMap r;
+  r.seq_div = m.seq_div > 0 ? m.seq_div : 1;
+  r.n_prefix = m.n_prefix; r.prefix_per_seq = m.prefix_per_seq;
+  r.outer_stride = m.outer_stride; r.inner_stride = m.inner_stride; r.pos_stride = m.pos_stride;
+  r.prefix_base = m.prefix_base; r.prefix_stride = m.prefix_stride;
+  return r;
+}
+
+template <int HD>
+static int launch_tc(const AttnTcParams& p, cudaStream_t st) {
+  const int kvr = p.kv_rows;
+  const int smem = 128 * 128 + 2 * kvr * 128 + (HD == 96 ? 128 * 64 + 2 * kvr * 64 : 0) + 64 + 1024;
+  static int cur = 0;
+  if (smem > cur) { YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cur = smem; }
+  dim3 grid((p.s_q + 127) / 128, p.n_heads, p.n_seq);
+  attn_tc_fwd_kernel<HD><<<grid, 128, smem, st>>>(p);
+  YMP_LAUNCH_CHECK();
+  return YMP_OK;
+}
+
+// Returns YMP_ENOSUP (without setting an error) when the configuration is outside this kernel's domain.
+int attn_tc_fwd_try(const ymp_attn_args* a, cudaStream_t st) {
+  if (!(a->head_dim == 64 || a->head_dim == 96) || a->s_kv > 256) return YMP_ENOSUP;
+  // packed block-diagonal (temporal) sequences use 1/8 of each score tile: the mma.sync kernel,
+  // which skips the masked chunks per warp, measured faster there (0.113 vs 0.128 ms)
+  if (a->mask == YMP_MASK_BLOCK) return YMP_ENOSUP;
+  if (a->q_head_stride % 8 || a->ldo % 8 || a->o_head_stride % 8) return YMP_ENOSUP;
+  AttnTcParams p = {};
+  p.q = (const __nv_bfloat16*)a->q; p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v;
+  p.o = (__nv_bfloat16*)a->o; p.lse = a->lse;
+  p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.ldo = a->ldo;
+  p.hsq = a->q_head_stride; p.hsk = a->k_head_stride; p.hsv = a->v_head_stride; p.hso = a->o_head_stride;
+  p.mq = tc_map(a->map_q); p.mkv = tc_map(a->map_kv); p.mo = tc_map(a->map_o);
+  p.n_seq = a->n_seq; p.n_heads = a->n_heads; p.s_q = a->s_q; p.s_kv = a->s_kv;
+  p.mask = a->mask; p.mask_block = a->mask_block > 0 ? a->mask_block : 1; p.total_rows = a->total_rows;
+  p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.kv_rows = (a->s_kv + 31) & ~31;
+  return a->head_dim == 64 ? launch_tc<64>(p, st) : launch_tc<96>(p, st);
+}
+
+}  // namespace ymp
