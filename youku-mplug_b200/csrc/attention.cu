@@ -718,7 +718,10 @@ static int launch_bwd(const AttnKParams& p, cudaStream_t st) {
 
 }  // namespace ymp
 
-namespace ymp { int attn_tc_fwd_try(const ymp_attn_args* a, cudaStream_t st); }
+namespace ymp {
+int attn_tc_fwd_try(const ymp_attn_args* a, cudaStream_t st);
+int attn_tc_bwd_try(const ymp_attn_bwd_args* b, cudaStream_t st);
+}
 
 extern "C" int ymp_attn_fwd(const ymp_attn_args* a, void* stream) {
   using namespace ymp;
@@ -757,6 +760,11 @@ extern "C" int ymp_attn_bwd(const ymp_attn_bwd_args* b, void* stream) {
   p.hsdq = b->dq_head_stride; p.hsdk = b->dk_head_stride; p.hsdv = b->dv_head_stride;
   p.mdo = to_map(b->map_do); p.mdq = to_map(b->map_dq); p.mdkv = to_map(b->map_dkv);
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool legacy = [] { const char* e = getenv("YMP_ATTN_LEGACY"); return e && e[0] == '1'; }();
+  if (!legacy) {
+    rc = attn_tc_bwd_try(b, st);
+    if (rc != YMP_ENOSUP) return rc;
+  }
   switch (a->head_dim) {
     case 64: return launch_bwd<64>(p, st);
     case 80: return launch_bwd<80>(p, st);

@@ -307,6 +307,335 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
   }
 }
 
+// ======================================================================================================
+// tcgen05 attention backward for s_q, s_kv <= 256.  One CTA (256 threads) = one (sequence, head).
+// Everything is computed in the TRANSPOSED frame (TMEM lane = key row, TMEM column = query row) so that
+// P^T and dS^T feed the dV / dK MMAs straight from TMEM:
+//   for key block j (128 keys):  load K_j, V_j
+//     for query block i (<= 128 queries; causal: i >= j):  load Q_i, dO_i
+//       S^T  = K_j Q_i^T,  dP^T = V_j dO_i^T               (K-major smem operands, fp32 in TMEM)
+//       P^T  = exp2(S^T scale - lse),  dS^T = P^T (dP^T - delta)   (8 warps, tcgen05.ld; bf16 pairs are
+//              written back over consumed S^T / dP^T columns, dS^T additionally into smem)
+//       dV_j += P^T dO_i,  dK_j += dS^T Q_i                 (A from TMEM, B = the same dO_i / Q_i tiles MN-major)
+//       dQ_i(j) = dS K_j                                    (A = dS^T tile read MN-major, B = K_j MN-major)
+//       dQ_i: first key block's partial is parked in smem (bf16), the last adds it and stores
+//     store dK_j (x scale), dV_j
+// delta = rowsum(dO o O) is computed in the prologue; no global workspace, no atomics, deterministic.
+// TMEM (512 columns): S^T [0,128)  dP^T [128,256)  dV [256,256+HD)  dK [256+HD,256+2HD)  dQ [448,512)+[32,64)
+// ======================================================================================================
+struct AttnTcBwdParams {
+  const __nv_bfloat16 *q, *k, *v, *o, *dout;
+  __nv_bfloat16 *dq, *dk, *dv;
+  const float* lse;
+  int ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
+  int hsq, hsk, hsv, hso, hsdo, hsdq, hsdk, hsdv;
+  TcSeqMap mq, mkv, mo, mdo, mdq, mdkv;
+  int n_seq, n_heads, s_q, s_kv, mask;
+  long total_rows;
+  float scale_log2, scale;
+};
+
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// MN-major / K-major descriptor with an explicit leading-dimension byte offset
+__device__ __forceinline__ uint64_t desc_sw_lbo(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+// 256-thread tile loader: thread -> (row = tid/4 of a 64-row pass, 16-byte chunks tid%4 + 4j)
+template <int HD>
+__device__ __forceinline__ void tc_load256(uint8_t* blk0, uint8_t* blk1, const TcMat& m, int r0, int rows, int n_valid) {
+  constexpr int CPT = HD / 32;
+  const int rl = threadIdx.x >> 2, c0 = threadIdx.x & 3;
+  for (int rb = 0; rb < rows; rb += 64) {
+    const int r = rb + rl;
+    if (r >= rows) break;
+    if (r0 + r < n_valid) {
+      const __nv_bfloat16* g = tc_row(m, r0 + r);
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = c0 + 4 * j;
+        cp16((c < 8) ? blk0 + sw128_off(r, c) : blk1 + sw64_off(r, c - 8), g + c * 8);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = c0 + 4 * j;
+        *reinterpret_cast<uint4*>((c < 8) ? blk0 + sw128_off(r, c) : blk1 + sw64_off(r, c - 8)) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdParams p) {
+  static_assert(HD == 64 || HD == 96, "head_dim 64 or 96");
+  constexpr bool TWO = (HD == 96);
+  constexpr int PARK_LD = HD * 2 + 16;  // bytes per parked dQ row (padding spreads the banks)
+  constexpr uint32_t C_ST = 0, C_DPT = 128, C_DV = 256, C_DK = 256 + HD, C_DQ0 = 448, C_DQ1 = 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* k0s = smem;                    // [128][128 B] SWIZZLE_128B, head-dim columns 0..63
+  uint8_t* v0s = k0s + 16384;
+  uint8_t* q0s = v0s + 16384;
+  uint8_t* d0s = q0s + 16384;             // dO
+  uint8_t* dss = d0s + 16384;             // dS^T: 2 blocks (queries 0..63 / 64..127) of [128 keys][128 B]
+  uint8_t* k1s = dss + 32768;             // [128][64 B] SWIZZLE_64B, head-dim columns 64..95 (HD = 96)
+  uint8_t* v1s = k1s + (TWO ? 8192 : 0);
+  uint8_t* q1s = v1s + (TWO ? 8192 : 0);
+  uint8_t* d1s = q1s + (TWO ? 8192 : 0);
+  uint8_t* park = d1s + (TWO ? 8192 : 0);                                  // [2][128][PARK_LD]
+  float2* stats = reinterpret_cast<float2*>(park + 2 * 128 * PARK_LD);    // [256] (lse * log2e, delta)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stats + 256);               // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wq = warp & 3, half = warp >> 2;  // TMEM lane quarter, column half
+  const int h = blockIdx.x, s = blockIdx.y;
+  int sq = p.s_q, skv = p.s_kv;
+  if (p.total_rows > 0) {
+    const long left = p.total_rows - (long)s * p.s_q;
+    if (left <= 0) return;
+    if (left < sq) sq = (int)left;
+    if (left < skv) skv = (int)left;
+  }
+  const bool causal = p.mask == TC_MASK_CAUSAL;
+  const int nkb = (skv + 127) >> 7, nqb = (sq + 127) >> 7;
+
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  if (threadIdx.x == 32) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  const TcMat Mq = tc_mat(p.q, p.mq, s, p.ldq, h * p.hsq);
+  const TcMat Mk = tc_mat(p.k, p.mkv, s, p.ldk, h * p.hsk);
+  const TcMat Mv = tc_mat(p.v, p.mkv, s, p.ldv, h * p.hsv);
+  const TcMat Mdo = tc_mat(p.dout, p.mdo, s, p.lddo, h * p.hsdo);
+  // ---- prologue: per-query statistics
+  {
+    const int r = threadIdx.x;
+    float2 st = make_float2(1e30f, 0.f);  // rows that do not exist: P = exp2(x - 1e30) = 0
+    if (r < sq) {
+      const TcMat Mo = tc_mat(p.o, p.mo, s, p.ldo, h * p.hso);
+      const uint4* po = reinterpret_cast<const uint4*>(tc_row(Mo, r));
+      const uint4* pd = reinterpret_cast<const uint4*>(tc_row(Mdo, r));
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < HD / 8; ++c) {
+        const uint4 a = __ldg(po + c), b = __ldg(pd + c);
+        acc += bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) + bf16_hi(a.y) * bf16_hi(b.y) +
+               bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) + bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
+      }
+      st.x = p.lse[((size_t)s * p.n_heads + h) * p.s_q + r] * 1.4426950408889634f;
+      st.y = acc;
+    }
+    stats[r] = st;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tl = tmem + ((uint32_t)(wq * 32) << 16);
+  const int kr = wq * 32 + lane;  // this thread's TMEM lane: key row (softmax, dK/dV) or query row (dQ)
+
+  int it = 0;
+  for (int j = 0; j < nkb; ++j) {
+    const int kj0 = j * 128;
+    const int nk = min(128, (skv - kj0 + 31) & ~31);  // key extent of this block used as an MMA K dimension
+    tc_load256<HD>(k0s, k1s, Mk, kj0, 128, skv);
+    tc_load256<HD>(v0s, v1s, Mv, kj0, 128, skv);
+    const int i0 = causal ? j : 0;
+    for (int i = i0; i < nqb; ++i, ++it) {
+      const int qi0 = i * 128;
+      const int nq = min(128, (sq - qi0 + 31) & ~31);  // query extent (MMA N of S^T / K of dV, dK)
+      tc_load256<HD>(q0s, q1s, Mq, qi0, nq, sq);
+      tc_load256<HD>(d0s, d1s, Mdo, qi0, nq, sq);
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      // ---- S^T = K_j Q_i^T, dP^T = V_j dO_i^T
+      if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, nq, 0, 0);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          uint64_t ad, bd;
+          if (ks < 4) {
+            ad = desc_sw(smem_u32(k0s) + ks * 32, 1024, LAYOUT_SW128);
+            bd = desc_sw(smem_u32(q0s) + ks * 32, 1024, LAYOUT_SW128);
+          } else {
+            ad = desc_sw(smem_u32(k1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
+            bd = desc_sw(smem_u32(q1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
+          }
+          umma_bf16(tmem + C_ST, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          uint64_t ad, bd;
+          if (ks < 4) {
+            ad = desc_sw(smem_u32(v0s) + ks * 32, 1024, LAYOUT_SW128);
+            bd = desc_sw(smem_u32(d0s) + ks * 32, 1024, LAYOUT_SW128);
+          } else {
+            ad = desc_sw(smem_u32(v1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
+            bd = desc_sw(smem_u32(d1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
+          }
+          umma_bf16(tmem + C_DPT, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(&bar[0]);
+      }
+      mbar_wait(&bar[0], it & 1);
+      tc_fence_after();
+
+      // ---- P^T and dS^T: warp (wq, half) owns key rows wq*32.. and query columns half*64..half*64+63
+      const bool diag = causal && (i == j);
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;     // 32-column chunk of the 128 query columns
+        if (c * 32 >= nq) break;         // warp-uniform
+        uint32_t sr[32], dr[32];
+        tmem_ld32(tl + C_ST + c * 32, sr);
+        tmem_ld32(tl + C_DPT + c * 32, dr);
+        tmem_ld_wait();
+        uint32_t ppk[16], dpk[16];
+        const float4* st4 = reinterpret_cast<const float4*>(stats + qi0 + c * 32);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float4 st = st4[e];  // (lse2, delta) of two consecutive queries, warp-broadcast
+          float p0 = ex2_fast(fmaf(__uint_as_float(sr[2 * e]), p.scale_log2, -st.x));
+          float p1 = ex2_fast(fmaf(__uint_as_float(sr[2 * e + 1]), p.scale_log2, -st.z));
+          if (diag) {  // key kj0 + kr attends query qi0 + col only if key <= query
+            if (c * 32 + 2 * e < kr) p0 = 0.f;
+            if (c * 32 + 2 * e + 1 < kr) p1 = 0.f;
+          }
+          const float d0 = p0 * (__uint_as_float(dr[2 * e]) - st.y);
+          const float d1 = p1 * (__uint_as_float(dr[2 * e + 1]) - st.w);
+          ppk[e] = pack_bf16(p0, p1);
+          dpk[e] = pack_bf16(d0, d1);
+        }
+        const uint32_t pc = half * 64 + cc * 16;  // packed pairs land inside this warp's consumed columns
+        tmem_st16(tl + C_ST + pc, ppk);
+        tmem_st16(tl + C_DPT + pc, dpk);
+        uint8_t* dsb = dss + half * 16384;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(dsb + sw128_off(kr, cc * 4 + g)) = make_uint4(dpk[4 * g], dpk[4 * g + 1], dpk[4 * g + 2], dpk[4 * g + 3]);
+      }
+      tmem_st_wait();
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+
+      // ---- dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i(j) = dS K_j
+      if (threadIdx.x == 0) {
+        const uint32_t id64 = make_idesc_bf16(128, 64, 0, 1), id32 = make_idesc_bf16(128, 32, 0, 1);
+        const int nks = nq / 16;
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint32_t acc = (i > i0 || ks > 0) ? 1u : 0u;
+          const uint32_t acol = (ks < 4) ? ks * 8 : 64 + (ks - 4) * 8;  // packed pairs: queries 0..63 at +0, 64..127 at +64
+          umma_ts(tmem + C_DV, tmem + C_ST + acol, desc_sw(smem_u32(d0s) + ks * 2048, 1024, LAYOUT_SW128), id64, acc);
+          if (TWO) umma_ts(tmem + C_DV + 64, tmem + C_ST + acol, desc_sw(smem_u32(d1s) + ks * 1024, 512, LAYOUT_SW64), id32, acc);
+          umma_ts(tmem + C_DK, tmem + C_DPT + acol, desc_sw(smem_u32(q0s) + ks * 2048, 1024, LAYOUT_SW128), id64, acc);
+          if (TWO) umma_ts(tmem + C_DK + 64, tmem + C_DPT + acol, desc_sw(smem_u32(q1s) + ks * 1024, 512, LAYOUT_SW64), id32, acc);
+        }
+        const uint32_t iq64 = make_idesc_bf16(128, 64, 1, 1), iq32 = make_idesc_bf16(128, 32, 1, 1);
+        const int nkk = nk / 16;
+        for (int ks = 0; ks < nkk; ++ks) {
+          const uint64_t ad = desc_sw_lbo(smem_u32(dss) + ks * 2048, 16384, 1024, LAYOUT_SW128);
+          umma_bf16(tmem + C_DQ0, ad, desc_sw(smem_u32(k0s) + ks * 2048, 1024, LAYOUT_SW128), iq64, ks > 0 ? 1u : 0u);
+          if (TWO) umma_bf16(tmem + C_DQ1, ad, desc_sw(smem_u32(k1s) + ks * 1024, 512, LAYOUT_SW64), iq32, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(&bar[1]);
+      }
+      mbar_wait(&bar[1], it & 1);
+      tc_fence_after();
+
+      // ---- dQ_i: TMEM lane = query row; chunk c of HD/32 handled by warpgroup c & 1
+      {
+        const int jl = causal ? min(i, nkb - 1) : nkb - 1;  // last key block contributing to this query block
+        const int row = qi0 + kr;
+        uint8_t* prow = park + ((size_t)(i * 128 + kr)) * PARK_LD;
+        __nv_bfloat16* grow = nullptr;
+        if (j == jl && row < sq) {
+          const TcMat Mdq = tc_mat(p.dq, p.mdq, s, p.lddq, h * p.hsdq);
+          grow = const_cast<__nv_bfloat16*>(tc_row(Mdq, row));
+        }
+#pragma unroll
+        for (int c = 0; c < HD / 32; ++c) {
+          if ((c & 1) != half) continue;
+          uint32_t r[32];
+          tmem_ld32(tl + (c < 2 ? C_DQ0 + c * 32 : C_DQ1), r);
+          tmem_ld_wait();
+          if (j < jl) {  // park this key block's partial
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<uint4*>(prow + c * 64 + g * 16) =
+                  make_uint4(pack_bf16(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1])), pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3])),
+                             pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5])), pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
+          } else if (grow) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[8 * g + e]);
+              if (j > 0) {
+                const uint4 pk = *reinterpret_cast<const uint4*>(prow + c * 64 + g * 16);
+                f[0] += bf16_lo(pk.x); f[1] += bf16_hi(pk.x); f[2] += bf16_lo(pk.y); f[3] += bf16_hi(pk.y);
+                f[4] += bf16_lo(pk.z); f[5] += bf16_hi(pk.z); f[6] += bf16_lo(pk.w); f[7] += bf16_hi(pk.w);
+              }
+              *reinterpret_cast<uint4*>(grow + c * 32 + g * 8) =
+                  make_uint4(pack_bf16(f[0] * p.scale, f[1] * p.scale), pack_bf16(f[2] * p.scale, f[3] * p.scale),
+                             pack_bf16(f[4] * p.scale, f[5] * p.scale), pack_bf16(f[6] * p.scale, f[7] * p.scale));
+            }
+          }
+        }
+      }
+    }
+    // ---- dV_j (warpgroup 0) and dK_j x scale (warpgroup 1): TMEM lane = key row
+    {
+      const int krow = kj0 + kr;
+      __nv_bfloat16* grow = nullptr;
+      if (krow < skv) {
+        const TcMat Mg = tc_mat(half ? p.dk : p.dv, p.mdkv, s, half ? p.lddk : p.lddv, h * (half ? p.hsdk : p.hsdv));
+        grow = const_cast<__nv_bfloat16*>(tc_row(Mg, krow));
+      }
+      const float sc = half ? p.scale : 1.f;
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tl + (half ? C_DK : C_DV) + c * 32, r);
+        tmem_ld_wait();
+        if (grow) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(grow + c * 32 + g * 8) =
+                make_uint4(pack_bf16(__uint_as_float(r[8 * g]) * sc, __uint_as_float(r[8 * g + 1]) * sc), pack_bf16(__uint_as_float(r[8 * g + 2]) * sc, __uint_as_float(r[8 * g + 3]) * sc),
+                           pack_bf16(__uint_as_float(r[8 * g + 4]) * sc, __uint_as_float(r[8 * g + 5]) * sc), pack_bf16(__uint_as_float(r[8 * g + 6]) * sc, __uint_as_float(r[8 * g + 7]) * sc));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+
 static TcSeqMap tc_map(const ymp_seqmap& m) {
   TcSeqMap r;
   r.seq_div = m.seq_div > 0 ? m.seq_div : 1;
@@ -346,6 +675,42 @@ int attn_tc_fwd_try(const ymp_attn_args* a, cudaStream_t st) {
   p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
   p.kv_rows = (a->s_kv + 31) & ~31;
   return a->head_dim == 64 ? launch_tc<64>(p, st) : launch_tc<96>(p, st);
+}
+
+template <int HD>
+static int launch_tc_bwd(const AttnTcBwdParams& p, cudaStream_t st) {
+  const int smem = 4 * 16384 + 32768 + (HD == 96 ? 4 * 8192 : 0) + 2 * 128 * (HD * 2 + 16) + 256 * 8 + 64 + 1024;
+  static bool set = false;
+  if (!set) { YMP_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+  dim3 grid(p.n_heads, p.n_seq);
+  attn_tc_bwd_kernel<HD><<<grid, 256, smem, st>>>(p);
+  YMP_LAUNCH_CHECK();
+  return YMP_OK;
+}
+
+// Backward counterpart of attn_tc_fwd_try: YMP_ENOSUP when outside the kernel's domain.
+int attn_tc_bwd_try(const ymp_attn_bwd_args* b, cudaStream_t st) {
+  const ymp_attn_args* a = &b->fwd;
+  if (!(a->head_dim == 64 || a->head_dim == 96) || a->s_kv > 256 || a->s_q > 256) return YMP_ENOSUP;
+  if (a->mask == YMP_MASK_BLOCK) return YMP_ENOSUP;
+  if (a->mask == YMP_MASK_CAUSAL && a->s_q != a->s_kv) return YMP_ENOSUP;
+  if (a->q_head_stride % 8 || a->ldo % 8 || a->o_head_stride % 8 || b->do_head_stride % 8 || b->dq_head_stride % 8 ||
+      b->dk_head_stride % 8 || b->dv_head_stride % 8)
+    return YMP_ENOSUP;
+  AttnTcBwdParams p = {};
+  p.q = (const __nv_bfloat16*)a->q; p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v;
+  p.o = (const __nv_bfloat16*)a->o; p.dout = (const __nv_bfloat16*)b->dout; p.lse = a->lse;
+  p.dq = (__nv_bfloat16*)b->dq; p.dk = (__nv_bfloat16*)b->dk; p.dv = (__nv_bfloat16*)b->dv;
+  p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.ldo = a->ldo;
+  p.lddo = b->lddo; p.lddq = b->lddq; p.lddk = b->lddk; p.lddv = b->lddv;
+  p.hsq = a->q_head_stride; p.hsk = a->k_head_stride; p.hsv = a->v_head_stride; p.hso = a->o_head_stride;
+  p.hsdo = b->do_head_stride; p.hsdq = b->dq_head_stride; p.hsdk = b->dk_head_stride; p.hsdv = b->dv_head_stride;
+  p.mq = tc_map(a->map_q); p.mkv = tc_map(a->map_kv); p.mo = tc_map(a->map_o);
+  p.mdo = tc_map(b->map_do); p.mdq = tc_map(b->map_dq); p.mdkv = tc_map(b->map_dkv);
+  p.n_seq = a->n_seq; p.n_heads = a->n_heads; p.s_q = a->s_q; p.s_kv = a->s_kv;
+  p.mask = a->mask; p.total_rows = a->total_rows;
+  p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
+  return a->head_dim == 64 ? launch_tc_bwd<64>(p, st) : launch_tc_bwd<96>(p, st);
 }
 
 }  // namespace ymp
