@@ -318,7 +318,9 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
 //              written back over consumed S^T / dP^T columns, dS^T additionally into smem)
 //       dV_j += P^T dO_i,  dK_j += dS^T Q_i                 (A from TMEM, B = the same dO_i / Q_i tiles MN-major)
 //       dQ_i(j) = dS K_j                                    (A = dS^T tile read MN-major, B = K_j MN-major)
-//       dQ_i: first key block's partial is parked in smem (bf16), the last adds it and stores
+//       dQ_i: the first key block's partial is parked (bf16, unscaled) in the dq rows themselves; the thread
+//             that wrote it reads it back, adds the last key block's partial and stores the result
+//     Q_i / dO_i tiles are double-buffered: the next step's tiles are fetched behind the current MMAs
 //     store dK_j (x scale), dV_j
 // delta = rowsum(dO o O) is computed in the prologue; no global workspace, no atomics, deterministic.
 // TMEM (512 columns): S^T [0,128)  dP^T [128,256)  dV [256,256+HD)  dK [256+HD,256+2HD)  dQ [448,512)+[32,64)
@@ -376,31 +378,85 @@ __device__ __forceinline__ void tc_load256(uint8_t* blk0, uint8_t* blk1, const T
   }
 }
 
+// Row-staging buffers ([128 rows][HD*2 + 16 B], the pad spreads the banks) make every global access of
+// the dQ / dK / dV outputs coalesced: 4 consecutive lanes move 64 contiguous bytes of one row.
+template <int HD>
+__device__ __forceinline__ void tc_rows_store256(const uint8_t* stage, const TcMat& m, int r0, int n_valid) {
+  constexpr int PITCH = HD * 2 + 16, CPT = HD / 32;
+  const int rl = threadIdx.x >> 2, c0 = threadIdx.x & 3;
+#pragma unroll
+  for (int rb = 0; rb < 128; rb += 64) {
+    const int r = rb + rl;
+    if (r0 + r < n_valid) {
+      __nv_bfloat16* g = const_cast<__nv_bfloat16*>(tc_row(m, r0 + r));
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = c0 + 4 * j;
+        *reinterpret_cast<uint4*>(g + c * 8) = *reinterpret_cast<const uint4*>(stage + r * PITCH + c * 16);
+      }
+    }
+  }
+}
+template <int HD>
+__device__ __forceinline__ void tc_rows_load256(uint8_t* stage, const TcMat& m, int r0, int n_valid) {
+  constexpr int PITCH = HD * 2 + 16, CPT = HD / 32;
+  const int rl = threadIdx.x >> 2, c0 = threadIdx.x & 3;
+#pragma unroll
+  for (int rb = 0; rb < 128; rb += 64) {
+    const int r = rb + rl;
+    if (r0 + r < n_valid) {
+      const __nv_bfloat16* g = tc_row(m, r0 + r);
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = c0 + 4 * j;
+        cp16(stage + r * PITCH + c * 16, g + c * 8);
+      }
+    }
+  }
+}
+
+#ifdef YMP_ATTN_DBG
+__device__ unsigned long long ymp_attn_dbg_buf[256];
+#define TDBG(k)                                                                                        \
+  do {                                                                                                 \
+    if (blockIdx.x == 3 && blockIdx.y == 200 && threadIdx.x == 0 && dbg_n < 256)                        \
+      ymp_attn_dbg_buf[dbg_n++] = ((unsigned long long)(k) << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull); \
+  } while (0)
+#else
+#define TDBG(k)
+#endif
+
 template <int HD>
 __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdParams p) {
   static_assert(HD == 64 || HD == 96, "head_dim 64 or 96");
   constexpr bool TWO = (HD == 96);
-  constexpr int PARK_LD = HD * 2 + 16;  // bytes per parked dQ row (padding spreads the banks)
   constexpr uint32_t C_ST = 0, C_DPT = 128, C_DV = 256, C_DK = 256 + HD, C_DQ0 = 448, C_DQ1 = 32;
+  constexpr int T0 = 16384, T1 = TWO ? 8192 : 0;  // bytes of a 128-row SWIZZLE_128B / SWIZZLE_64B tile
+  constexpr int PITCH = HD * 2 + 16;              // row pitch of the staging buffers
+  static_assert(128 * PITCH <= 2 * T0, "dS area doubles as a staging buffer");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint8_t* k0s = smem;                    // [128][128 B] SWIZZLE_128B, head-dim columns 0..63
-  uint8_t* v0s = k0s + 16384;
-  uint8_t* q0s = v0s + 16384;
-  uint8_t* d0s = q0s + 16384;             // dO
-  uint8_t* dss = d0s + 16384;             // dS^T: 2 blocks (queries 0..63 / 64..127) of [128 keys][128 B]
-  uint8_t* k1s = dss + 32768;             // [128][64 B] SWIZZLE_64B, head-dim columns 64..95 (HD = 96)
-  uint8_t* v1s = k1s + (TWO ? 8192 : 0);
-  uint8_t* q1s = v1s + (TWO ? 8192 : 0);
-  uint8_t* d1s = q1s + (TWO ? 8192 : 0);
-  uint8_t* park = d1s + (TWO ? 8192 : 0);                                  // [2][128][PARK_LD]
-  float2* stats = reinterpret_cast<float2*>(park + 2 * 128 * PARK_LD);    // [256] (lse * log2e, delta)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(stats + 256);               // [2]
+  uint8_t* v0s = k0s + T0;
+  uint8_t* q0s = v0s + T0;                // Q, two stages
+  uint8_t* d0s = q0s + 2 * T0;            // dO, two stages
+  uint8_t* dss = d0s + 2 * T0;            // dS^T: 2 blocks (queries 0..63 / 64..127) of [128 keys][128 B]
+  uint8_t* k1s = dss + 2 * T0;            // [128][64 B] SWIZZLE_64B, head-dim columns 64..95 (HD = 96)
+  uint8_t* v1s = k1s + T1;
+  uint8_t* q1s = v1s + T1;
+  uint8_t* d1s = q1s + 2 * T1;
+  uint8_t* pst = d1s + 2 * T1;            // [128][PITCH] row staging: parked dQ read-back, dK store
+  float2* stats = reinterpret_cast<float2*>(pst + 128 * PITCH);  // [256] (lse * log2e, delta)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stats + 256);  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wq = warp & 3, half = warp >> 2;  // TMEM lane quarter, column half
+#ifdef YMP_ATTN_DBG
+  int dbg_n = 0;
+#endif
+  TDBG(0);
   const int h = blockIdx.x, s = blockIdx.y;
   int sq = p.s_q, skv = p.s_kv;
   if (p.total_rows > 0) {
@@ -414,15 +470,23 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
 
   if (warp == 0) tmem_alloc<512>(tmem_ptr);
   if (threadIdx.x == 32) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    mbar_init(&bar[0], 2);  // S^T and dP^T issuers
+    mbar_init(&bar[1], 3);  // dV, dK and dQ issuers
     fence_mbar_init();
   }
   const TcMat Mq = tc_mat(p.q, p.mq, s, p.ldq, h * p.hsq);
   const TcMat Mk = tc_mat(p.k, p.mkv, s, p.ldk, h * p.hsk);
   const TcMat Mv = tc_mat(p.v, p.mkv, s, p.ldv, h * p.hsv);
   const TcMat Mdo = tc_mat(p.dout, p.mdo, s, p.lddo, h * p.hsdo);
-  // ---- prologue: per-query statistics
+  const TcMat Mdq = tc_mat(p.dq, p.mdq, s, p.lddq, h * p.hsdq);
+  // the first tiles are in flight while the per-query statistics are computed
+  tc_load256<HD>(k0s, k1s, Mk, 0, 128, skv);
+  tc_load256<HD>(v0s, v1s, Mv, 0, 128, skv);
+  {
+    const int nq0 = min(128, (sq + 31) & ~31);
+    tc_load256<HD>(q0s, q1s, Mq, 0, nq0, sq);
+    tc_load256<HD>(d0s, d1s, Mdo, 0, nq0, sq);
+  }
   {
     const int r = threadIdx.x;
     float2 st = make_float2(1e30f, 0.f);  // rows that do not exist: P = exp2(x - 1e30) = 0
@@ -448,55 +512,71 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
   const uint32_t tmem = *tmem_ptr;
   const uint32_t tl = tmem + ((uint32_t)(wq * 32) << 16);
   const int kr = wq * 32 + lane;  // this thread's TMEM lane: key row (softmax, dK/dV) or query row (dQ)
+  TDBG(1);
 
   int it = 0;
   for (int j = 0; j < nkb; ++j) {
     const int kj0 = j * 128;
     const int nk = min(128, (skv - kj0 + 31) & ~31);  // key extent of this block used as an MMA K dimension
-    tc_load256<HD>(k0s, k1s, Mk, kj0, 128, skv);
-    tc_load256<HD>(v0s, v1s, Mv, kj0, 128, skv);
+    if (j > 0) {  // every MMA that read the previous key block has completed (bar[1] of its last step)
+      tc_load256<HD>(k0s, k1s, Mk, kj0, 128, skv);
+      tc_load256<HD>(v0s, v1s, Mv, kj0, 128, skv);
+    }
     const int i0 = causal ? j : 0;
     for (int i = i0; i < nqb; ++i, ++it) {
-      const int qi0 = i * 128;
+      const int qi0 = i * 128, sb = it & 1;
       const int nq = min(128, (sq - qi0 + 31) & ~31);  // query extent (MMA N of S^T / K of dV, dK)
-      tc_load256<HD>(q0s, q1s, Mq, qi0, nq, sq);
-      tc_load256<HD>(d0s, d1s, Mdo, qi0, nq, sq);
+      uint8_t *qa = q0s + sb * T0, *qb = q1s + sb * T1, *da = d0s + sb * T0, *db = d1s + sb * T1;
+      TDBG(10);
       asm volatile("cp.async.wait_all;" ::: "memory");
+      TDBG(11);
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
-      // ---- S^T = K_j Q_i^T, dP^T = V_j dO_i^T
-      if (threadIdx.x == 0) {
+      TDBG(12);
+      // ---- S^T = K_j Q_i^T (thread 0), dP^T = V_j dO_i^T (thread 32): independent accumulators, so two
+      // threads of different warps issue them concurrently (one thread sustains ~1 MMA / 60 clk)
+      if (threadIdx.x == 0 || threadIdx.x == 32) {
+        const bool second = threadIdx.x == 32;
         const uint32_t idesc = make_idesc_bf16(128, nq, 0, 0);
+        const uint32_t a0 = smem_u32(second ? v0s : k0s), a1 = smem_u32(second ? v1s : k1s);
+        const uint32_t b0 = smem_u32(second ? da : qa), b1 = smem_u32(second ? db : qb);
+        const uint32_t dcol = tmem + (second ? C_DPT : C_ST);
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks) {
           uint64_t ad, bd;
           if (ks < 4) {
-            ad = desc_sw(smem_u32(k0s) + ks * 32, 1024, LAYOUT_SW128);
-            bd = desc_sw(smem_u32(q0s) + ks * 32, 1024, LAYOUT_SW128);
+            ad = desc_sw(a0 + ks * 32, 1024, LAYOUT_SW128);
+            bd = desc_sw(b0 + ks * 32, 1024, LAYOUT_SW128);
           } else {
-            ad = desc_sw(smem_u32(k1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
-            bd = desc_sw(smem_u32(q1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
+            ad = desc_sw(a1 + (ks - 4) * 32, 512, LAYOUT_SW64);
+            bd = desc_sw(b1 + (ks - 4) * 32, 512, LAYOUT_SW64);
           }
-          umma_bf16(tmem + C_ST, ad, bd, idesc, ks > 0 ? 1u : 0u);
-        }
-#pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks) {
-          uint64_t ad, bd;
-          if (ks < 4) {
-            ad = desc_sw(smem_u32(v0s) + ks * 32, 1024, LAYOUT_SW128);
-            bd = desc_sw(smem_u32(d0s) + ks * 32, 1024, LAYOUT_SW128);
-          } else {
-            ad = desc_sw(smem_u32(v1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
-            bd = desc_sw(smem_u32(d1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
-          }
-          umma_bf16(tmem + C_DPT, ad, bd, idesc, ks > 0 ? 1u : 0u);
+          umma_bf16(dcol, ad, bd, idesc, ks > 0 ? 1u : 0u);
         }
         umma_commit(&bar[0]);
       }
+      TDBG(13);
+      // ---- prefetch the next step's Q / dO into the other stage (its last readers finished a step ago)
+      {
+        int ni = i + 1, nj = j;
+        if (ni >= nqb) { nj = j + 1; ni = causal ? nj : 0; }
+        if (nj < nkb && ni < nqb) {
+          const int nqn = min(128, (sq - ni * 128 + 31) & ~31);
+          tc_load256<HD>(q0s + (sb ^ 1) * T0, q1s + (sb ^ 1) * T1, Mq, ni * 128, nqn, sq);
+          tc_load256<HD>(d0s + (sb ^ 1) * T0, d1s + (sb ^ 1) * T1, Mdo, ni * 128, nqn, sq);
+        }
+      }
+      // ---- dQ bookkeeping: the first key block's partial is parked (bf16, unscaled) in the dq output rows
+      // themselves; the step that processes the last contributing key block reads it back (coalesced) into pst
+      const int jl = causal ? min(i, nkb - 1) : nkb - 1;
+      const bool last_kb = (j == jl);
+      if (j > 0 && last_kb) tc_rows_load256<HD>(pst, Mdq, qi0, sq);
+      TDBG(14);
       mbar_wait(&bar[0], it & 1);
       tc_fence_after();
+      TDBG(15);
 
       // ---- P^T and dS^T: warp (wq, half) owns key rows wq*32.. and query columns half*64..half*64+63
       const bool diag = causal && (i == j);
@@ -527,106 +607,107 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
         const uint32_t pc = half * 64 + cc * 16;  // packed pairs land inside this warp's consumed columns
         tmem_st16(tl + C_ST + pc, ppk);
         tmem_st16(tl + C_DPT + pc, dpk);
-        uint8_t* dsb = dss + half * 16384;
+        uint8_t* dsb = dss + half * T0;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           *reinterpret_cast<uint4*>(dsb + sw128_off(kr, cc * 4 + g)) = make_uint4(dpk[4 * g], dpk[4 * g + 1], dpk[4 * g + 2], dpk[4 * g + 3]);
       }
+      TDBG(16);
       tmem_st_wait();
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
+      TDBG(17);
 
-      // ---- dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i(j) = dS K_j
-      if (threadIdx.x == 0) {
+      // ---- dV_j += P^T dO_i (thread 0), dK_j += dS^T Q_i (thread 32), dQ_i(j) = dS K_j (thread 64)
+      if (threadIdx.x == 0 || threadIdx.x == 32) {
+        const bool second = threadIdx.x == 32;
         const uint32_t id64 = make_idesc_bf16(128, 64, 0, 1), id32 = make_idesc_bf16(128, 32, 0, 1);
+        const uint32_t b0 = smem_u32(second ? qa : da), b1 = smem_u32(second ? qb : db);
+        const uint32_t dcol = tmem + (second ? C_DK : C_DV), acolb = tmem + (second ? C_DPT : C_ST);
         const int nks = nq / 16;
         for (int ks = 0; ks < nks; ++ks) {
           const uint32_t acc = (i > i0 || ks > 0) ? 1u : 0u;
           const uint32_t acol = (ks < 4) ? ks * 8 : 64 + (ks - 4) * 8;  // packed pairs: queries 0..63 at +0, 64..127 at +64
-          umma_ts(tmem + C_DV, tmem + C_ST + acol, desc_sw(smem_u32(d0s) + ks * 2048, 1024, LAYOUT_SW128), id64, acc);
-          if (TWO) umma_ts(tmem + C_DV + 64, tmem + C_ST + acol, desc_sw(smem_u32(d1s) + ks * 1024, 512, LAYOUT_SW64), id32, acc);
-          umma_ts(tmem + C_DK, tmem + C_DPT + acol, desc_sw(smem_u32(q0s) + ks * 2048, 1024, LAYOUT_SW128), id64, acc);
-          if (TWO) umma_ts(tmem + C_DK + 64, tmem + C_DPT + acol, desc_sw(smem_u32(q1s) + ks * 1024, 512, LAYOUT_SW64), id32, acc);
+          umma_ts(dcol, acolb + acol, desc_sw(b0 + ks * 2048, 1024, LAYOUT_SW128), id64, acc);
+          if (TWO) umma_ts(dcol + 64, acolb + acol, desc_sw(b1 + ks * 1024, 512, LAYOUT_SW64), id32, acc);
         }
+        umma_commit(&bar[1]);
+      } else if (threadIdx.x == 64) {
         const uint32_t iq64 = make_idesc_bf16(128, 64, 1, 1), iq32 = make_idesc_bf16(128, 32, 1, 1);
         const int nkk = nk / 16;
         for (int ks = 0; ks < nkk; ++ks) {
-          const uint64_t ad = desc_sw_lbo(smem_u32(dss) + ks * 2048, 16384, 1024, LAYOUT_SW128);
+          const uint64_t ad = desc_sw_lbo(smem_u32(dss) + ks * 2048, T0, 1024, LAYOUT_SW128);
           umma_bf16(tmem + C_DQ0, ad, desc_sw(smem_u32(k0s) + ks * 2048, 1024, LAYOUT_SW128), iq64, ks > 0 ? 1u : 0u);
           if (TWO) umma_bf16(tmem + C_DQ1, ad, desc_sw(smem_u32(k1s) + ks * 1024, 512, LAYOUT_SW64), iq32, ks > 0 ? 1u : 0u);
         }
         umma_commit(&bar[1]);
       }
+      TDBG(18);
       mbar_wait(&bar[1], it & 1);
       tc_fence_after();
+      TDBG(19);
 
-      // ---- dQ_i: TMEM lane = query row; chunk c of HD/32 handled by warpgroup c & 1
+      // ---- dQ_i: TMEM lane = query row; chunk c of HD/32 handled by warpgroup c & 1.  The rows are staged in
+      // the (now idle) dS area and stored with coalesced 16-byte accesses.
+      if (j > 0 && last_kb) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();  // parked rows were fetched by other threads
+      }
       {
-        const int jl = causal ? min(i, nkb - 1) : nkb - 1;  // last key block contributing to this query block
-        const int row = qi0 + kr;
-        uint8_t* prow = park + ((size_t)(i * 128 + kr)) * PARK_LD;
-        __nv_bfloat16* grow = nullptr;
-        if (j == jl && row < sq) {
-          const TcMat Mdq = tc_mat(p.dq, p.mdq, s, p.lddq, h * p.hsdq);
-          grow = const_cast<__nv_bfloat16*>(tc_row(Mdq, row));
-        }
+        const float sc = last_kb ? p.scale : 1.f;  // parked partials stay unscaled
 #pragma unroll
         for (int c = 0; c < HD / 32; ++c) {
           if ((c & 1) != half) continue;
           uint32_t r[32];
           tmem_ld32(tl + (c < 2 ? C_DQ0 + c * 32 : C_DQ1), r);
           tmem_ld_wait();
-          if (j < jl) {  // park this key block's partial
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              *reinterpret_cast<uint4*>(prow + c * 64 + g * 16) =
-                  make_uint4(pack_bf16(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1])), pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3])),
-                             pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5])), pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
-          } else if (grow) {
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[8 * g + e]);
-              if (j > 0) {
-                const uint4 pk = *reinterpret_cast<const uint4*>(prow + c * 64 + g * 16);
-                f[0] += bf16_lo(pk.x); f[1] += bf16_hi(pk.x); f[2] += bf16_lo(pk.y); f[3] += bf16_hi(pk.y);
-                f[4] += bf16_lo(pk.z); f[5] += bf16_hi(pk.z); f[6] += bf16_lo(pk.w); f[7] += bf16_hi(pk.w);
-              }
-              *reinterpret_cast<uint4*>(grow + c * 32 + g * 8) =
-                  make_uint4(pack_bf16(f[0] * p.scale, f[1] * p.scale), pack_bf16(f[2] * p.scale, f[3] * p.scale),
-                             pack_bf16(f[4] * p.scale, f[5] * p.scale), pack_bf16(f[6] * p.scale, f[7] * p.scale));
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[8 * g + e]);
+            if (j > 0 && last_kb) {
+              const uint4 q4 = *reinterpret_cast<const uint4*>(pst + kr * PITCH + c * 64 + g * 16);
+              f[0] += bf16_lo(q4.x); f[1] += bf16_hi(q4.x); f[2] += bf16_lo(q4.y); f[3] += bf16_hi(q4.y);
+              f[4] += bf16_lo(q4.z); f[5] += bf16_hi(q4.z); f[6] += bf16_lo(q4.w); f[7] += bf16_hi(q4.w);
             }
+            *reinterpret_cast<uint4*>(dss + kr * PITCH + c * 64 + g * 16) =
+                make_uint4(pack_bf16(f[0] * sc, f[1] * sc), pack_bf16(f[2] * sc, f[3] * sc), pack_bf16(f[4] * sc, f[5] * sc), pack_bf16(f[6] * sc, f[7] * sc));
           }
         }
       }
+      tc_fence_before();
+      __syncthreads();
+      tc_rows_store256<HD>(dss, Mdq, qi0, sq);
     }
-    // ---- dV_j (warpgroup 0) and dK_j x scale (warpgroup 1): TMEM lane = key row
+    TDBG(20);
+    // ---- dV_j (warpgroup 0, staged in the dS area) and dK_j x scale (warpgroup 1, staged in pst)
+    __syncthreads();  // the last dQ store pass has finished reading the dS area
     {
-      const int krow = kj0 + kr;
-      __nv_bfloat16* grow = nullptr;
-      if (krow < skv) {
-        const TcMat Mg = tc_mat(half ? p.dk : p.dv, p.mdkv, s, half ? p.lddk : p.lddv, h * (half ? p.hsdk : p.hsdv));
-        grow = const_cast<__nv_bfloat16*>(tc_row(Mg, krow));
-      }
+      uint8_t* stg = half ? pst : dss;
       const float sc = half ? p.scale : 1.f;
 #pragma unroll
       for (int c = 0; c < HD / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tl + (half ? C_DK : C_DV) + c * 32, r);
         tmem_ld_wait();
-        if (grow) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(grow + c * 32 + g * 8) =
-                make_uint4(pack_bf16(__uint_as_float(r[8 * g]) * sc, __uint_as_float(r[8 * g + 1]) * sc), pack_bf16(__uint_as_float(r[8 * g + 2]) * sc, __uint_as_float(r[8 * g + 3]) * sc),
-                           pack_bf16(__uint_as_float(r[8 * g + 4]) * sc, __uint_as_float(r[8 * g + 5]) * sc), pack_bf16(__uint_as_float(r[8 * g + 6]) * sc, __uint_as_float(r[8 * g + 7]) * sc));
-        }
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(stg + kr * PITCH + c * 64 + g * 16) =
+              make_uint4(pack_bf16(__uint_as_float(r[8 * g]) * sc, __uint_as_float(r[8 * g + 1]) * sc), pack_bf16(__uint_as_float(r[8 * g + 2]) * sc, __uint_as_float(r[8 * g + 3]) * sc),
+                         pack_bf16(__uint_as_float(r[8 * g + 4]) * sc, __uint_as_float(r[8 * g + 5]) * sc), pack_bf16(__uint_as_float(r[8 * g + 6]) * sc, __uint_as_float(r[8 * g + 7]) * sc));
       }
+      tc_fence_before();
+      __syncthreads();
+      const TcMat Mdv = tc_mat(p.dv, p.mdkv, s, p.lddv, h * p.hsdv);
+      const TcMat Mdk = tc_mat(p.dk, p.mdkv, s, p.lddk, h * p.hsdk);
+      tc_rows_store256<HD>(dss, Mdv, kj0, skv);
+      tc_rows_store256<HD>(pst, Mdk, kj0, skv);
     }
   }
+  TDBG(21);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -634,7 +715,6 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
     tmem_dealloc<512>(tmem);
   }
 }
-
 
 static TcSeqMap tc_map(const ymp_seqmap& m) {
   TcSeqMap r;
@@ -679,7 +759,7 @@ int attn_tc_fwd_try(const ymp_attn_args* a, cudaStream_t st) {
 
 template <int HD>
 static int launch_tc_bwd(const AttnTcBwdParams& p, cudaStream_t st) {
-  const int smem = 4 * 16384 + 32768 + (HD == 96 ? 4 * 8192 : 0) + 2 * 128 * (HD * 2 + 16) + 256 * 8 + 64 + 1024;
+  const int smem = 8 * 16384 + (HD == 96 ? 6 * 8192 : 0) + 128 * (HD * 2 + 16) + 256 * 8 + 64 + 1024;
   static bool set = false;
   if (!set) { YMP_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
   dim3 grid(p.n_heads, p.n_seq);
@@ -714,3 +794,9 @@ int attn_tc_bwd_try(const ymp_attn_bwd_args* b, cudaStream_t st) {
 }
 
 }  // namespace ymp
+
+#ifdef YMP_ATTN_DBG
+extern "C" int ymp_attn_dbg_read(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, ymp::ymp_attn_dbg_buf, sizeof(unsigned long long) * 256);
+}
+#endif
