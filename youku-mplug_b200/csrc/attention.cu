@@ -721,6 +721,8 @@ static int launch_bwd(const AttnKParams& p, cudaStream_t st) {
 namespace ymp {
 int attn_tc_fwd_try(const ymp_attn_args* a, cudaStream_t st);
 int attn_tc_bwd_try(const ymp_attn_bwd_args* b, cudaStream_t st);
+int attn_small_fwd_try(const ymp_attn_args* a, cudaStream_t st);
+int attn_small_bwd_try(const ymp_attn_bwd_args* b, cudaStream_t st);
 }
 
 extern "C" int ymp_attn_fwd(const ymp_attn_args* a, void* stream) {
@@ -733,6 +735,8 @@ extern "C" int ymp_attn_fwd(const ymp_attn_args* a, void* stream) {
   // short key ranges run on the tcgen05 kernel (attention_tc.cu); YMP_ATTN_LEGACY=1 forces mma.sync
   static const bool legacy = [] { const char* e = getenv("YMP_ATTN_LEGACY"); return e && e[0] == '1'; }();
   if (!legacy) {
+    rc = attn_small_fwd_try(a, st);  // short dense block-diagonal sequences (attention_small.cu)
+    if (rc != YMP_ENOSUP) return rc;
     rc = attn_tc_fwd_try(a, st);
     if (rc != YMP_ENOSUP) return rc;
   }
@@ -762,6 +766,8 @@ extern "C" int ymp_attn_bwd(const ymp_attn_bwd_args* b, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   static const bool legacy = [] { const char* e = getenv("YMP_ATTN_LEGACY"); return e && e[0] == '1'; }();
   if (!legacy) {
+    rc = attn_small_bwd_try(b, st);
+    if (rc != YMP_ENOSUP) return rc;
     rc = attn_tc_bwd_try(b, st);
     if (rc != YMP_ENOSUP) return rc;
   }
