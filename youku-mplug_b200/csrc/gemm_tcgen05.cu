@@ -83,9 +83,52 @@ __device__ __forceinline__ void store16(__nv_bfloat16* p, bool v32, const float*
   }
 }
 
+// Global operands of one epilogue chunk (32 columns of one row), fetched BEFORE the tcgen05.wait::ld so
+// that their latency overlaps the TMEM read instead of following it (the epilogue warps are only two per
+// scheduler: every exposed round trip is paid in full).
+struct EpiPrefetch {
+  uint32_t bias[16];  // 32 bf16
+  uint32_t aux[16];   // 32 bf16 (aux_in)
+  uint32_t res[32];   // 32 fp32 or 32 bf16 (first 16 words)
+};
+__device__ __forceinline__ void load32_raw(const __nv_bfloat16* p, bool v32, uint32_t* r) {
+  if (v32) {
+    uint32_t a[8], b[8];
+    ld_v8(p, a);
+    ld_v8(p + 16, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r[i] = a[i]; r[8 + i] = b[i]; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(p) + j);
+      r[4 * j] = a.x; r[4 * j + 1] = a.y; r[4 * j + 2] = a.z; r[4 * j + 3] = a.w;
+    }
+  }
+}
+__device__ __forceinline__ void epilogue_prefetch(const GemmKParams& p, int row, int col0, EpiPrefetch& pf) {
+  if (row >= p.M || col0 + 32 > p.N) return;
+  if (p.bias) load32_raw(p.bias + col0, p.v32_bias, pf.bias);
+  if (p.aux_in) load32_raw(p.aux_in + (size_t)row * p.ldd + col0, p.v32_aux, pf.aux);
+  if (p.residual) {
+    const int rrow = p.res_row_mod ? row % p.res_row_mod : row;
+    if (p.res_f32) {
+      const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + (size_t)rrow * p.ldr + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 a = __ldg(rp + j);
+        pf.res[4 * j] = __float_as_uint(a.x); pf.res[4 * j + 1] = __float_as_uint(a.y);
+        pf.res[4 * j + 2] = __float_as_uint(a.z); pf.res[4 * j + 3] = __float_as_uint(a.w);
+      }
+    } else {
+      load32_raw(reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)rrow * p.ldr + col0, p.v32_res, pf.res);
+    }
+  }
+}
+
 // Epilogue for one thread: 32 consecutive columns of one output row.
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint32_t (&r)[32],
-                                               int row, int col0) {
+                                               int row, int col0, const EpiPrefetch& pf) {
   if (row >= p.M || col0 >= p.N) return;
   const bool full = (col0 + 32 <= p.N);
   const int drow = p.d_row_block ? (row / p.d_row_block) * p.d_row_stride + row % p.d_row_block : row;
@@ -102,12 +145,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
   if (full) {
     if (p.bias) {
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        float b[16];
-        load16(p.bias + col0 + 16 * hh, p.v32_bias, b);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[16 * hh + i] += b[i];
-      }
+      for (int i = 0; i < 16; ++i) { v[2 * i] += bf16_lo(pf.bias[i]); v[2 * i + 1] += bf16_hi(pf.bias[i]); }
     }
     const size_t off = (size_t)row * p.ldd + col0;          // aux tensors: plain rows
     const size_t doff = (size_t)drow * p.ldd + col0;        // D: optionally re-blocked rows
@@ -115,12 +153,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
     // without one the value itself.  aux_in: a plain multiplier.  Switches are warp-uniform.
     if (p.aux_in) {
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        float a[16];
-        load16(p.aux_in + off + 16 * hh, p.v32_aux, a);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[16 * hh + i] *= a[i];
-      }
+      for (int i = 0; i < 16; ++i) { v[2 * i] *= bf16_lo(pf.aux[i]); v[2 * i + 1] *= bf16_hi(pf.aux[i]); }
     } else if (p.act == YMP_ACT_GELU_ERF) {
       if (p.aux_out) {
         float d[32];
@@ -149,21 +182,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
     }
     if (p.residual) {
       if (p.res_f32) {  // fp32 residual stream
-        const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + (size_t)rrow * p.ldr + col0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 a = __ldg(rp + j);
-          v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
-        }
+        for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(pf.res[i]);
       } else {
-        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)rrow * p.ldr + col0;
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          float a[16];
-          load16(rp + 16 * hh, p.v32_res, a);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[16 * hh + i] += a[i];
-        }
+        for (int i = 0; i < 16; ++i) { v[2 * i] += bf16_lo(pf.res[i]); v[2 * i + 1] += bf16_hi(pf.res[i]); }
       }
     }
     if (!p.out_f32) {
@@ -368,6 +391,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         const int coff = half * (BN / 2) + c * 32;
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + coff), r);
+        EpiPrefetch pf;
+        epilogue_prefetch(p, row, n_blk * BN + coff, pf);
         tmem_ld_wait();
         if (c == CHUNKS - 1) {
           // all TMEM reads of this warp are done: hand the accumulator stage back early
@@ -375,7 +400,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
-        epilogue_chunk(p, r, row, n_blk * BN + coff);
+        epilogue_chunk(p, r, row, n_blk * BN + coff, pf);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -400,6 +425,15 @@ constexpr int NSTAGE2 = 6;
 constexpr int B2_STAGE_BYTES = (BN2 / 2) * BK * 2;
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;
 constexpr int SMEM2_BYTES = NSTAGE2 * STAGE2_BYTES + 256 + 1024;
+
+#ifdef YMP_GEMM_DBG
+// [0] MMA warp: total cycles, [1] waiting for a free accumulator, [2] waiting for smem stages, [3] tiles
+// [4] producer: cycles waiting for empty slots   [5] epilogue warp 4: waiting for tfull, [6] epilogue total
+__device__ unsigned long long ymp_gemm_dbg_buf[16];
+#define GDBG_T() clock64()
+#else
+#define GDBG_T() 0ll
+#endif
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
@@ -460,7 +494,13 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
+#ifdef YMP_GEMM_DBG
+          const long long tw0 = GDBG_T();
+#endif
           mbar_wait(&empty_bar[stage], phase ^ 1);
+#ifdef YMP_GEMM_DBG
+          if (blockIdx.x == 0) ymp_gemm_dbg_buf[4] += GDBG_T() - tw0;
+#endif
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);  // bytes of both CTAs land here
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * B2_STAGE_BYTES;
@@ -496,12 +536,24 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
         const int ks = u % p.split_k;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+#ifdef YMP_GEMM_DBG
+        const long long ta0 = GDBG_T();
+#endif
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
+#ifdef YMP_GEMM_DBG
+        if (blockIdx.x == 0) { ymp_gemm_dbg_buf[1] += GDBG_T() - ta0; ymp_gemm_dbg_buf[3] += 1; if (ymp_gemm_dbg_buf[7] == 0) ymp_gemm_dbg_buf[7] = ta0; ymp_gemm_dbg_buf[0] = GDBG_T() - ymp_gemm_dbg_buf[7]; }
+#endif
         const uint32_t tmem_d = tmem_base + as * BN2;
         for (int kb = kb0; kb < kb1; ++kb) {
+#ifdef YMP_GEMM_DBG
+          const long long tf0 = GDBG_T();
+#endif
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+#ifdef YMP_GEMM_DBG
+          if (blockIdx.x == 0) ymp_gemm_dbg_buf[2] += GDBG_T() - tf0;
+#endif
           const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
           const uint32_t sb = smem_u32(smem_b + stage * B2_STAGE_BYTES);
 #pragma unroll
@@ -528,22 +580,34 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
       const int t = u / p.split_k;
       const int m0 = (p.n_fast ? t / num_n : t % num_m) * 2 * BM + (int)rank * BM;
       const int n_blk = p.n_fast ? t % num_n : t / num_m;
+#ifdef YMP_GEMM_DBG
+      const long long te0 = GDBG_T();
+#endif
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
+#ifdef YMP_GEMM_DBG
+      const long long te1 = GDBG_T();
+      if (blockIdx.x == 0 && warp_idx == 4 && lane == 0) ymp_gemm_dbg_buf[5] += te1 - te0;
+#endif
       const int row = m0 + q * 32 + lane;
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         const int coff = half * (BN2 / 2) + c * 32;
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN2 + coff), r);
+        EpiPrefetch pf;
+        epilogue_prefetch(p, row, n_blk * BN2 + coff, pf);
         tmem_ld_wait();
         if (c == CHUNKS - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // always on the leader's barrier
         }
-        epilogue_chunk(p, r, row, n_blk * BN2 + coff);
+        epilogue_chunk(p, r, row, n_blk * BN2 + coff, pf);
       }
+#ifdef YMP_GEMM_DBG
+      if (blockIdx.x == 0 && warp_idx == 4 && lane == 0) ymp_gemm_dbg_buf[6] += GDBG_T() - te1;
+#endif
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
@@ -688,8 +752,16 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
     if (a->accumulate) {
       const long tiles = bn == 512 ? (long)((a->M + 2 * BM - 1) / (2 * BM)) * ((a->N + 255) / 256)
                                    : (long)((a->M + BM - 1) / BM) * ((a->N + bn - 1) / bn);
-      const long want = bn == 512 ? sms : 2L * sms;
-      while (tiles * split < want && split * 8 <= kb_total) split *= 2;
+      // cost model (k-blocks of MMA time): waves x (k-blocks per unit + a fixed pipeline-fill / atomic-epilogue
+      // overhead of ~24 k-blocks).  Measured on the ViT wgrads: 768x768x50208 is fastest at 8 splits
+      // (72 units = one wave of the 74 CTA pairs, 53 us vs 82 us at 32 splits), 3072x768 at 2.
+      const long workers = bn == 512 ? sms / 2 : sms;
+      long best = -1;
+      for (int sp = 1; sp <= 64 && sp * 8 <= kb_total; ++sp) {
+        const long waves = (tiles * sp + workers - 1) / workers;
+        const long cost = waves * ((kb_total + sp - 1) / sp + 24);
+        if (best < 0 || cost < best) { best = cost; split = sp; }
+      }
     }
   }
   YMP_CHECK_ARG(split == 1 || (a->accumulate && a->out_dtype == YMP_DT_F32), "ymp_gemm: split_k>1 needs accumulate=1 and fp32 output");
@@ -724,3 +796,14 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
   if (bn == 256) return launch_gemm<256>(a, kp, st);
   return launch_gemm<128>(a, kp, st);
 }
+
+#ifdef YMP_GEMM_DBG
+extern "C" int ymp_gemm_dbg_read(unsigned long long* out, int reset) {
+  int rc = (int)cudaMemcpyFromSymbol(out, ymp::ymp_gemm_dbg_buf, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(ymp::ymp_gemm_dbg_buf, z, sizeof(z));
+  }
+  return rc;
+}
+#endif

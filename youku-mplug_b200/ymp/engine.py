@@ -434,15 +434,17 @@ def gpt_layer_bwd(W, G, pre, c, dout, g, B, S):
                              dgamma=G.get(pre + "input_layernorm.weight"), dbeta=G.get(pre + "input_layernorm.bias"))
 
 
-def gpt_fwd(W, x, gcfg, B, S, train_w=False, save=True):
+def gpt_fwd(W, x, gcfg, B, S, train_w=False, save=True, out_rows=None):
     """x [B*S, H] fp32: input embeddings with the learned position embeddings already added
-    (GPT3Embedding.forward, :640-666).  Returns final-LN hidden states [B*S, H]."""
+    (GPT3Embedding.forward, :640-666).  Returns final-LN hidden states [B*S, H], or only the rows
+    listed in out_rows (int32 row indices, compact [len(out_rows), H]) when the caller needs no others."""
     g = GptDims(gcfg)
-    c = Ctx(g=g, B=B, S=S, layers=[])
+    c = Ctx(g=g, B=B, S=S, layers=[], out_rows=out_rows)
     for i in range(g.layers):
         x, lc = gpt_layer_fwd(W, f"{GPT}encoder.layers.{i}.", x, g, B, S, train_w)
         c.layers.append(lc if save else None)
-    hid, c.mf, c.rf = ops.layernorm_fwd(x, W[GPT + "encoder.final_layernorm.weight"], W[GPT + "encoder.final_layernorm.bias"], g.eps)
+    hid, c.mf, c.rf = ops.layernorm_fwd(x, W[GPT + "encoder.final_layernorm.weight"], W[GPT + "encoder.final_layernorm.bias"], g.eps,
+                                        in_rows=out_rows)
     if save:
         c.xL = x
     return hid, c
@@ -450,8 +452,12 @@ def gpt_fwd(W, x, gcfg, B, S, train_w=False, save=True):
 
 def gpt_bwd(W, G, c, dhid):
     g, B, S = c.g, c.B, c.S
+    dx = None
+    if c.out_rows is not None:  # rows without a consumer get no gradient from the final LayerNorm
+        dx = torch.zeros((c.xL.shape[0], c.xL.shape[1]), device=dhid.device, dtype=torch.bfloat16)
     dx = ops.layernorm_bwd(dhid, c.xL, W[GPT + "encoder.final_layernorm.weight"], c.mf, c.rf,
-                           dgamma=G.get(GPT + "encoder.final_layernorm.weight"), dbeta=G.get(GPT + "encoder.final_layernorm.bias"))
+                           dgamma=G.get(GPT + "encoder.final_layernorm.weight"), dbeta=G.get(GPT + "encoder.final_layernorm.bias"),
+                           in_rows=c.out_rows, dx=dx)
     for i in reversed(range(g.layers)):
         dx = gpt_layer_bwd(W, G, f"{GPT}encoder.layers.{i}.", c.layers[i], dx, g, B, S)
         c.layers[i] = None

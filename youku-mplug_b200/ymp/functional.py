@@ -75,6 +75,18 @@ class _GradStore:
                      for k, p in zip(keys, params))
 
 
+_TEXT_ROWS = {}
+
+
+def _text_rows(B, S, Q, dev):
+    """int32 row indices b*S + s for s >= Q (cached: the tensor must outlive CUDA-graph replays)."""
+    key = (B, S, Q, str(dev))
+    if key not in _TEXT_ROWS:
+        r = torch.arange(B, device=dev, dtype=torch.int32)[:, None] * S + torch.arange(Q, S, device=dev, dtype=torch.int32)[None, :]
+        _TEXT_ROWS[key] = r.reshape(-1).contiguous()
+    return _TEXT_ROWS[key]
+
+
 def masked_mean_loss(losses_bs, loss_mask):
     """models/modeling_distributed_gpt3.py:1612-1617."""
     lm = loss_mask.reshape(-1).float()
@@ -104,13 +116,19 @@ class PretrainFn(torch.autograd.Function):
                  d_row_block=Q, d_row_stride=S)
         ops.embed_gather(input_ids.contiguous(), W[engine.GPT + "embedding.word_embeddings.weight"], pos, x_in, S, Q)
         train_gpt = any(n for k, n in zip(keys, ctx.needs_input_grad[7:]) if k.startswith(engine.GPT + "encoder.layers"))
-        hid, cg = engine.gpt_fwd(W, x_in, gcfg, B, S, train_w=train_gpt, save=need_bwd)
-        logits, losses, lse = engine.lm_head_fwd(W, hid, targets)
-        losses_bs = losses.view(B, S)
+        # The visual-prefix positions never reach the loss (loss_mask = cat(0*Q, ...), distributed_gpt3.py:
+        # 142-159), so the final LayerNorm, the LM head and the CE run on the B*L text rows only; their
+        # per-token losses are reported as 0.
+        text_rows = _text_rows(B, S, Q, video.device)
+        targets_t = targets[:, Q:].contiguous()
+        hid, cg = engine.gpt_fwd(W, x_in, gcfg, B, S, train_w=train_gpt, save=need_bwd, out_rows=text_rows)
+        logits, losses, lse = engine.lm_head_fwd(W, hid, targets_t)
+        losses_bs = torch.zeros((B, S), device=video.device, dtype=torch.float32)
+        losses_bs[:, Q:] = losses.view(B, L)
         loss = masked_mean_loss(losses_bs, loss_mask)
         if need_bwd:
             ctx.W, ctx.keys, ctx.cv, ctx.ca, ctx.cg = W, keys, cv, ca, cg
-            ctx.q, ctx.hid, ctx.logits, ctx.lse, ctx.targets, ctx.loss_mask = q, hid, logits, lse, targets, loss_mask
+            ctx.q, ctx.hid, ctx.logits, ctx.lse, ctx.targets, ctx.loss_mask = q, hid, logits, lse, targets_t, loss_mask
             ctx.dims = (B, S, Q, H)
             ctx.params = params
         ctx.mark_non_differentiable(losses_bs)
@@ -129,7 +147,7 @@ class PretrainFn(torch.autograd.Function):
         lm = ctx.loss_mask.float()
         grow = torch.zeros((B, S), device=dev, dtype=torch.float32)
         grow[:, :-1] = lm * (dloss.float() / lm.sum())
-        dhid = engine.lm_head_bwd(W, G, ctx.hid, ctx.logits, ctx.targets, ctx.lse, grow.view(-1))
+        dhid = engine.lm_head_bwd(W, G, ctx.hid, ctx.logits, ctx.targets, ctx.lse, grow[:, Q:].reshape(-1))
         ctx.logits = None
         dx_in = engine.gpt_bwd(W, G, ctx.cg, dhid)
         dqf = dx_in.view(B, S, H)[:, :Q].reshape(B * Q, H)
