@@ -126,7 +126,7 @@ struct LnBwdParams {
 };
 
 template <int VPL, bool WGRAD, bool XF32>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnBwdParams p) {
+__global__ void __launch_bounds__(LN_WARPS * 32, WGRAD ? (VPL <= 4 ? 3 : 1) : 4) ln_bwd_kernel(const LnBwdParams p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nvec = p.D >> 3;
@@ -264,7 +264,9 @@ extern "C" int ymp_layernorm_bwd(const ymp_layernorm_bwd_args* a, void* stream) 
   const bool wg = a->dgamma != nullptr;
   // with weight grads each block ends with 2*D atomics; 6 blocks per SM keeps enough warps in
   // flight for HBM while bounding the atomic tail (~900 adds per address)
-  const int cap = wg ? num_sms() * 4 : num_sms() * 8;
+  // resident blocks per SM: 3 with weight grads (80 registers at D <= 1024), 4 without; the grid is a whole
+  // number of such waves so that the row loop stays balanced
+  const int cap = wg ? num_sms() * (a->D <= 1024 ? 3 : 2) : num_sms() * 8;
   const int blocks = min((a->rows + LN_WARPS - 1) / LN_WARPS, cap);
   const int thr = LN_WARPS * 32;
   const bool xf = (a->x_dtype == YMP_DT_F32);
