@@ -139,11 +139,80 @@ def run(name, vcfg, gcfg, Q, B, L, wseed, iseed, randomize, sample_logits=None, 
     print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
 
 
+def run_generate(name, vcfg, gcfg, Q, B, L, wseed, iseed, beam_size=3, n_new=6, pos_gain=30.0, ln_gain=16.0, stop_after=3):
+    """Golden vectors for the generation path: the UNMODIFIED reference's per-sample beam
+    search and batched greedy sampling over its KV cache, with the visual prefix, next to the oracle's
+    full-recompute restatement.  A random tiny decoder with tied embeddings just repeats its last input
+    token, so the position embeddings (x pos_gain) and the final LayerNorm affine (x ln_gain) are scaled up:
+    the continuations then vary from step to step.  The stop token is chosen as the token greedy decoding
+    of sample 0 emits at step `stop_after`, so early termination and finished beams are exercised."""
+    def build(eod):
+        g = dict(gcfg, tokens_to_generate=n_new, top_k=1, top_p=0.0, eod_id=eod)
+        return g, port.generation_state_dict(vcfg, g, Q, wseed, pos_gain, ln_gain)
+
+    video, ids, att = make_inputs(B, vcfg, L, gcfg["vocab_size"], iseed)
+    plen = att.sum(-1) - 1               # DistributedGPT3_Caption.generate: prompt_length = mask.sum(-1) - 1
+    g0, sd = build(eod=gcfg["vocab_size"] - 1)
+    with torch.no_grad():
+        qf_port = port.visual_prefix(video, sd, vcfg)[3]
+        probe = port.sample_generate(ids.clone(), sd, g0, query_features=qf_port, prompt_length=plen.clone(), tokens_to_generate=n_new,
+                                     eod_id=g0["eod_id"], top_k=1, top_p=0.0)
+    eod = int(probe[0, int(plen[0]) + stop_after])
+    ids[ids == eod] = (eod + 1) % gcfg["vocab_size"]   # no accidental stop tokens inside the prompts
+    gcfg, sd = build(eod)
+    ref_vcfg = dict(vcfg, drop_path=0, use_abs_pos_emb=True)
+    model, G = ref_shims.build_reference_pretrain(ref_vcfg, gcfg, Q)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    with torch.no_grad():
+        _, image_embeds = model.visual_encoder(video)
+        image_query = model.attn_pool(model.learnable_queries.repeat(B, 1, 1), image_embeds)
+        qf = model.visual_norm(model.visual_fc(image_query))
+        ref_beam = [model.text_decoder.generate(ids[i:i + 1], query_embeds=qf[i:i + 1], termination_id=eod, do_sample=False,
+                                                prompt_length=plen[i], beam_size=beam_size) for i in range(B)]
+        ref_greedy = model.text_decoder.generate(ids.clone(), query_embeds=qf, termination_id=eod, do_sample=True,
+                                                 prompt_length=plen.clone())
+    del model
+    with torch.no_grad():
+        qf_port = port.visual_prefix(video, sd, vcfg)[3]
+        assert (qf_port - qf).abs().max() <= 2e-4 * qf.abs().max()
+        beams = []
+        for i in range(B):
+            seq, sc = port.beam_search_generate(ids[i:i + 1], sd, gcfg, query_features=qf_port[i:i + 1], prompt_length=plen[i],
+                                                beam_size=beam_size, stop_token=eod, tokens_to_generate=n_new, eod_id=eod)
+            assert torch.equal(seq, ref_beam[i].sequences), (name, i, seq, ref_beam[i].sequences)
+            assert (sc - ref_beam[i].scores.reshape(-1)).abs().max() < 1e-4, (sc, ref_beam[i].scores)
+            beams.append((ref_beam[i].sequences.clone(), ref_beam[i].scores.reshape(-1).clone()))
+        greedy = port.sample_generate(ids.clone(), sd, gcfg, query_features=qf_port, prompt_length=plen.clone(), tokens_to_generate=n_new,
+                                      eod_id=eod, top_k=1, top_p=0.0, termination_id=eod)
+        assert torch.equal(greedy, ref_greedy), (greedy, ref_greedy)
+        # teacher-forced next-token log-probs along the greedy sequences (what a bf16 run is compared with)
+        steps = []
+        for i in range(B):
+            for t in range(int(plen[i]), ref_greedy.shape[1]):
+                lp = torch.log_softmax(port.next_token_logits(qf_port[i:i + 1], ref_greedy[i:i + 1, :t], sd, gcfg)[0], -1)
+                top = torch.topk(lp, 2)
+                steps.append(dict(sample=i, pos=t, logprobs=lp.clone(), margin=float(top[0][0] - top[0][1])))
+    print(f"[{name}] stop token {eod}; port == reference: beam {[b[0].tolist() for b in beams]} scores {[b[1].tolist() for b in beams]}\n"
+          f"[{name}] greedy {ref_greedy.tolist()} min margin {min(s['margin'] for s in steps):.3f}", flush=True)
+    fix = dict(name=name, vcfg=vcfg, gcfg=gcfg, Q=Q, B=B, L=L, wseed=wseed, iseed=iseed, beam_size=beam_size, n_new=n_new,
+               pos_gain=pos_gain, ln_gain=ln_gain, eod=eod, ids=ids, att=att, prompt_length=plen, video_checksum=float(video.double().abs().sum()),
+               query_features=qf.detach(), beam_sequences=[b[0] for b in beams], beam_scores=[b[1] for b in beams], greedy=ref_greedy,
+               steps=steps, torch_version=torch.__version__)
+    path = os.path.join(GOLD, name + ".pt")
+    torch.save(fix, path)
+    print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also the real 1.3B / T=8 / B=1 config (~6 GB RAM, minutes)")
+    ap.add_argument("--only-generate", action="store_true", help="only (re)write the generation fixture")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
+    run_generate("tiny_generate", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=2, L=8, wseed=51, iseed=52)
+    if a.only_generate:
+        sys.exit(0)
     run("tiny_pretrain", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=2, L=8, wseed=11, iseed=12, randomize=True)
     run("tiny_pretrain_refinit", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=1, L=6, wseed=13, iseed=14, randomize=False)
     if a.full:

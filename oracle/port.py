@@ -391,3 +391,175 @@ def retrieval_loss(vfeat, tfeat, idx, temp):
     pos = torch.eq(idx.view(-1, 1), idx.view(1, -1)).float()
     tgt = pos / pos.sum(1, keepdim=True)
     return (-(F.log_softmax(sim_i2t, 1) * tgt).sum(1).mean() - (F.log_softmax(sim_t2i, 1) * tgt).sum(1).mean()) / 2
+
+
+# ------------------------------------------------------------------------------------------
+# Generation: greedy / top-k / top-p sampling and beam search with
+# the visual prefix.  The reference decodes incrementally over a KV cache
+# (models/modeling_distributed_gpt3.py:868-923); the oracle recomputes the whole [prefix | tokens]
+# sequence at every step, which is the same arithmetic for a causal decoder.
+# ------------------------------------------------------------------------------------------
+def next_token_logits(query_features, tokens, sd, gcfg):
+    """Logits [B, V] of the position after `tokens` [B, n] (prefix [B, Q, h] optional)."""
+    emb_w = sd[GPT_PRE + "embedding.word_embeddings.weight"]
+    x = emb_w[tokens]
+    if query_features is not None:
+        x = torch.cat([query_features, x], dim=1)
+    hidden = gpt3_decoder(x, sd, gcfg)
+    return F.linear(hidden[:, -1], emb_w)
+
+
+def filter_top_k(logits, top_k):
+    """modify_logits_for_top_k_filtering (:1369-1373), out of place."""
+    kth = torch.topk(logits, top_k)[0][..., -1, None]
+    return logits.masked_fill(logits < kth, float("-inf"))
+
+
+def filter_top_p(logits, top_p):
+    """modify_logits_for_top_p_filtering (:1376-1395): nucleus with the historical shift-by-one."""
+    sorted_logits, sorted_idx = torch.sort(logits, descending=True)
+    cum = sorted_logits.softmax(dim=-1).cumsum(dim=-1)
+    drop = cum > top_p
+    drop[:, 1:] = drop[:, :-1].clone()
+    drop[..., 0] = False
+    drop = drop.scatter(1, sorted_idx, drop)
+    return logits.masked_fill(drop, float("-inf"))
+
+
+def pick_token(logits, top_k=0, top_p=0.0, temperature=1.0, vocab_size=None, generator=None):
+    """sample() (:1398-1446): argmax for top_k == 1, otherwise temperature -> top-k | top-p -> multinomial."""
+    assert logits.ndim == 2
+    if top_k == 1:
+        assert top_p == 0.0
+        out = torch.argmax(logits, dim=-1)
+    else:
+        lg = logits.clone()
+        if temperature != 1.0:
+            lg = lg / temperature
+        if top_k > 1:
+            assert top_p == 0.0 and top_k <= lg.size(1)
+            lg = filter_top_k(lg, top_k)
+        elif top_p > 0.0:
+            assert top_p <= 1.0
+            lg = filter_top_p(lg, top_p)
+        out = torch.multinomial(lg.softmax(dim=-1), num_samples=1, generator=generator).view(-1)
+    if vocab_size:
+        out = torch.clamp(out, min=0, max=vocab_size - 1)
+    return out
+
+
+def sample_generate(tokens, sd, gcfg, query_features=None, prompt_length=None, tokens_to_generate=100, eod_id=7,
+                    top_k=0, top_p=0.9, temperature=1.0, termination_id=None, early_stop=True, generator=None):
+    """DistributedGPT3.sample (:1620-1741) for the default stop rule (termination id).  tokens [B, n];
+    prompt_length [B] (tokens beyond a sample's prompt are overwritten as soon as generation reaches them)."""
+    B = tokens.size(0)
+    lengths = prompt_length if prompt_length is not None else torch.tensor([tokens.size(1)])
+    tokens = torch.cat([tokens, torch.full((B, tokens_to_generate), eod_id, dtype=torch.long)], dim=-1)
+    max_len = min(tokens.size(1), gcfg["max_position_embeddings"])
+    min_prompt = int(lengths.min())
+    if min_prompt >= max_len:
+        raise ValueError("context length + tokens_to_generate too large")
+    if termination_id is None:
+        termination_id = eod_id
+    done = torch.zeros(B, dtype=torch.bool)
+    ctx = min_prompt
+    for ctx in range(min_prompt, max_len):
+        new = pick_token(next_token_logits(query_features, tokens[:, :ctx], sd, gcfg), top_k, top_p, temperature,
+                         gcfg["vocab_size"], generator)
+        started = lengths <= ctx
+        tokens[started, ctx] = new[started]
+        done |= (new == termination_id) & started
+        if early_stop and bool(done.all()):
+            break
+    # the reference slices with the context length that still counts the prefix positions (:1740), so with a
+    # visual prefix the returned rows keep (most of) their stop-token padding
+    nq = query_features.size(1) if query_features is not None else 0
+    return tokens[:, :ctx + nq + 1]
+
+
+def generation_state_dict(vcfg, gcfg, num_query, seed, pos_gain, ln_gain):
+    """Weights of the generation fixtures: a random tiny decoder with tied embeddings only repeats its last
+    input token, so the learned position embeddings (x pos_gain) and the final LayerNorm affine (x ln_gain)
+    are scaled up - continuations then change from step to step and have usable top-2 margins."""
+    sd = init_state_dict(vcfg, gcfg, num_query, seed=seed, randomize=True)
+    kp = GPT_PRE + "embedding.position_embeddings.weight"
+    sd[kp] = sd[kp] * pos_gain
+    for kk in ("encoder.final_layernorm.weight", "encoder.final_layernorm.bias"):
+        sd[GPT_PRE + kk] = sd[GPT_PRE + kk] * ln_gain
+    return sd
+
+
+class BeamPool:
+    """BeamHypotheses (:1908-1961): n-best list; the score is sum_logprobs / len(hyp) ** length_penalty where
+    hyp is the PADDED token row the caller hands in (so every hypothesis is normalised by the same length)."""
+
+    def __init__(self, num_beams, length_penalty=1.0, early_stopping=False):
+        self.num_beams, self.length_penalty, self.early_stopping = num_beams, length_penalty, early_stopping
+        self.beams, self.worst_score = [], 1e9
+
+    def add(self, hyp, sum_logprobs):
+        score = sum_logprobs / (hyp.shape[-1] ** self.length_penalty)
+        if len(self.beams) < self.num_beams or score > self.worst_score:
+            self.beams.append((score, hyp))
+            if len(self.beams) > self.num_beams:
+                order = sorted((s, i) for i, (s, _) in enumerate(self.beams))
+                del self.beams[order[0][1]]
+                self.worst_score = order[1][0]
+            else:
+                self.worst_score = min(score, self.worst_score)
+
+    def is_done(self, best_sum_logprobs, cur_len):
+        if len(self.beams) < self.num_beams:
+            return False
+        if self.early_stopping:
+            return True
+        return self.worst_score >= best_sum_logprobs / cur_len ** self.length_penalty
+
+
+def beam_search_generate(tokens, sd, gcfg, query_features=None, prompt_length=None, beam_size=5, num_return_gen=1,
+                         stop_token=None, tokens_to_generate=100, eod_id=7):
+    """DistributedGPT3.beam_search (:1743-1875), batch size 1.  Returns (sequences [n, len], scores [n])."""
+    assert tokens.size(0) == 1
+    plen = int(prompt_length) if prompt_length is not None else tokens.size(1)
+    if stop_token is None:
+        stop_token = eod_id
+    tokens = torch.cat([tokens, torch.full((1, tokens_to_generate), stop_token, dtype=torch.long)], dim=-1)
+    final_len = min(tokens.size(1), gcfg["max_position_embeddings"])
+    if plen >= final_len:
+        raise ValueError("context length + tokens_to_generate too large")
+    pool = BeamPool(beam_size)
+    scores = torch.zeros(beam_size, 1)
+    tokens = tokens.repeat(beam_size, 1)
+    qf = query_features.repeat(beam_size, 1, 1) if query_features is not None else None
+    done = False
+    ctx = plen
+    for ctx in range(plen, final_len):
+        logp = F.log_softmax(next_token_logits(qf, tokens[:, :ctx], sd, gcfg), dim=-1)
+        V = logp.size(1)
+        cand = logp + scores
+        flat = cand[0] if ctx == plen else cand.view(-1)   # all beams are identical at the first step
+        best_scores, idx = torch.sort(flat, descending=True)
+        idx, best_scores = idx[:2 * beam_size], best_scores[:2 * beam_size]
+        beam_ids, words = torch.div(idx, V, rounding_mode="floor"), idx % V
+        nxt = []
+        for rank, (w, sc, b) in enumerate(zip(words.tolist(), best_scores, beam_ids.tolist())):
+            if w == stop_token:
+                if rank >= beam_size:
+                    continue
+                pool.add(tokens[b].clone(), sc)
+            else:
+                nxt.append((w, sc, b))
+            if len(nxt) == beam_size:
+                break
+        if pool.is_done(float(best_scores.max()), ctx + 1 - plen):
+            done = True
+            break
+        keep = torch.tensor([b for _, _, b in nxt])
+        tokens = tokens[keep]
+        tokens[:, ctx] = torch.tensor([w for w, _, _ in nxt])
+        scores = torch.stack([sc for _, sc, _ in nxt]).reshape(-1, 1)
+    if not done:
+        for b in range(beam_size):
+            pool.add(tokens[b].clone(), scores[b])
+    hyps = sorted(pool.beams, key=lambda x: float(x[0]), reverse=True)[:num_return_gen]
+    return torch.stack([h for _, h in hyps]), torch.stack([torch.as_tensor(s).reshape(()) for s, _ in hyps])

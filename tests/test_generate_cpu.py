@@ -1,0 +1,82 @@
+"""CPU: the generation host logic of the product (models.modeling_distributed_gpt3.run_sample /
+run_beam_search, BeamHypotheses, sample) driven by the ORACLE's fp32 next-token logits must reproduce the
+unmodified reference's sequences and scores (tests/golden/tiny_generate.pt, oracle/make_golden.py)."""
+import os
+
+import torch
+
+from oracle import port
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class _OracleDecoder:
+    """Decode callbacks with the same contract as DistributedGPT3._decode_callbacks, full recompute inside."""
+
+    def __init__(self, qf, sd, gcfg):
+        self.qf, self.sd, self.gcfg, self.hist = qf, sd, gcfg, None
+
+    def step(self, new_tokens, first):
+        self.hist = new_tokens.clone() if first else torch.cat([self.hist, new_tokens], dim=1)
+        with torch.no_grad():
+            return port.next_token_logits(self.qf, self.hist, self.sd, self.gcfg)
+
+    def reorder(self, idx):
+        self.hist = self.hist[idx]
+
+
+def _fixture():
+    fx = torch.load(os.path.join(GOLD, "tiny_generate.pt"), weights_only=False)
+    sd = port.generation_state_dict(fx["vcfg"], fx["gcfg"], fx["Q"], fx["wseed"], fx["pos_gain"], fx["ln_gain"])
+    return fx, sd
+
+
+def test_oracle_generation_matches_reference_fixture():
+    fx, sd = _fixture()
+    g, eod, qf = fx["gcfg"], fx["eod"], fx["query_features"]
+    with torch.no_grad():
+        for i in range(fx["B"]):
+            seq, sc = port.beam_search_generate(fx["ids"][i:i + 1], sd, g, query_features=qf[i:i + 1], prompt_length=fx["prompt_length"][i],
+                                                beam_size=fx["beam_size"], stop_token=eod, tokens_to_generate=fx["n_new"], eod_id=eod)
+            assert torch.equal(seq, fx["beam_sequences"][i])
+            assert (sc - fx["beam_scores"][i]).abs().max() < 1e-4
+        greedy = port.sample_generate(fx["ids"].clone(), sd, g, query_features=qf, prompt_length=fx["prompt_length"].clone(),
+                                      tokens_to_generate=fx["n_new"], eod_id=eod, top_k=1, top_p=0.0, termination_id=eod)
+    assert torch.equal(greedy, fx["greedy"])
+
+
+def test_product_host_logic_with_oracle_logits():
+    import models.modeling_distributed_gpt3 as M
+    fx, sd = _fixture()
+    g, eod, qf, Q = fx["gcfg"], fx["eod"], fx["query_features"], fx["Q"]
+    for i in range(fx["B"]):
+        dec = _OracleDecoder(qf[i:i + 1].repeat(fx["beam_size"], 1, 1), sd, g)
+        out = M.run_beam_search(dec.step, dec.reorder, fx["ids"][i:i + 1], int(fx["prompt_length"][i]), Q, beam_size=fx["beam_size"],
+                                num_return_gen=1, stop_token=eod, tokens_to_generate=fx["n_new"],
+                                max_position_embeddings=g["max_position_embeddings"])
+        assert torch.equal(out.sequences, fx["beam_sequences"][i])
+        assert (out.scores.reshape(-1) - fx["beam_scores"][i]).abs().max() < 1e-4
+    dec = _OracleDecoder(qf, sd, g)
+    toks = M.run_sample(dec.step, fx["ids"].clone(), fx["prompt_length"].clone(), Q, tokens_to_generate=fx["n_new"], eod_id=eod,
+                        max_position_embeddings=g["max_position_embeddings"], top_k=1, top_p=0.0, vocab_size=g["vocab_size"],
+                        termination_id=eod)
+    assert torch.equal(toks, fx["greedy"])
+
+
+def test_sampling_filters():
+    import models.modeling_distributed_gpt3 as M
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(4, 50, generator=g)
+    a = logits.clone()
+    M.modify_logits_for_top_k_filtering(a, 5)
+    assert torch.equal(a, port.filter_top_k(logits, 5)) and int(torch.isfinite(a).sum()) == 20
+    b = logits.clone()
+    M.modify_logits_for_top_p_filtering(b, 0.7)
+    assert torch.equal(b, port.filter_top_p(logits, 0.7))
+    assert bool(torch.isfinite(b).any(dim=-1).all())
+    assert torch.equal(M.sample(logits, top_k=1), logits.argmax(-1))
+    torch.manual_seed(3)
+    s1 = M.sample(logits, top_k=0, top_p=0.9, temperature=0.7, vocab_size=40)
+    torch.manual_seed(3)
+    s2 = port.pick_token(logits, top_k=0, top_p=0.9, temperature=0.7, vocab_size=40)
+    assert torch.equal(s1, s2) and int(s1.max()) < 40

@@ -183,8 +183,7 @@ class DistributedGPT3_Pretrain(_PrefixModelBase):
 
 
 class DistributedGPT3_Caption(_PrefixModelBase):
-    """Caption fine-tuning forward (:751-788); generate() (beam search over a KV cache) is the
-    'next' row N2 of SURVEY.md section 8f and is not built yet."""
+    """Caption fine-tuning forward (:751-788) and generate() (:790-809, beam search over the KV cache)."""
 
     def __init__(self, config=None, tokenizer=None):
         super().__init__()
@@ -204,8 +203,18 @@ class DistributedGPT3_Caption(_PrefixModelBase):
         input_embeds = torch.cat([query_features, self._word_embedding()(text.input_ids).to(query_features.dtype)], dim=1)
         return self.text_decoder(input_embeds=input_embeds, loss_mask=loss_mask, labels=targets).loss
 
+    @torch.no_grad()
     def generate(self, image, text):
-        raise NotImplementedError("generation (KV-cache beam search) is SURVEY.md section 8f row N2")
+        """Per-sample beam search (beam 5) over the visual prefix (:790-809): list of [1, len] LongTensors on
+        the CPU.  prompt_length = attention_mask.sum(-1) - 1, stop token = the tokenizer's <|endoftext|>."""
+        _, _, _, query_features = self.visual_prefix(image)
+        eos = self.tokenizer.tokenizer.eos if self.tokenizer is not None else self.text_decoder.config.eod_id
+        res = []
+        for i in range(len(text.input_ids)):
+            out = self.text_decoder.generate(text.input_ids[i:i + 1], query_embeds=query_features[i:i + 1], termination_id=eos,
+                                             do_sample=False, prompt_length=text.attention_mask.sum(-1)[i] - 1)
+            res.append(out.sequences.cpu())
+        return res
 
 
 class _PromptClsBase(_PrefixModelBase):

@@ -253,6 +253,196 @@ def _check_tp1(megatron_cfg):
                              "(as the reference's own scripts/*.sh:13-14 and retrieval yaml do)")
 
 
+# ----------------------------------------------------------------------------------------------
+# Generation: the host logic of models/modeling_distributed_gpt3.py:1369-1473,1620-1886,
+# 1908-1961 on top of the KV-cache decode path of ymp.engine.
+# ----------------------------------------------------------------------------------------------
+def modify_logits_for_top_k_filtering(logits, top_k):
+    """In place: everything below the k-th largest logit of its row becomes -inf (:1369-1373)."""
+    kth = torch.topk(logits, top_k)[0][..., -1, None]
+    logits.masked_fill_(logits < kth, float('-Inf'))
+
+
+def modify_logits_for_top_p_filtering(logits, top_p):
+    """In place nucleus filter (:1376-1395): sorted cumulative probability > top_p is dropped, shifted by
+    one position so that the token crossing the threshold is kept; the best token always survives."""
+    sorted_logits, sorted_indices = torch.sort(logits, descending=True)
+    drop = sorted_logits.softmax(dim=-1).cumsum(dim=-1) > top_p
+    drop[:, 1:] = drop[:, :-1].clone()
+    drop[..., 0] = 0
+    logits.masked_fill_(drop.scatter(1, sorted_indices, drop), float('-Inf'))
+
+
+def sample(logits, top_k=0, top_p=0.0, temperature=1.0, vocab_size=None):
+    """One token per row of logits [b, v] (:1398-1446): argmax when top_k == 1, otherwise temperature,
+    top-k or top-p filtering and a multinomial draw; clamped into [0, vocab_size)."""
+    assert logits.ndim == 2, 'expected the logits to be of [b, v] shape.'
+    if top_k == 1:
+        assert top_p == 0.0, 'cannot set both greedy and top-p samplings.'
+        samples = torch.argmax(logits, dim=-1)
+    else:
+        logits = logits.clone()
+        if temperature != 1.0:
+            logits.div_(temperature)
+        if top_k > 1:
+            assert top_p == 0.0, 'cannot set both top-k and top-p samplings.'
+            assert top_k <= logits.size(1), 'top-k is larger than logit size.'
+            if vocab_size:
+                assert top_k < vocab_size, 'top-k is larger than vocab size.'
+            modify_logits_for_top_k_filtering(logits, top_k)
+        elif top_p > 0.0:
+            assert top_p <= 1.0, 'top-p should be in (0, 1].'
+            modify_logits_for_top_p_filtering(logits, top_p)
+        samples = torch.multinomial(logits.softmax(dim=-1), num_samples=1).view(-1)
+    if vocab_size:
+        samples = torch.clamp(samples, min=0, max=(vocab_size - 1))
+    return samples
+
+
+class InferenceParams:
+    """Incremental-decoding state (:1449-1473).  The key/value memory of every layer lives in one
+    ymp.engine.KVCache (packed QKV rows the attention kernels read in place); `key_value_memory_dict`
+    exposes it per layer number for code that only checks for emptiness."""
+
+    def __init__(self, max_batch_size, max_sequence_len):
+        self.max_sequence_len = max_sequence_len
+        self.max_batch_size = max_batch_size
+        self.sequence_len_offset = 0
+        self.batch_size_offset = 0
+        self.key_value_memory_dict = {}
+        self.cache = None
+
+    def swap_key_value_dict(self, batch_idx):
+        'swap between batches'
+        if self.cache is None:
+            raise ValueError('should not swap when dict in empty')
+        assert len(batch_idx) == self.cache.B  # make sure batch size is the same
+        self.cache.reorder(torch.as_tensor(batch_idx, device=self.cache.qkv[0].device, dtype=torch.long))
+        self.key_value_memory_dict = {i + 1: t for i, t in enumerate(self.cache.qkv)}
+
+
+class BeamHypotheses:
+    """n-best list of finished hypotheses (:1908-1961).  score = sum_logprobs / len(hyp) ** length_penalty,
+    where hyp is the (padded) token row handed in by beam_search."""
+
+    def __init__(self, num_beams, length_penalty=1.0, early_stopping=False):
+        self.length_penalty = length_penalty
+        self.early_stopping = early_stopping
+        self.num_beams = num_beams
+        self.beams = []
+        self.worst_score = 1e9
+
+    def __len__(self):
+        return len(self.beams)
+
+    def add(self, hyp, sum_logprobs, beam_indices=None):
+        score = sum_logprobs / (hyp.shape[-1] ** self.length_penalty)
+        if len(self) < self.num_beams or score > self.worst_score:
+            self.beams.append((score, hyp, beam_indices))
+            if len(self) > self.num_beams:
+                ranked = sorted((s, idx) for idx, (s, _, _) in enumerate(self.beams))
+                del self.beams[ranked[0][1]]
+                self.worst_score = ranked[1][0]
+            else:
+                self.worst_score = min(score, self.worst_score)
+
+    def is_done(self, best_sum_logprobs, cur_len):
+        if len(self) < self.num_beams:
+            return False
+        if self.early_stopping:
+            return True
+        return self.worst_score >= best_sum_logprobs / cur_len ** self.length_penalty
+
+
+def run_sample(step, tokens, lengths, n_query, *, tokens_to_generate, eod_id, max_position_embeddings, top_k, top_p,
+               temperature=1.0, vocab_size=None, termination_id=None, use_eod_token_for_early_termination=True,
+               stop_on_double_eol=False, stop_on_eol=False):
+    """DistributedGPT3.sample's loop (:1620-1741) over a decode callback.
+    step(new_tokens [B, n], first) -> next-token logits [B, V] of the last position (fp32); the callback owns
+    the KV cache and the visual prefix (n_query positions, fed on the first call)."""
+    B = tokens.size(0)
+    dev = tokens.device
+    lengths = lengths.to(dev)
+    tokens = torch.cat((tokens, torch.full((B, tokens_to_generate), eod_id, dtype=torch.long, device=dev)), dim=-1)
+    max_len = min(tokens.size(1), max_position_embeddings)
+    min_prompt = int(lengths.min().item())
+    if min_prompt >= max_len:
+        raise ValueError('context length + tokens_to_generate too large')
+    if termination_id is None:
+        termination_id = eod_id
+    finished = torch.zeros(B, dtype=torch.bool, device=dev)
+    prev = 0
+    ctx = min_prompt
+    for ctx in range(min_prompt, max_len):
+        logits = step(tokens[:, prev:ctx], ctx == min_prompt)
+        new = sample(logits, top_k=top_k, top_p=top_p, temperature=temperature, vocab_size=vocab_size)
+        started = lengths <= ctx  # samples whose prompt has been consumed start writing their own tokens
+        tokens[started, ctx] = new[started]
+        prev = ctx
+        if stop_on_double_eol:
+            hit = ((new == 628) | ((new == 198) & (tokens[:, ctx - 1] == 198))) & started
+        elif stop_on_eol:
+            hit = ((new == 628) | (new == 198)) & started
+        else:
+            hit = (new == termination_id) & started
+        finished |= hit
+        if use_eod_token_for_early_termination and bool(finished.all()):
+            break
+    # the reference slices with the context length that still counts the prefix positions (:1740)
+    return tokens[:, :ctx + n_query + 1]
+
+
+def run_beam_search(step, reorder, tokens, prompt_length, n_query, *, beam_size, num_return_gen, stop_token,
+                    tokens_to_generate, max_position_embeddings):
+    """DistributedGPT3.beam_search's loop (:1743-1875), batch size 1, over a decode callback.
+    step(new_tokens [beam, n], first) -> logits [beam, V]; reorder(idx) permutes the callback's KV cache."""
+    assert tokens.size(0) == 1
+    dev = tokens.device
+    tokens = torch.cat((tokens, torch.full((1, tokens_to_generate), stop_token, dtype=torch.long, device=dev)), dim=-1)
+    final_len = min(tokens.size(1), max_position_embeddings)
+    if prompt_length >= final_len:
+        raise ValueError('context length + tokens_to_generate too large')
+    pool = BeamHypotheses(beam_size)
+    scores = torch.zeros(beam_size, 1, dtype=torch.float32, device=dev)
+    tokens = tokens.repeat(beam_size, 1)
+    done = False
+    prev = 0
+    ctx = prompt_length
+    for ctx in range(prompt_length, final_len):
+        logits = step(tokens[:, prev:ctx], ctx == prompt_length)
+        vocab = logits.size(-1)
+        cand = torch.log_softmax(logits.float(), dim=-1) + scores
+        flat = cand[0] if ctx == prompt_length else cand.view(-1)  # identical beams at the first step
+        ranked_scores, ranked = torch.sort(flat, descending=True)
+        ranked, ranked_scores = ranked[:2 * beam_size], ranked_scores[:2 * beam_size]
+        beam_of, word_of = torch.div(ranked, vocab, rounding_mode='floor').tolist(), (ranked % vocab).tolist()
+        survivors = []
+        for rank, (word, beam) in enumerate(zip(word_of, beam_of)):
+            if word == stop_token:
+                if rank >= beam_size:  # a finished hypothesis outside the top beam_size candidates is dropped
+                    continue
+                pool.add(tokens[beam].clone(), ranked_scores[rank], ctx + 1 - prompt_length)
+            else:
+                survivors.append((word, ranked_scores[rank], beam))
+            if len(survivors) == beam_size:
+                break
+        if pool.is_done(ranked_scores.max().item(), ctx + 1 - prompt_length):
+            done = True
+            break
+        keep = torch.tensor([b for _, _, b in survivors], dtype=torch.long, device=dev)
+        tokens = tokens[keep, :]
+        tokens[:, ctx] = torch.tensor([w for w, _, _ in survivors], dtype=torch.long, device=dev)
+        scores = torch.stack([sc for _, sc, _ in survivors]).reshape(-1, 1).float()
+        reorder(keep)
+        prev = ctx
+    if not done:
+        for b in range(beam_size):
+            pool.add(tokens[b].clone(), scores[b], ctx + 1 - prompt_length)
+    best = sorted(pool.beams, key=lambda x: float(x[0]), reverse=True)[:min(num_return_gen, len(pool.beams))]
+    return AttrDict(sequences=torch.stack([h for _, h, _ in best], dim=0),
+                    scores=torch.stack([torch.as_tensor(sc, device=dev).reshape(-1)[0] for sc, _, _ in best], dim=0))
+
+
 class GPT3Model(nn.Module):
     """Parameter container with the reference's names: language_model.{embedding,encoder}...."""
 
@@ -335,7 +525,7 @@ class DistributedGPT3(nn.Module):
         if query_embeds is not None:
             input_embeds = torch.cat([query_embeds.to(input_embeds.dtype), input_embeds], dim=1)
         if labels is None:
-            raise NotImplementedError("KV-cache decoding is a later row (SURVEY.md section 8f N2); pass labels")
+            return self._decode(tokens, input_embeds, 0 if query_embeds is None else query_embeds.size(1))
         keys, params = self._param_list()
         logits, losses, hidden = YF.GptFn.apply(input_embeds, labels.contiguous(), self.config.engine_cfg(), True,
                                                 keys, *params)
@@ -345,3 +535,77 @@ class DistributedGPT3(nn.Module):
         lm = loss_mask.reshape(-1).float()
         loss = torch.sum(losses.reshape(-1) * lm) / lm.sum()
         return AttrDict(logits=logits, loss=loss, losses=losses, last_hidden_state=hidden)
+
+    # ------------------------------------------------------------------------------------------ generation
+    def _decode(self, tokens, input_embeds, n_query):
+        """Inference branch of forward (:1576-1603): one incremental step over the KV cache.  input_embeds
+        [B, n, H] already holds [prefix | word embeddings]; logits are returned for the LAST position only
+        ([B, 1, V] fp32 - the only row sample()/beam_search() read)."""
+        from ymp import engine, ops
+        if self.inference_params is None:
+            raise ValueError("no labels and no inference_params: call sample()/beam_search()/generate()")
+        ip = self.inference_params
+        keys, params = self._param_list()
+        W = {k: YF.as_bf16(p) for k, p in zip(keys, params)}
+        B, n, H = input_embeds.shape
+        if ip.cache is None:
+            ip.cache = engine.KVCache(self.config.engine_cfg(), ip.max_batch_size, ip.max_sequence_len, input_embeds.device)
+            ip.key_value_memory_dict = {i + 1: t for i, t in enumerate(ip.cache.qkv)}
+        off = ip.sequence_len_offset
+        assert off == ip.cache.len and B == ip.cache.B
+        pos = W[engine.GPT + "embedding.position_embeddings.weight"]
+        x = (input_embeds.float() + pos[off:off + n][None].float()).reshape(B * n, H).contiguous()
+        hid = engine.gpt_decode(W, x, ip.cache, n)
+        logits = ops.gemm(hid, W[engine.GPT + "embedding.word_embeddings.weight"]).float()
+        ip.sequence_len_offset += n  # tokens.size(1) + query_embeds.size(1) of the reference
+        return AttrDict(logits=logits.view(B, 1, -1), loss=None, losses=None, last_hidden_state=hid.view(B, 1, H))
+
+    def _decode_callbacks(self, query_embeds):
+        def step(new_tokens, first):
+            out = self(tokens=new_tokens, query_embeds=query_embeds if first else None)
+            return out.logits[:, -1, :]
+
+        def reorder(idx):
+            self.inference_params.swap_key_value_dict(idx)
+        return step, reorder
+
+    @torch.no_grad()
+    def sample(self, tokens, query_embeds=None, temperature=1.0, use_eod_token_for_early_termination=True,
+               stop_on_double_eol=False, stop_on_eol=False, termination_id=None, **kwargs):
+        """Batched greedy / top-k / top-p decoding (:1620-1741)."""
+        cfg = self.config
+        lengths = kwargs.pop('prompt_length', torch.tensor([tokens.size(1)], device=tokens.device))
+        lengths = torch.as_tensor(lengths, device=tokens.device).reshape(-1)
+        nq = 0 if query_embeds is None else query_embeds.size(1)
+        max_len = min(tokens.size(1) + cfg.tokens_to_generate, cfg.max_position_embeddings)
+        self.inference_params = InferenceParams(tokens.size(0), max_len + nq)
+        step, _ = self._decode_callbacks(query_embeds)
+        return run_sample(step, tokens, lengths, nq, tokens_to_generate=cfg.tokens_to_generate, eod_id=cfg.eod_id,
+                          max_position_embeddings=cfg.max_position_embeddings, top_k=cfg.top_k, top_p=cfg.top_p,
+                          temperature=temperature, vocab_size=cfg.vocab_size, termination_id=termination_id,
+                          use_eod_token_for_early_termination=use_eod_token_for_early_termination,
+                          stop_on_double_eol=stop_on_double_eol, stop_on_eol=stop_on_eol)
+
+    @torch.no_grad()
+    def beam_search(self, tokens, query_embeds=None, beam_size=5, num_return_gen=1, stop_token=None, **kwargs):
+        """Beam search for one sample (:1743-1875): Dict(sequences [n, len], scores [n])."""
+        cfg = self.config
+        assert tokens.size(0) == 1
+        prompt_length = int(kwargs.pop('prompt_length', tokens.size(1)))
+        if stop_token is None:
+            stop_token = cfg.eod_id
+        nq = 0 if query_embeds is None else query_embeds.size(1)
+        final_len = min(tokens.size(1) + cfg.tokens_to_generate, cfg.max_position_embeddings)
+        self.inference_params = InferenceParams(beam_size, final_len + nq)
+        qe = None if query_embeds is None else query_embeds.repeat(beam_size, 1, 1)
+        step, reorder = self._decode_callbacks(qe)
+        return run_beam_search(step, reorder, tokens, prompt_length, nq, beam_size=beam_size, num_return_gen=num_return_gen,
+                               stop_token=stop_token, tokens_to_generate=cfg.tokens_to_generate,
+                               max_position_embeddings=cfg.max_position_embeddings)
+
+    @torch.no_grad()
+    def generate(self, tokens, do_sample=True, termination_id=None, *args, **kwargs):
+        """(:1878-1883)"""
+        if do_sample:
+            return self.sample(tokens, termination_id=termination_id, *args, **kwargs)
+        return self.beam_search(tokens, stop_token=termination_id, *args, **kwargs)

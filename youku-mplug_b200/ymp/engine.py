@@ -464,6 +464,63 @@ def gpt_bwd(W, G, c, dhid):
     return dx
 
 
+class KVCache:
+    """Incremental-decoding state (the reference's InferenceParams.key_value_memory_dict,
+    models/modeling_distributed_gpt3.py:874-923).  One packed QKV buffer [B*max_len, 3H] per layer in the
+    per-head [q|k|v] column layout of the QKV GEMM, so new rows are written by the GEMM epilogue itself
+    (row re-blocking) and the attention kernels read K/V of all cached positions in place."""
+
+    def __init__(self, gcfg, batch, max_len, device):
+        g = GptDims(gcfg)
+        self.g, self.B, self.max_len, self.len = g, batch, max_len, 0
+        self.qkv = [torch.zeros((batch * max_len, 3 * g.H), device=device, dtype=bf16) for _ in range(g.layers)]
+
+    def reorder(self, idx):
+        """Row b of the cache becomes old row idx[b] (beam search, swap_key_value_dict :1460-1473)."""
+        assert idx.numel() == self.B
+        for i, t in enumerate(self.qkv):
+            self.qkv[i] = t.view(self.B, self.max_len, -1).index_select(0, idx).reshape(self.B * self.max_len, -1)
+
+
+def gpt_decode(W, x, cache, n):
+    """n new positions per sequence through all layers with the KV cache.  x [B*n, H] fp32 = embeddings +
+    learned positions of positions cache.len .. cache.len+n-1 (rows b*n + i).  Either the first call
+    (cache empty: causal attention inside the block) or single-token steps (n == 1: the query sees every
+    cached key).  Returns the final-LayerNorm hidden state of the LAST new position of every sequence [B, H]."""
+    g, B, ML, off = cache.g, cache.B, cache.max_len, cache.len
+    H, hd = g.H, g.hd
+    if off + n > ML:
+        raise ValueError(f"KV cache overflow: {off} + {n} > {ML}")
+    if off > 0 and n != 1:
+        raise NotImplementedError("multi-token continuation after the first block is not supported")
+    for i in range(g.layers):
+        pre = f"{GPT}encoder.layers.{i}."
+        ln1, _, _ = ops.layernorm_fwd(x, W[pre + "input_layernorm.weight"], W[pre + "input_layernorm.bias"], g.eps, stats=False)
+        buf = cache.qkv[i]
+        new_rows = buf[off:]  # GEMM row (b, i) -> buffer row b*max_len + off + i
+        ops.gemm(ln1, W[pre + "self_attention.query_key_value.weight"], bias=W[pre + "self_attention.query_key_value.bias"],
+                 out=new_rows, d_row_block=n, d_row_stride=ML)
+        att = torch.empty((B * n, H), device=x.device, dtype=bf16)
+        mq = ops.seqmap(seq_div=1, outer_stride=ML, pos_stride=1)
+        mkv = ops.dense_map(ML)
+        q = TView(new_rows, 0, 3 * hd, mq)
+        k, v = TView(buf, hd, 3 * hd, mkv), TView(buf, 2 * hd, 3 * hd, mkv)
+        ops.attn_fwd(q, k, v, TView(att, 0, hd, ops.dense_map(n)), n_seq=B, n_heads=g.heads, head_dim=hd, s_q=n, s_kv=off + n,
+                     causal=(off == 0 and n > 1), scale=g.scale)
+        x1 = ops.gemm(att, W[pre + "self_attention.dense.weight"], bias=W[pre + "self_attention.dense.bias"], residual=x,
+                      out_dtype=torch.float32)
+        ln2, _, _ = ops.layernorm_fwd(x1, W[pre + "post_attention_layernorm.weight"], W[pre + "post_attention_layernorm.bias"], g.eps,
+                                      stats=False)
+        h = ops.gemm(ln2, W[pre + "mlp.dense_h_to_4h.weight"], bias=W[pre + "mlp.dense_h_to_4h.bias"], act=ACT_GELU_TANH)
+        x = ops.gemm(h, W[pre + "mlp.dense_4h_to_h.weight"], bias=W[pre + "mlp.dense_4h_to_h.bias"], residual=x1,
+                     out_dtype=torch.float32)
+    cache.len = off + n
+    last = torch.arange(B, device=x.device, dtype=torch.int32) * n + (n - 1)
+    hid, _, _ = ops.layernorm_fwd(x, W[GPT + "encoder.final_layernorm.weight"], W[GPT + "encoder.final_layernorm.bias"], g.eps,
+                                  in_rows=last, stats=False)
+    return hid
+
+
 def lm_head_fwd(W, hid, labels):
     """Tied LM head + per-token CE on fp32 math (modeling_distributed_gpt3.py:1348-1359).
     Returns (logits [B*S, V] bf16, losses [B*S] fp32, lse)."""

@@ -33,7 +33,8 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, 
         assert not accumulate, "accumulate needs an explicit (zeroed or running) output"
     _chk2d(out, "out")
     if d_row_block:
-        assert out.shape[1] == N and out.shape[0] >= (M // d_row_block) * d_row_stride
+        assert out.shape[1] == N and M % d_row_block == 0
+        assert out.shape[0] >= (M // d_row_block - 1) * d_row_stride + d_row_block  # last row written
     else:
         assert out.shape == (M, N), f"gemm: out shape {tuple(out.shape)} != {(M, N)}"
     g = L.GemmArgs()
