@@ -91,7 +91,10 @@ def _attn_ref(q, k, v, scale, causal):
 
 @pytest.mark.parametrize("hd,heads,S,causal,layout", [
     (64, 4, 256, True, "gpt"), (64, 2, 100, True, "gpt"), (80, 2, 130, True, "gpt"),
-    (96, 2, 197, False, "vit"), (96, 8, 64, False, "vit"), (64, 2, 300, False, "vit")])
+    (96, 2, 197, False, "vit"), (96, 8, 64, False, "vit"), (64, 2, 300, False, "vit"),
+    # tcgen05 kernels at block boundaries: one / two key blocks, partial second query block, tiny sequences
+    (64, 2, 129, True, "gpt"), (96, 1, 33, True, "vit"), (96, 2, 128, False, "vit"), (96, 2, 256, False, "gpt"),
+    (64, 3, 160, False, "gpt"), (64, 1, 8, True, "gpt")])
 def test_attn_dense_fwd_bwd(cuda, hd, heads, S, causal, layout):
     from ymp import ops
     torch.manual_seed(2)
@@ -131,6 +134,36 @@ def test_attn_dense_fwd_bwd(cuda, hd, heads, S, causal, layout):
     assert _rel(dq, q.grad) < 3e-2
     assert _rel(dk, k.grad) < 3e-2
     assert _rel(dv, v.grad) < 3e-2
+
+
+@pytest.mark.parametrize("hd,S,total,causal", [(64, 100, 250, True), (96, 197, 300, False), (64, 256, 700, True)])
+def test_attn_dense_ragged_total_rows(cuda, hd, S, total, causal):
+    """Dense packed sequences whose last sequence is cut short by total_rows (forward + backward)."""
+    from ymp import ops
+    torch.manual_seed(12)
+    heads = 2
+    C = heads * hd
+    n = (total + S - 1) // S
+    qkv = (torch.randn(total, 3 * C, device=cuda) * 0.7).to(bf16)
+    out = torch.zeros(total, C, device=cuda, dtype=bf16)
+    m = ops.dense_map(S)
+    tq, tk, tv = (ops.TView(qkv, i * C, hd, m) for i in range(3))
+    kw = dict(n_seq=n, n_heads=heads, head_dim=hd, s_q=S, s_kv=S, causal=causal, scale=hd ** -0.5, total_rows=total)
+    lse = ops.attn_fwd(tq, tk, tv, ops.TView(out, 0, hd, m), **kw)
+    dout = torch.randn(total, C, device=cuda).to(bf16)
+    dqkv = torch.zeros_like(qkv)
+    ops.attn_bwd(tq, tk, tv, ops.TView(out, 0, hd, m), lse, ops.TView(dout, 0, hd, m),
+                 *(ops.TView(dqkv, i * C, hd, m) for i in range(3)), **kw)
+    for s in range(n):
+        r0, r1 = s * S, min(total, (s + 1) * S)
+        x = qkv[r0:r1].float().view(r1 - r0, 3, heads, hd)
+        q, k, v = (x[:, i].permute(1, 0, 2)[None].contiguous().requires_grad_() for i in range(3))
+        ref = _attn_ref(q, k, v, hd ** -0.5, causal)
+        assert _rel(out[r0:r1].view(r1 - r0, heads, hd).permute(1, 0, 2)[None], ref) < 2e-2
+        ref.backward(dout[r0:r1].float().view(r1 - r0, heads, hd).permute(1, 0, 2)[None])
+        d = dqkv[r0:r1].float().view(r1 - r0, 3, heads, hd)
+        for i, g in enumerate((q.grad, k.grad, v.grad)):
+            assert _rel(d[:, i].permute(1, 0, 2)[None], g) < 3e-2, (s, i)
 
 
 def test_attn_cross_shared_q(cuda):
