@@ -12,7 +12,20 @@ from ymp import lib as L  # noqa: E402
 import attn_probe  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "spatial"
-(attn_probe.spatial if which == "spatial" else attn_probe.gpt)(reps=1)
+if which == "fwd":  # forward only (the backward would overwrite the trace buffer)
+    from ymp import ops
+    from ymp.ops import TView
+    B, N, T, heads, hd = 32, 196, 8, 8, 96
+    D, R, RB = heads * hd, B * N * T, B * N * T + B
+    qkv = (torch.randn(RB, 3 * D, device="cuda") * 0.5).to(torch.bfloat16)
+    att = torch.empty(RB + B * T, D, device="cuda", dtype=torch.bfloat16)
+    m_in = ops.seqmap(seq_div=T, outer_stride=N * T, inner_stride=1, pos_stride=T, n_prefix=1, prefix_base=R, prefix_stride=1)
+    m_out = ops.seqmap(seq_div=T, outer_stride=N * T, inner_stride=1, pos_stride=T, n_prefix=1, prefix_base=RB, prefix_stride=1, prefix_per_seq=1)
+    q, k, v = (TView(qkv, i * D, hd, m_in) for i in range(3))
+    for _ in range(3):
+        ops.attn_fwd(q, k, v, TView(att, 0, hd, m_out), n_seq=B * T, n_heads=heads, head_dim=hd, s_q=N + 1, s_kv=N + 1, causal=False, scale=hd ** -0.5)
+else:
+    (attn_probe.spatial if which == "spatial" else attn_probe.gpt)(reps=1)
 torch.cuda.synchronize()
 buf = (ctypes.c_ulonglong * 256)()
 rc = L.lib.ymp_attn_dbg_read(buf)

@@ -125,6 +125,17 @@ __device__ __forceinline__ void tc_load(uint8_t* blk0, uint8_t* blk1, const TcMa
   }
 }
 
+#ifdef YMP_ATTN_DBG
+__device__ unsigned long long ymp_attn_dbg_buf[256];
+#define TDBG(k)                                                                                        \
+  do {                                                                                                 \
+    if (YMP_DBG_BLOCK && threadIdx.x == 0 && dbg_n < 256)                        \
+      ymp_attn_dbg_buf[dbg_n++] = ((unsigned long long)(k) << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull); \
+  } while (0)
+#else
+#define TDBG(k)
+#endif
+
 template <int HD>
 __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) {
   static_assert(HD == 64 || HD == 96, "head_dim 64 or 96");
@@ -144,6 +155,11 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, s = blockIdx.z;
+#ifdef YMP_ATTN_DBG
+#define YMP_DBG_BLOCK (blockIdx.x == 0 && blockIdx.y == 3 && blockIdx.z == 100 && gridDim.z > 100 && blockDim.x == 128)
+  int dbg_n = 0;
+#endif
+  TDBG(0);
   int sq = p.s_q, skv = p.s_kv;
   if (p.total_rows > 0) {
     const long left = p.total_rows - (long)s * p.s_q;
@@ -170,12 +186,14 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
     tc_load<HD>(k0s, k1s, Mk, 0, nkv, kv_end);
     tc_load<HD>(v0s, v1s, Mv, 0, nkv, kv_end);
   }
+  TDBG(1);
   asm volatile("cp.async.wait_all;" ::: "memory");
   fence_proxy_async();  // smem written through the generic proxy is read by the tensor core's async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  TDBG(2);
 
   // ---- S = Q K^T
   if (threadIdx.x == 0) {
@@ -194,8 +212,10 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
     }
     umma_commit(&bar[0]);
   }
+  TDBG(3);
   mbar_wait(&bar[0], 0);
   tc_fence_after();
+  TDBG(4);
 
   // ---- exact softmax: thread = query row = TMEM lane
   const int row = q0 + warp * 32 + lane;
@@ -223,6 +243,7 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
       }
     }
   }
+  TDBG(5);
   const float ms = (mx == -CUDART_INF_F) ? 0.f : mx * p.scale_log2;
   float lsum = 0.f;
   for (int c = 0; c < nch; ++c) {
@@ -252,10 +273,12 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
     }
     tmem_st16(tl + c * 16, pk);  // P (bf16 pairs) overwrites S columns that are already consumed
   }
+  TDBG(6);
   tmem_st_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  TDBG(7);
 
   // ---- O = P V   (A = P from TMEM, B = V MN-major)
   constexpr uint32_t O_COL = 128;
@@ -270,8 +293,10 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
     }
     umma_commit(&bar[1]);
   }
+  TDBG(8);
   mbar_wait(&bar[1], 0);
   tc_fence_after();
+  TDBG(9);
 
   // ---- epilogue
   const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
@@ -299,6 +324,7 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
     }
   }
   if (valid && p.lse) p.lse[((size_t)s * p.n_heads + h) * p.s_q + row] = mx * p.scale + logf(lsum);
+  TDBG(10);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -415,16 +441,6 @@ __device__ __forceinline__ void tc_rows_load256(uint8_t* stage, const TcMat& m, 
   }
 }
 
-#ifdef YMP_ATTN_DBG
-__device__ unsigned long long ymp_attn_dbg_buf[256];
-#define TDBG(k)                                                                                        \
-  do {                                                                                                 \
-    if (blockIdx.x == 3 && blockIdx.y == 200 && threadIdx.x == 0 && dbg_n < 256)                        \
-      ymp_attn_dbg_buf[dbg_n++] = ((unsigned long long)(k) << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull); \
-  } while (0)
-#else
-#define TDBG(k)
-#endif
 
 template <int HD>
 __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdParams p) {
