@@ -209,6 +209,24 @@ typedef struct ymp_im2col_args {
 } ymp_im2col_args;
 int ymp_im2col(const ymp_im2col_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Input pipeline tail on the GPU: uint8 clips [B,T,H,W,C] (decoded, resized and
+ * augmented frames) -> normalised bf16 model input [B,C,T,H,W].  Replaces
+ * volume_transforms.ClipToTensor (`clip / 255.`, dataset/video_utils/volume_transforms.py:25-37) +
+ * video_transforms.Normalize (`sub_(mean).div_(std)`, dataset/video_utils/functional.py:125-137) +
+ * the default collate + `.to(device)` + bf16 cast (dataset/__init__.py:60-85), and cuts the
+ * host->device traffic 4x (1 byte per value instead of an fp32).
+ * lut[c*256 + v] is the bf16 result for channel c and pixel value v; the host fills it with the
+ * reference's own fp32 op order, so the kernel is bit-exact by construction (a gather).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ymp_clip_args {
+  const void* frames;  /* uint8 [B,T,H,W,C] contiguous */
+  void* out;           /* bf16 [B,C,T,H,W] contiguous */
+  const void* lut;     /* bf16 [C*256] (device memory) */
+  int32_t B, T, H, W, C;
+} ymp_clip_args;
+int ymp_clip_normalize(const ymp_clip_args* a, void* stream);
+
 /* Word-embedding gather + learned position add, written straight into the decoder input
  * buffer [B, S, hidden] at rows row_offset..row_offset+L-1 of each sample.  Replaces
  * word_embeddings(ids) + cat + position add (models/distributed_gpt3.py:155-156,

@@ -563,3 +563,24 @@ def beam_search_generate(tokens, sd, gcfg, query_features=None, prompt_length=No
             pool.add(tokens[b].clone(), scores[b])
     hyps = sorted(pool.beams, key=lambda x: float(x[0]), reverse=True)[:num_return_gen]
     return torch.stack([h for _, h in hyps]), torch.stack([torch.as_tensor(s).reshape(()) for s, _ in hyps])
+
+
+# ------------------------------------------------------------------------------------------
+# Input pipeline tail
+# ------------------------------------------------------------------------------------------
+CLIP_MEAN = [0.48145466, 0.4578275, 0.40821073]   # dataset/__init__.py:69-72
+CLIP_STD = [0.26862954, 0.26130258, 0.27577711]
+
+
+def clip_to_model_input(frames, mean=CLIP_MEAN, std=CLIP_STD):
+    """uint8 [B,T,H,W,C] -> bf16 [B,C,T,H,W]: volume_transforms.ClipToTensor (`torch.from_numpy(clip) / 255.` after the
+    (3,0,1,2) transpose, dataset/video_utils/volume_transforms.py:25-37), functional.normalize (`sub_(mean).div_(std)`
+    with fp32 mean/std tensors, dataset/video_utils/functional.py:125-137), default collate, bf16 cast."""
+    out = []
+    for clip in frames:
+        x = clip.permute(3, 0, 1, 2) / 255.
+        m = torch.as_tensor(mean, dtype=x.dtype)
+        s = torch.as_tensor(std, dtype=x.dtype)
+        x.sub_(m[:, None, None, None]).div_(s[:, None, None, None])
+        out.append(x)
+    return torch.stack(out).to(torch.bfloat16)

@@ -31,7 +31,7 @@ def test_ctypes_structs_match_header_field_order():
     hdr = open(os.path.join(ROOT, "include", "ymp.h")).read()
     mirrors = {"ymp_gemm_args": L.GemmArgs, "ymp_layernorm_args": L.LayerNormArgs, "ymp_layernorm_bwd_args": L.LayerNormBwdArgs,
                "ymp_seqmap": L.SeqMap, "ymp_attn_args": L.AttnArgs, "ymp_attn_bwd_args": L.AttnBwdArgs,
-               "ymp_adamw_args": L.AdamwArgs, "ymp_im2col_args": L.Im2colArgs, "ymp_embed_args": L.EmbedArgs,
+               "ymp_adamw_args": L.AdamwArgs, "ymp_im2col_args": L.Im2colArgs, "ymp_clip_args": L.ClipArgs, "ymp_embed_args": L.EmbedArgs,
                "ymp_ce_args": L.CeArgs, "ymp_colsum_args": L.ColsumArgs, "ymp_group_args": L.GroupArgs}
     for name, cls in mirrors.items():
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
@@ -143,3 +143,14 @@ def test_resize_embeddings():
     te = torch.randn(1, 4, 8)
     assert V.resize_temporal_embed(te, torch.zeros(1, 8, 8)).shape == (1, 8, 8)
     assert torch.equal(V.resize_temporal_embed(te, torch.zeros(1, 4, 8)), te)
+
+
+def test_clip_lut_equals_reference_ops():
+    """The table the GPU kernel gathers from reproduces ClipToTensor + Normalize + bf16 cast bit for bit."""
+    from ymp import ops
+    g = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (2, 3, 8, 16, 3), generator=g, dtype=torch.uint8)
+    ref = port.clip_to_model_input(frames)
+    lut = ops.clip_lut(port.CLIP_MEAN, port.CLIP_STD, "cpu").view(3, 256)
+    got = torch.stack([lut[c][frames[..., c].long()] for c in range(3)], dim=1)  # [B,C,T,H,W]
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))

@@ -5,6 +5,8 @@ import math
 import pytest
 import torch
 
+from oracle import port
+
 pytestmark = pytest.mark.gpu
 bf16 = torch.bfloat16
 
@@ -376,3 +378,16 @@ def test_gemm_row_remap_and_broadcast_residual(cuda):
     ref = (a.float() @ w.float().t()).view(B, Q, N) + pos[:Q].float()[None]
     assert _rel(out.view(B, S, N)[:, :Q], ref) < 1e-2
     assert out.view(B, S, N)[:, Q:].abs().sum() == 0
+
+
+@pytest.mark.parametrize("B,T,H,W,C", [(2, 3, 32, 24, 3), (1, 8, 224, 224, 3), (3, 2, 16, 8, 1), (2, 2, 8, 16, 4)])
+def test_clip_normalize_bit_exact(cuda, B, T, H, W, C):
+    """uint8 clips -> normalised bf16 model input: bit-exact against the reference's ClipToTensor + Normalize."""
+    from ymp import ops
+    g = torch.Generator().manual_seed(9)
+    frames = torch.randint(0, 256, (B, T, H, W, C), generator=g, dtype=torch.uint8)
+    mean, std = (port.CLIP_MEAN + [0.5])[:C], (port.CLIP_STD + [0.25])[:C]
+    ref = port.clip_to_model_input(frames, mean, std)
+    out = ops.clip_normalize(frames.to(cuda), mean, std)
+    assert out.shape == ref.shape and out.dtype == torch.bfloat16
+    assert torch.equal(out.cpu().view(torch.int16), ref.view(torch.int16))

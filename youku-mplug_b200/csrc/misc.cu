@@ -261,6 +261,43 @@ __global__ void __launch_bounds__(256) group_bcast_kernel(const __nv_bfloat16* _
   }
 }
 
+
+// ------------------------------------------------------------------------------ clip -> model input
+// uint8 [B,T,H,W,C] -> bf16 [B,C,T,H,W] through a per-channel 256-entry table (see include/ymp.h).
+// One thread = 8 consecutive pixels of one frame: 8*C contiguous input bytes, one 16-byte store per channel
+// plane.  HBM-bound: 1 byte read + 2 bytes written per value.
+template <int CH>
+__global__ void __launch_bounds__(256) clip_normalize_kernel(const uint8_t* __restrict__ frames, __nv_bfloat16* __restrict__ out,
+                                                            const __nv_bfloat16* __restrict__ lut, int B, int T, long HW) {
+  __shared__ uint16_t tab[CH * 256];
+  for (int i = threadIdx.x; i < CH * 256; i += blockDim.x) tab[i] = reinterpret_cast<const uint16_t*>(lut)[i];
+  __syncthreads();
+  const long groups_per_frame = HW >> 3;
+  const long total = (long)B * T * groups_per_frame;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const long frame = g / groups_per_frame, pg = g - frame * groups_per_frame;  // frame = b*T + t
+    const long b = frame / T, t = frame - b * T;
+    const uint8_t* src = frames + (frame * HW + pg * 8) * CH;
+    uint8_t px[8 * CH];
+    if constexpr ((8 * CH) % 8 == 0) {
+#pragma unroll
+      for (int i = 0; i < CH; ++i) reinterpret_cast<uint2*>(px)[i] = __ldg(reinterpret_cast<const uint2*>(src) + i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8 * CH; ++i) px[i] = __ldg(src + i);
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        w[i] = (uint32_t)tab[c * 256 + px[(2 * i) * CH + c]] | ((uint32_t)tab[c * 256 + px[(2 * i + 1) * CH + c]] << 16);
+      __nv_bfloat16* dst = out + ((b * CH + c) * T + t) * HW + pg * 8;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
 }  // namespace ymp
 
 using namespace ymp;
@@ -275,6 +312,25 @@ extern "C" int ymp_im2col(const ymp_im2col_args* a, void* stream) {
   const int blocks = (int)min((total + 255) / 256, (long)num_sms() * 16);
   im2col_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a->video, (__nv_bfloat16*)a->out,
                                                            a->B, a->C, a->T, a->H, a->W, a->P, a->ldo);
+  YMP_LAUNCH_CHECK();
+  return YMP_OK;
+}
+
+extern "C" int ymp_clip_normalize(const ymp_clip_args* a, void* stream) {
+  YMP_CHECK_ARG(a && a->frames && a->out && a->lut, "ymp_clip_normalize: null pointer");
+  YMP_CHECK_ARG(a->C == 1 || a->C == 3 || a->C == 4, "ymp_clip_normalize: C must be 1, 3 or 4 (got %d)", a->C);
+  const long HW = (long)a->H * a->W;
+  YMP_CHECK_ARG(a->B > 0 && a->T > 0 && HW > 0 && HW % 8 == 0, "ymp_clip_normalize: H*W must be a positive multiple of 8");
+  YMP_CHECK_ARG((reinterpret_cast<uintptr_t>(a->frames) & 7) == 0 && aligned16(a->out), "ymp_clip_normalize: alignment");
+  const long total = (long)a->B * a->T * (HW / 8);
+  const int blocks = (int)min((total + 255) / 256, (long)num_sms() * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint8_t* f = (const uint8_t*)a->frames;
+  __nv_bfloat16* o = (__nv_bfloat16*)a->out;
+  const __nv_bfloat16* l = (const __nv_bfloat16*)a->lut;
+  if (a->C == 3) clip_normalize_kernel<3><<<blocks, 256, 0, st>>>(f, o, l, a->B, a->T, HW);
+  else if (a->C == 4) clip_normalize_kernel<4><<<blocks, 256, 0, st>>>(f, o, l, a->B, a->T, HW);
+  else clip_normalize_kernel<1><<<blocks, 256, 0, st>>>(f, o, l, a->B, a->T, HW);
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }

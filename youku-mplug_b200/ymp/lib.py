@@ -94,6 +94,11 @@ class Im2colArgs(C.Structure):
                 ("W", c_i32), ("P", c_i32), ("ldo", c_i32)]
 
 
+class ClipArgs(C.Structure):
+    _fields_ = [("frames", c_vp), ("out", c_vp), ("lut", c_vp), ("B", c_i32), ("T", c_i32), ("H", c_i32), ("W", c_i32),
+                ("C", c_i32)]
+
+
 class EmbedArgs(C.Structure):
     _fields_ = [("ids", c_vp), ("table", c_vp), ("pos", c_vp), ("out", c_vp), ("B", c_i32), ("L", c_i32),
                 ("S", c_i32), ("row_offset", c_i32), ("hidden", c_i32), ("vocab", c_i32), ("ldo", c_i32),
@@ -139,6 +144,7 @@ _ln_bwd = _declare("ymp_layernorm_bwd", LayerNormBwdArgs)
 _attn_fwd = _declare("ymp_attn_fwd", AttnArgs)
 _attn_bwd = _declare("ymp_attn_bwd", AttnBwdArgs)
 _im2col = _declare("ymp_im2col", Im2colArgs)
+_clip = _declare("ymp_clip_normalize", ClipArgs)
 _embed = _declare("ymp_embed_gather", EmbedArgs)
 _ce_fwd = _declare("ymp_ce_fwd", CeArgs)
 _ce_bwd = _declare("ymp_ce_bwd", CeArgs)

@@ -212,6 +212,35 @@ def im2col(video, P, out=None):
     return out
 
 
+_CLIP_LUT = {}
+
+
+def clip_lut(mean, std, device):
+    """bf16 table [C*256]: lut[c*256+v] = bf16(((v / 255.) - mean[c]) / std[c]) evaluated with the reference's own
+    fp32 torch ops (ClipToTensor: `clip / 255.`; normalize: `sub_(mean).div_(std)`), hence bit-exact."""
+    key = (tuple(float(m) for m in mean), tuple(float(x) for x in std), str(device))
+    if key not in _CLIP_LUT:
+        v = torch.arange(256, dtype=torch.uint8)[None, :].repeat(len(mean), 1)      # [C, 256] uint8
+        x = v / 255.
+        x.sub_(torch.as_tensor(mean, dtype=x.dtype)[:, None]).div_(torch.as_tensor(std, dtype=x.dtype)[:, None])
+        _CLIP_LUT[key] = x.to(bf16).reshape(-1).contiguous().to(device)
+    return _CLIP_LUT[key]
+
+
+def clip_normalize(frames, mean, std, out=None):
+    """frames uint8 [B,T,H,W,C] (CUDA, contiguous) -> bf16 [B,C,T,H,W] = Normalize(ClipToTensor(frames))."""
+    assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 5 and frames.is_contiguous()
+    B, T, H, W, Cc = frames.shape
+    assert len(mean) == Cc and len(std) == Cc
+    if out is None:
+        out = torch.empty((B, Cc, T, H, W), device=frames.device, dtype=bf16)
+    a = L.ClipArgs()
+    a.frames, a.out, a.lut = frames.data_ptr(), out.data_ptr(), clip_lut(mean, std, frames.device).data_ptr()
+    a.B, a.T, a.H, a.W, a.C = B, T, H, W, Cc
+    L.call(L._clip, a, "ymp_clip_normalize")
+    return out
+
+
 def embed_gather(ids, table, pos, out, S, row_offset):
     """out[(b*S + row_offset + l)] = table[ids[b,l]] + pos[row_offset + l]."""
     assert ids.dtype == torch.int64 and ids.is_contiguous()
