@@ -391,3 +391,18 @@ def test_clip_normalize_bit_exact(cuda, B, T, H, W, C):
     out = ops.clip_normalize(frames.to(cuda), mean, std)
     assert out.shape == ref.shape and out.dtype == torch.bfloat16
     assert torch.equal(out.cpu().view(torch.int16), ref.view(torch.int16))
+
+
+def test_device_prefetcher_orders_copies(cuda):
+    from ymp.data import DevicePrefetcher
+    pf = DevicePrefetcher(cuda)
+    hosts = [torch.full((1 << 20,), float(i)).pin_memory() for i in range(4)]
+    pf.submit(hosts[0], hosts[1])
+    pf.submit(hosts[2], hosts[3])
+    with pytest.raises(RuntimeError):
+        pf.submit(hosts[0])
+    a, b = pf.take()
+    c, d = pf.take()
+    assert len(pf) == 0
+    for t, v in ((a, 0.0), (b, 1.0), (c, 2.0), (d, 3.0)):
+        assert t.is_cuda and float(t.sum()) == v * (1 << 20)
