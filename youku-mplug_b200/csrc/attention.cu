@@ -1,8 +1,12 @@
 // Fused attention (softmax(scale * Q K^T + mask) V) forward and backward.
 //
-// Attention is ~3 % of the path's FLOPs with awkward shapes (head_dim 96,
-// S = 197 / 8 / 1570), so these kernels use warp-level mma.sync (m16n8k16 bf16, fp32 accumulate)
-// flash-style tiles; the score matrix never touches HBM.  The tcgen05 budget is spent on the GEMMs.
+// This file holds the GENERIC kernels: warp-level mma.sync (m16n8k16 bf16, fp32 accumulate) flash-style
+// tiles for any sequence length and head_dim in {64, 80, 96, 128}; the score matrix never touches HBM.
+// ymp_attn_fwd / ymp_attn_bwd (bottom of the file) dispatch first to the specialised kernels -
+// attention_small.cu (block-diagonal sequences of <= 16 rows: TimeSformer temporal attention) and
+// attention_tc.cu (tcgen05, key range <= 256, head_dim 64 / 96: ViT spatial and GPT attention) - and fall
+// back to these for everything else (the abstractor's 1570-key cross attention, head_dim 80 / 128, long
+// decode contexts) or when YMP_ATTN_LEGACY=1.
 //   forward   : CTA = 64 query rows x (seq, head); K/V tiles streamed with cp.async double buffering
 //   backward  : two kernels, no atomics, deterministic -
 //               dQ   kernel: CTA = 64 query rows, streams K/V   (also emits delta = rowsum(dO*O))
