@@ -290,8 +290,17 @@ def run_ymp(args, rank, local_rank, world):
     tf = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     ms_step = ms / args.steps
     step_tf = GF_PER_SAMPLE * (B if (T, L, Q) == (8, 128, 128) else float("nan")) / ms_step  # GFLOP/ms == TFLOP/s
-    roofline = dict(bound="tensor", kernel="gemm_bf16_tcgen05_kernel", achieved=tf, peak=pk["tf_sustained"], unit="TFLOP/s",
-                    frac=tf / pk["tf_sustained"], traffic=None, peak_source=pk["source"] + ", sustained figure",
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tpath) and (B, T, L, Q) == (32, 8, 128, 128):
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        traffic = tj["bytes_per_launch"]
+        traffic_note = ("dram__bytes_read+write per GEMM launch, ncu capture committed in profiles/r01_gemm_traffic.json "
+                        f"(= {tj['measured_over_algorithmic']:.2f} x the algorithmic operand bytes)")
+    roofline = dict(bound="tensor", kernel="gemm_bf16_tcgen05_2cta_kernel", achieved=tf, peak=pk["tf_sustained"], unit="TFLOP/s",
+                    frac=tf / pk["tf_sustained"], traffic=traffic, traffic_note=traffic_note,
+                    peak_source=pk["source"] + ", sustained figure",
                     launches_per_step=len(rec), gemm_ms_per_step=gemm_ms, gemm_share_of_step=gemm_ms / ms_step,
                     note="events around each GEMM launch of one extra untimed step; algorithmic 2MNK per launch")
     value = B * world * args.steps / (ms * 1e-3)
