@@ -113,12 +113,23 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmKParams& p, int row,
   if (p.residual) {
     const int rrow = p.res_row_mod ? row % p.res_row_mod : row;
     if (p.res_f32) {
-      const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + (size_t)rrow * p.ldr + col0);
+      const float* rf = reinterpret_cast<const float*>(p.residual) + (size_t)rrow * p.ldr + col0;
+      if (p.v32_res) {  // one 256-bit load per 32-byte sector (two 128-bit loads would touch every sector twice)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 a = __ldg(rp + j);
-        pf.res[4 * j] = __float_as_uint(a.x); pf.res[4 * j + 1] = __float_as_uint(a.y);
-        pf.res[4 * j + 2] = __float_as_uint(a.z); pf.res[4 * j + 3] = __float_as_uint(a.w);
+        for (int j = 0; j < 4; ++j) {
+          uint32_t a[8];
+          ld_v8(rf + 8 * j, a);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pf.res[8 * j + i] = a[i];
+        }
+      } else {
+        const float4* rp = reinterpret_cast<const float4*>(rf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 a = __ldg(rp + j);
+          pf.res[4 * j] = __float_as_uint(a.x); pf.res[4 * j + 1] = __float_as_uint(a.y);
+          pf.res[4 * j + 2] = __float_as_uint(a.z); pf.res[4 * j + 3] = __float_as_uint(a.w);
+        }
       }
     } else {
       load32_raw(reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)rrow * p.ldr + col0, p.v32_res, pf.res);
