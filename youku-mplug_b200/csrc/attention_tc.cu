@@ -1,16 +1,18 @@
-// tcgen05 attention forward for short key ranges (s_kv <= 256): ViT spatial (197), packed temporal,
-// GPT causal (256).  One CTA = 128 query rows of one (sequence, head):
+// tcgen05 attention for short key ranges (s_kv <= 256, head_dim 64 / 96): ViT spatial (197) and GPT causal (256).
+// Forward, one CTA (256 threads) = 128 query rows of one (sequence, head):
 //   1. cp.async gathers Q [128 x HD], K, V [Nkv x HD] through the seqmap into shared memory laid out
 //      exactly as the UMMA canonical SWIZZLE_128B (first 64 head-dim columns) / SWIZZLE_64B (columns
 //      64..95 when HD = 96) tiles
 //   2. one elected thread issues S[128 x Nkv] = Q K^T  (tcgen05.mma, K-major A and B, fp32 in TMEM)
-//   3. 128 threads (thread = row = TMEM lane) do the exact softmax over the whole row with two passes of
-//      tcgen05.ld, and write P as packed bf16 back into the same TMEM columns (tcgen05.st)
-//   4. O[128 x HD] = P V  with A = P read from TMEM and B = V as an MN-major smem operand
+//   3. two threads per query row (= TMEM lane), one per key-column half, do the exact softmax with two passes
+//      of tcgen05.ld (row maxima / sums exchanged through shared memory) and write P as packed bf16 back into
+//      TMEM columns they have already consumed (tcgen05.st)
+//   4. O[128 x HD] = P V  with A = P read from TMEM and B = V as an MN-major smem operand (two issuer threads
+//      for the 64- and 32-column parts)
 //   5. tcgen05.ld O, scale by 1/l, 16-byte row stores + lse
 // No online-softmax rescaling, no KV loop, no register-resident accumulators.  TMEM use is 256 columns
-// (S/P in [0,256), O aliased onto [128,224) once S is consumed), shared memory ~80-105 KB, so two CTAs
-// share an SM and overlap each other's load / MMA / softmax phases.
+// (S, then P in [0,64) and [128,192), O in [64,128) and [192,224)), shared memory ~80-113 KB, so two CTAs
+// share an SM and overlap each other's load / MMA / softmax phases.  The backward kernel is described below.
 #include <math_constants.h>
 
 #include "common.h"
@@ -136,10 +138,39 @@ __device__ unsigned long long ymp_attn_dbg_buf[256];
 #define TDBG(k)
 #endif
 
+// 256-thread tile loader: thread -> (row = tid/4 of a 64-row pass, 16-byte chunks tid%4 + 4j)
 template <int HD>
-__global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) {
+__device__ __forceinline__ void tc_load256(uint8_t* blk0, uint8_t* blk1, const TcMat& m, int r0, int rows, int n_valid) {
+  constexpr int CPT = HD / 32;
+  const int rl = threadIdx.x >> 2, c0 = threadIdx.x & 3;
+  for (int rb = 0; rb < rows; rb += 64) {
+    const int r = rb + rl;
+    if (r >= rows) break;
+    if (r0 + r < n_valid) {
+      const __nv_bfloat16* g = tc_row(m, r0 + r);
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = c0 + 4 * j;
+        cp16((c < 8) ? blk0 + sw128_off(r, c) : blk1 + sw64_off(r, c - 8), g + c * 8);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = c0 + 4 * j;
+        *reinterpret_cast<uint4*>((c < 8) ? blk0 + sw128_off(r, c) : blk1 + sw64_off(r, c - 8)) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) {
   static_assert(HD == 64 || HD == 96, "head_dim 64 or 96");
   constexpr bool TWO = (HD == 96);
+  // TMEM columns (256 allocated): S in [0, nkv); the two warpgroups own the key-column halves [0,128) / [128,256):
+  // P (bf16 pairs) of half 0 lands in [0,64), of half 1 in [128,192) - always inside columns its own threads
+  // have already consumed; O accumulates in the columns both halves have released: [64,128) (+ [192,224), HD = 96)
+  constexpr uint32_t P1_COL = 128, O0_COL = 64, O1_COL = 192;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -150,13 +181,15 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
   uint8_t* q1s = v0s + kvr * 128;                       // 128 x 64 B   (HD = 96 only)
   uint8_t* k1s = q1s + (TWO ? 128 * 64 : 0);
   uint8_t* v1s = k1s + (TWO ? kvr * 64 : 0);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(v1s + (TWO ? kvr * 64 : 0));  // [2]
+  float* xch = reinterpret_cast<float*>(v1s + (TWO ? kvr * 64 : 0));  // [2][128]: row max, then row sum, per half
+  uint64_t* bar = reinterpret_cast<uint64_t*>(xch + 256);              // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wq = warp & 3, half = warp >> 2;  // TMEM lane quarter (query rows), key-column half
   const int q0 = blockIdx.x * 128, h = blockIdx.y, s = blockIdx.z;
 #ifdef YMP_ATTN_DBG
-#define YMP_DBG_BLOCK (blockIdx.x == 0 && blockIdx.y == 3 && blockIdx.z == 100 && gridDim.z > 100 && blockDim.x == 128)
+#define YMP_DBG_BLOCK (blockIdx.x == 0 && blockIdx.y == 3 && blockIdx.z == 100 && gridDim.z > 100 && blockDim.x == 256 && gridDim.x == 2)
   int dbg_n = 0;
 #endif
   TDBG(0);
@@ -175,16 +208,16 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
   if (warp == 0) tmem_alloc<256>(tmem_ptr);
   if (threadIdx.x == 32) {
     mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    mbar_init(&bar[1], TWO ? 2 : 1);
     fence_mbar_init();
   }
   {
     const TcMat Mq = tc_mat(p.q, p.mq, s, p.ldq, h * p.hsq);
     const TcMat Mk = tc_mat(p.k, p.mkv, s, p.ldk, h * p.hsk);
     const TcMat Mv = tc_mat(p.v, p.mkv, s, p.ldv, h * p.hsv);
-    tc_load<HD>(q0s, q1s, Mq, q0, 128, sq);
-    tc_load<HD>(k0s, k1s, Mk, 0, nkv, kv_end);
-    tc_load<HD>(v0s, v1s, Mv, 0, nkv, kv_end);
+    tc_load256<HD>(q0s, q1s, Mq, q0, 128, sq);
+    tc_load256<HD>(k0s, k1s, Mk, 0, nkv, kv_end);
+    tc_load256<HD>(v0s, v1s, Mv, 0, nkv, kv_end);
   }
   TDBG(1);
   asm volatile("cp.async.wait_all;" ::: "memory");
@@ -217,16 +250,18 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
   tc_fence_after();
   TDBG(4);
 
-  // ---- exact softmax: thread = query row = TMEM lane
-  const int row = q0 + warp * 32 + lane;
-  const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+  // ---- exact softmax: two threads per query row (= TMEM lane), one per key-column half
+  const int rl = wq * 32 + lane;  // row inside the tile
+  const int row = q0 + rl;
+  const uint32_t tl = tmem + ((uint32_t)(wq * 32) << 16);
   // valid key columns of this row form one interval [lo, hi): bounds + causal + block-diagonal masks
   int lo = 0, hi = kv_end;
   if (p.mask == TC_MASK_CAUSAL) hi = min(hi, row + 1);
   if (p.mask == TC_MASK_BLOCK) { lo = (row / p.mask_block) * p.mask_block; hi = min(hi, lo + p.mask_block); }
-  float mx = -CUDART_INF_F;
   const int nch = nkv / 32;
-  for (int c = 0; c < nch; ++c) {
+  const int c_lo = half * 4, c_hi = min(nch, half * 4 + 4);  // this thread's 32-column chunks
+  float mx = -CUDART_INF_F;
+  for (int c = c_lo; c < c_hi; ++c) {
     // tcgen05.ld is .sync.aligned: the skip decision must be warp-uniform
     if (__all_sync(0xffffffffu, c * 32 >= hi || c * 32 + 32 <= lo)) continue;
     uint32_t r[32];
@@ -243,10 +278,14 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
       }
     }
   }
+  xch[half * 128 + rl] = mx;
+  __syncthreads();
+  mx = fmaxf(mx, xch[(half ^ 1) * 128 + rl]);
+  __syncthreads();  // both halves have read the maxima: the buffer is reused for the sums
   TDBG(5);
   const float ms = (mx == -CUDART_INF_F) ? 0.f : mx * p.scale_log2;
   float lsum = 0.f;
-  for (int c = 0; c < nch; ++c) {
+  for (int c = c_lo; c < c_hi; ++c) {
     uint32_t pk[16];
     if (__all_sync(0xffffffffu, c * 32 >= hi || c * 32 + 32 <= lo)) {   // warp-uniform
 #pragma unroll
@@ -271,25 +310,29 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
 #pragma unroll
       for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
     }
-    tmem_st16(tl + c * 16, pk);  // P (bf16 pairs) overwrites S columns that are already consumed
+    // P (bf16 pairs) overwrites S columns this thread has already consumed
+    tmem_st16(tl + half * P1_COL + (c - c_lo) * 16, pk);
   }
+  xch[half * 128 + rl] = lsum;
   TDBG(6);
   tmem_st_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  lsum += xch[(half ^ 1) * 128 + rl];
   TDBG(7);
 
-  // ---- O = P V   (A = P from TMEM, B = V MN-major)
-  constexpr uint32_t O_COL = 128;
-  if (threadIdx.x == 0) {
-    const uint32_t id64 = make_idesc_bf16(128, 64, 0, 1);
-    const uint32_t id32 = make_idesc_bf16(128, 32, 0, 1);
+  // ---- O = P V   (A = P from TMEM, B = V MN-major): thread 0 issues the 64-column part, thread 32 the rest
+  if (threadIdx.x == 0 || (TWO && threadIdx.x == 32)) {
+    const bool second = threadIdx.x == 32;
+    const uint32_t idesc = second ? make_idesc_bf16(128, 32, 0, 1) : make_idesc_bf16(128, 64, 0, 1);
+    const uint32_t ocol = tmem + (second ? O1_COL : O0_COL);
+    const uint32_t vb = smem_u32(second ? v1s : v0s);
     const int nks = nkv / 16;
     for (int ks = 0; ks < nks; ++ks) {
-      umma_ts(tmem + O_COL, tmem + ks * 8, desc_sw(smem_u32(v0s) + ks * 2048, 1024, LAYOUT_SW128), id64, ks > 0 ? 1u : 0u);
-      if (TWO)
-        umma_ts(tmem + O_COL + 64, tmem + ks * 8, desc_sw(smem_u32(v1s) + ks * 1024, 512, LAYOUT_SW64), id32, ks > 0 ? 1u : 0u);
+      const uint32_t acol = tmem + (ks < 8 ? ks * 8 : P1_COL + (ks - 8) * 8);  // 16 keys = 8 packed columns
+      umma_ts(ocol, acol, second ? desc_sw(vb + ks * 1024, 512, LAYOUT_SW64) : desc_sw(vb + ks * 2048, 1024, LAYOUT_SW128), idesc,
+              ks > 0 ? 1u : 0u);
     }
     umma_commit(&bar[1]);
   }
@@ -298,7 +341,7 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
   tc_fence_after();
   TDBG(9);
 
-  // ---- epilogue
+  // ---- epilogue: 32-column chunk c of O is read by warpgroup c & 1
   const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
   const bool valid = row < sq;
   __nv_bfloat16* orow = nullptr;
@@ -308,8 +351,9 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
   }
 #pragma unroll
   for (int c = 0; c < HD / 32; ++c) {
+    if ((c & 1) != half) continue;
     uint32_t r[32];
-    tmem_ld32(tl + O_COL + c * 32, r);
+    tmem_ld32(tl + (c < 2 ? O0_COL + c * 32 : O1_COL), r);
     tmem_ld_wait();
     if (valid) {
 #pragma unroll
@@ -323,7 +367,7 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const AttnTcParams p) 
       }
     }
   }
-  if (valid && p.lse) p.lse[((size_t)s * p.n_heads + h) * p.s_q + row] = mx * p.scale + logf(lsum);
+  if (valid && half == 0 && p.lse) p.lse[((size_t)s * p.n_heads + h) * p.s_q + row] = mx * p.scale + logf(lsum);
   TDBG(10);
   tc_fence_before();
   __syncthreads();
@@ -377,31 +421,6 @@ __device__ __forceinline__ uint64_t desc_sw_lbo(uint32_t saddr, uint32_t lbo, ui
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)layout << 61;
   return d;
-}
-
-// 256-thread tile loader: thread -> (row = tid/4 of a 64-row pass, 16-byte chunks tid%4 + 4j)
-template <int HD>
-__device__ __forceinline__ void tc_load256(uint8_t* blk0, uint8_t* blk1, const TcMat& m, int r0, int rows, int n_valid) {
-  constexpr int CPT = HD / 32;
-  const int rl = threadIdx.x >> 2, c0 = threadIdx.x & 3;
-  for (int rb = 0; rb < rows; rb += 64) {
-    const int r = rb + rl;
-    if (r >= rows) break;
-    if (r0 + r < n_valid) {
-      const __nv_bfloat16* g = tc_row(m, r0 + r);
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const int c = c0 + 4 * j;
-        cp16((c < 8) ? blk0 + sw128_off(r, c) : blk1 + sw64_off(r, c - 8), g + c * 8);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const int c = c0 + 4 * j;
-        *reinterpret_cast<uint4*>((c < 8) ? blk0 + sw128_off(r, c) : blk1 + sw64_off(r, c - 8)) = make_uint4(0, 0, 0, 0);
-      }
-    }
-  }
 }
 
 // Row-staging buffers ([128 rows][HD*2 + 16 B], the pad spreads the banks) make every global access of
@@ -744,11 +763,11 @@ static TcSeqMap tc_map(const ymp_seqmap& m) {
 template <int HD>
 static int launch_tc(const AttnTcParams& p, cudaStream_t st) {
   const int kvr = p.kv_rows;
-  const int smem = 128 * 128 + 2 * kvr * 128 + (HD == 96 ? 128 * 64 + 2 * kvr * 64 : 0) + 64 + 1024;
+  const int smem = 128 * 128 + 2 * kvr * 128 + (HD == 96 ? 128 * 64 + 2 * kvr * 64 : 0) + 1024 + 64 + 1024;
   static int cur = 0;
   if (smem > cur) { YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cur = smem; }
   dim3 grid((p.s_q + 127) / 128, p.n_heads, p.n_seq);
-  attn_tc_fwd_kernel<HD><<<grid, 128, smem, st>>>(p);
+  attn_tc_fwd_kernel<HD><<<grid, 256, smem, st>>>(p);
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }
