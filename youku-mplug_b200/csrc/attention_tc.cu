@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) 
   // TMEM columns (256 allocated): S in [0, nkv); the two warpgroups own the key-column halves [0,128) / [128,256):
   // P (bf16 pairs) of half 0 lands in [0,64), of half 1 in [128,192) - always inside columns its own threads
   // have already consumed; O accumulates in the columns both halves have released: [64,128) (+ [192,224), HD = 96)
-  constexpr uint32_t P1_COL = 128, O0_COL = 64, O1_COL = 192;
+  // (short key ranges, <= 128 columns: the halves split at the middle chunk and O uses [128,224))
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -259,7 +259,10 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) 
   if (p.mask == TC_MASK_CAUSAL) hi = min(hi, row + 1);
   if (p.mask == TC_MASK_BLOCK) { lo = (row / p.mask_block) * p.mask_block; hi = min(hi, lo + p.mask_block); }
   const int nch = nkv / 32;
-  const int c_lo = half * 4, c_hi = min(nch, half * 4 + 4);  // this thread's 32-column chunks
+  const int c1 = nch > 4 ? 4 : (nch + 1) / 2;                  // first chunk of the second half
+  const uint32_t P1_COL = 32 * c1;                              // where the second half's packed P starts
+  const uint32_t O0_COL = nch > 4 ? 64 : 128, O1_COL = 192;
+  const int c_lo = half ? c1 : 0, c_hi = half ? nch : c1;       // this thread's 32-column chunks
   float mx = -CUDART_INF_F;
   for (int c = c_lo; c < c_hi; ++c) {
     // tcgen05.ld is .sync.aligned: the skip decision must be warp-uniform
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) 
     const uint32_t vb = smem_u32(second ? v1s : v0s);
     const int nks = nkv / 16;
     for (int ks = 0; ks < nks; ++ks) {
-      const uint32_t acol = tmem + (ks < 8 ? ks * 8 : P1_COL + (ks - 8) * 8);  // 16 keys = 8 packed columns
+      const uint32_t acol = tmem + (ks < 2 * c1 ? ks * 8 : P1_COL + (ks - 2 * c1) * 8);  // 16 keys = 8 packed columns
       umma_ts(ocol, acol, second ? desc_sw(vb + ks * 1024, 512, LAYOUT_SW64) : desc_sw(vb + ks * 2048, 1024, LAYOUT_SW128), idesc,
               ks > 0 ? 1u : 0u);
     }
