@@ -314,6 +314,9 @@ def run_ymp(args, rank, local_rank, world):
                 config=dict(workload="mPLUG-Video GPT-3 1.3B pretrain step (BASELINE configs[1])", batch_per_gpu=B,
                             global_batch=B * world, frames=T, image=224, text_len=L, queries=Q, parallelism=f"dp{world}",
                             trainable_params=n_train, step="fwd+bwd+allreduce+clip+AdamW, dropout 0", cuda_graph=use_graph,
+                            lm_head_rows="B*L text rows: the B*Q visual-prefix rows have loss_mask 0 in the reference "
+                                         "(distributed_gpt3.py:142-159) and get no final-LN / LM-head / CE work; loss and all "
+                                         "gradients are unchanged, algorithmic FLOPs still count them",
                             l2="per-step working set (~30 GB of activations) >> 126 MB L2; no explicit flush"),
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=dict(value=e2e_val, unit="samples/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
