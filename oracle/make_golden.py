@@ -204,15 +204,124 @@ def run_generate(name, vcfg, gcfg, Q, B, L, wseed, iseed, beam_size=3, n_new=6, 
     print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
 
 
+def run_downstream(name, vcfg, gcfg, Q, wseed):
+    """Golden vectors for the downstream task models: the UNMODIFIED reference's
+    DistributedGPT3_Cls (train + eval, use_cls), _Caption (forward), _Retrieval (features + loss) and
+    _Retrieval_Cls (train + eval) on CPU next to the oracle's compositions (oracle/port.py)."""
+    import torch.distributed as dist
+    if not dist.is_initialized():  # the retrieval model all-gathers its features (world size 1 here)
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1)
+    ref_vcfg = dict(vcfg, drop_path=0, use_abs_pos_emb=True)
+    H, D = gcfg["hidden_size"], vcfg["embed_dim"]
+    g = torch.Generator().manual_seed(wseed + 1)
+
+    def sd_with(extra):
+        sd = port.init_state_dict(vcfg, gcfg, Q, seed=wseed, randomize=True)
+        for k, shape in extra.items():
+            sd[k] = 0.05 * torch.randn(shape, generator=g)
+        return sd
+
+    def load(cls_name, sd, **cfg):
+        model, G = ref_shims.build_reference_model(cls_name, ref_vcfg, gcfg, Q, **cfg)
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not unexpected and not missing, (cls_name, missing, unexpected)
+        return model, G
+
+    def chk(a, b, what, tol=2e-4):
+        err = (a.float() - b.float()).abs().max().item()
+        scale = b.float().abs().max().item() + 1e-12
+        assert err <= tol * scale + 1e-6, f"{name}: port != reference for {what}: {err} (scale {scale})"
+
+    fix = dict(name=name, vcfg=vcfg, gcfg=gcfg, Q=Q, wseed=wseed, torch_version=torch.__version__)
+    B, L, ncls = 2, 8, 3
+    head = {"cls_head.0.weight": (H, H), "cls_head.0.bias": (H,), "cls_head.2.weight": (5, H), "cls_head.2.bias": (5,)}
+    with torch.no_grad():
+        # ---------------- DistributedGPT3_Cls
+        sd = sd_with(head)
+        model, G = load("DistributedGPT3_Cls", sd, use_cls=True, num_classes=5)
+        video, ids, att = make_inputs(B, vcfg, L, gcfg["vocab_size"], 31)
+        _, pids, patt = make_inputs(B, vcfg, L, gcfg["vocab_size"], 32)
+        pl, labels = torch.tensor([2, 3]), torch.tensor([1, 4])
+        enc = lambda **kw: G.BatchEncoding(dict(kw))  # noqa: E731
+        lc, lk = model(video, enc(input_ids=ids, attention_mask=att, prompt_lengths=pl), enc(input_ids=pids, attention_mask=patt),
+                       labels, train=True)
+        qf = port.visual_prefix(video, sd, vcfg)[3]
+        plc, plk = port.cls_train_losses(qf, ids, att, pl, pids, patt, labels, sd, gcfg)
+        chk(plc, lc, "cls train loss_caption", 1e-5)
+        chk(plk, lk, "cls train loss_cls", 1e-5)
+        _, cids, catt = make_inputs(B * ncls, vcfg, L, gcfg["vocab_size"], 33)
+        cpl = torch.randint(1, 4, (B * ncls,), generator=torch.Generator().manual_seed(5))
+        gen, clsl = model(video, enc(input_ids=cids, attention_mask=catt, prompt_lengths=cpl), enc(input_ids=pids, attention_mask=patt),
+                          train=False)
+        chk(port.cls_eval_scores(qf, cids, catt, cpl, sd, gcfg, ncls), gen, "cls eval generation_logits")
+        chk(port.cls_head(port.prompt_pooled_hidden(qf, pids, patt, sd, gcfg), sd), clsl, "cls eval cls_logits")
+        fix["cls"] = dict(seeds=(31, 32, 33), prompt_lengths=pl, labels=labels, eval_prompt_lengths=cpl, ncls=ncls,
+                          head={k: sd[k] for k in head}, loss_caption=lc, loss_cls=lk, eval_generation=gen, eval_cls_logits=clsl)
+        del model
+        # ---------------- DistributedGPT3_Caption
+        sd = sd_with({})
+        model, G = load("DistributedGPT3_Caption", sd)
+        loss = model(video, G.BatchEncoding(dict(input_ids=ids, attention_mask=att, prompt_lengths=pl)))
+        chk(port.prefix_decoder_pass(qf, ids, att, pl, sd, gcfg)["loss"], loss, "caption loss", 1e-5)
+        fix["caption"] = dict(seed=31, prompt_lengths=pl, loss=loss)
+        del model
+        # ---------------- DistributedGPT3_Retrieval
+        proj = {"vision_proj.weight": (32, D), "vision_proj.bias": (32,), "text_proj.weight": (32, H), "text_proj.bias": (32,)}
+        sd = sd_with(proj)
+        sd["temp"] = torch.tensor(0.07)
+        model, G = load("DistributedGPT3_Retrieval", sd, contrastive_embed_dim=32)
+        video3, ids3, att3 = make_inputs(3, vcfg, L, gcfg["vocab_size"], 41)
+        idx = torch.tensor([7, 9, 7])
+        text3 = G.BatchEncoding(dict(input_ids=ids3, attention_mask=att3))
+        rv, rt = model.extract_vision_feature(video3), model.extract_text_feature(text3)
+        rloss = model(video3, text3, idx)
+        pv, pt = port.retrieval_features(video3, ids3, att3, sd, vcfg, gcfg)
+        chk(pv, rv, "retrieval vision feature")
+        chk(pt, rt, "retrieval text feature")
+        chk(port.retrieval_loss(pv, pt, idx, 0.07), rloss, "retrieval loss", 1e-5)
+        fix["retrieval"] = dict(seed=41, idx=idx, proj={k: sd[k] for k in proj}, vision_feats=rv, text_feats=rt, loss=rloss)
+        del model
+        # ---------------- DistributedGPT3_Retrieval_Cls
+        head2 = {"cls_head.0.weight": (H, H), "cls_head.0.bias": (H,), "cls_head.2.weight": (2, H), "cls_head.2.bias": (2,)}
+        sd = sd_with(head2)
+        model, G = load("DistributedGPT3_Retrieval_Cls", sd, use_cls=True, num_classes=2)
+        videoB, _, _ = make_inputs(B, vcfg, L, gcfg["vocab_size"], 51)
+        _, ids4, att4 = make_inputs(2 * B, vcfg, L, gcfg["vocab_size"], 52)       # positives then negatives
+        pl4, neg, lab4 = torch.tensor([2, 2, 3, 1]), torch.tensor([1, 0]), torch.tensor([1, 1, 0, 0])
+        text4 = G.BatchEncoding(dict(input_ids=ids4, attention_mask=att4, prompt_lengths=pl4))
+        prompt4 = G.BatchEncoding(dict(input_ids=ids4, attention_mask=att4))
+        lc4, lk4 = model(videoB, text4, prompt4, neg, lab4, train=True)
+        qfB = port.visual_prefix(videoB, sd, vcfg)[3]
+        p_lc4, p_lk4 = port.retrieval_cls_train_losses(qfB, neg, ids4, att4, pl4, ids4, att4, lab4, sd, gcfg)
+        chk(p_lc4, lc4, "retrieval_cls train loss_caption", 1e-5)
+        chk(p_lk4, lk4, "retrieval_cls train loss_cls", 1e-5)
+        gen4, cls4 = model(videoB, text4, prompt4, train=False)
+        p_gen4, p_cls4 = port.retrieval_cls_eval(qfB, ids4, att4, pl4, ids4, att4, sd, gcfg)
+        chk(p_gen4, gen4, "retrieval_cls eval generation_logits")
+        chk(p_cls4, cls4, "retrieval_cls eval cls_logits")
+        fix["retrieval_cls"] = dict(seeds=(51, 52), prompt_lengths=pl4, negative_indices=neg, labels=lab4, head={k: sd[k] for k in head2},
+                                    loss_caption=lc4, loss_cls=lk4, eval_generation=gen4, eval_cls=cls4)
+        del model
+    print(f"[{name}] port == reference for Cls (train/eval), Caption, Retrieval (features/loss), Retrieval_Cls (train/eval)", flush=True)
+    path = os.path.join(GOLD, name + ".pt")
+    torch.save(fix, path)
+    print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also the real 1.3B / T=8 / B=1 config (~6 GB RAM, minutes)")
     ap.add_argument("--only-generate", action="store_true", help="only (re)write the generation fixture")
+    ap.add_argument("--only-downstream", action="store_true", help="only (re)write the downstream-model fixture")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
+    if a.only_downstream:
+        run_downstream("tiny_downstream", port.VCFG_TINY, port.GCFG_TINY, Q=8, wseed=21)
+        sys.exit(0)
     run_generate("tiny_generate", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=2, L=8, wseed=51, iseed=52)
     if a.only_generate:
         sys.exit(0)
+    run_downstream("tiny_downstream", port.VCFG_TINY, port.GCFG_TINY, Q=8, wseed=21)
     run("tiny_pretrain", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=2, L=8, wseed=11, iseed=12, randomize=True)
     run("tiny_pretrain_refinit", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=1, L=6, wseed=13, iseed=14, randomize=False)
     if a.full:

@@ -372,6 +372,47 @@ def cls_eval_scores(query_features, input_ids, attention_mask, prompt_lengths, s
     return (-(out["losses"] * out["loss_mask"]).sum(-1)).view(B, num_cls).softmax(-1)
 
 
+def cls_head(x, sd):
+    """nn.Sequential(Linear, ReLU, Linear) head of the Cls / Retrieval_Cls models (models/distributed_gpt3.py:523-529)."""
+    return F.linear(torch.relu(F.linear(x, sd["cls_head.0.weight"], sd["cls_head.0.bias"])), sd["cls_head.2.weight"], sd["cls_head.2.bias"])
+
+
+def prompt_pooled_hidden(query_features, prompt_ids, prompt_att, sd, gcfg):
+    """Hidden state of the last attended prompt token after a [prefix | prompt] decoder pass
+    (models/distributed_gpt3.py:569-588): position Q + attention_mask.sum(-1) - 1."""
+    Q = query_features.shape[1]
+    hidden = prefix_decoder_pass(query_features, prompt_ids, prompt_att, None, sd, gcfg)["hidden"]
+    return hidden[torch.arange(hidden.shape[0]), Q + prompt_att.sum(-1) - 1]
+
+
+def cls_train_losses(query_features, input_ids, attention_mask, prompt_lengths, prompt_ids, prompt_att, labels, sd, gcfg):
+    """DistributedGPT3_Cls.forward(train=True, use_cls=True) - models/distributed_gpt3.py:540-592:
+    (caption-style loss with the prompt masked out, CE of cls_head on the prompt pass)."""
+    loss_caption = prefix_decoder_pass(query_features, input_ids, attention_mask, prompt_lengths, sd, gcfg)["loss"]
+    logits = cls_head(prompt_pooled_hidden(query_features, prompt_ids, prompt_att, sd, gcfg), sd)
+    return loss_caption, F.cross_entropy(logits, labels)
+
+
+def retrieval_cls_train_losses(query_features, negative_indices, input_ids, attention_mask, prompt_lengths, prompt_ids, prompt_att,
+                               labels, sd, gcfg):
+    """DistributedGPT3_Retrieval_Cls.forward(train=True) - models/distributed_gpt3.py:1105-1157: the prefix of every video
+    followed by the prefixes of its negatives (query_features[negative_indices])."""
+    qf = torch.cat([query_features, query_features[negative_indices]], dim=0)
+    return cls_train_losses(qf, input_ids, attention_mask, prompt_lengths, prompt_ids, prompt_att, labels, sd, gcfg)
+
+
+def retrieval_cls_eval(query_features, input_ids, attention_mask, prompt_lengths, prompt_ids, prompt_att, sd, gcfg):
+    """DistributedGPT3_Retrieval_Cls.forward(train=False) - :1159-1213: every video against t texts;
+    (-(losses * mask).sum [v, t], softmax(cls_head)[:, 1] [v, t])."""
+    v = query_features.shape[0]
+    t = input_ids.shape[0] // v
+    qf = query_features.repeat_interleave(t, dim=0)
+    out = prefix_decoder_pass(qf, input_ids, attention_mask, prompt_lengths, sd, gcfg)
+    gen = (-(out["losses"] * out["loss_mask"]).sum(-1)).view(v, t)
+    cls = torch.softmax(cls_head(prompt_pooled_hidden(qf, prompt_ids, prompt_att, sd, gcfg), sd), dim=-1)[:, 1].view(v, t)
+    return gen, cls
+
+
 def retrieval_features(video, input_ids, attention_mask, sd, vcfg, gcfg):
     """DistributedGPT3_Retrieval.extract_{vision,text}_feature - models/distributed_gpt3.py:909-945:
     CLS-pooled ViT feature -> vision_proj -> L2 ; GPT hidden at the last valid token -> text_proj -> L2."""

@@ -207,8 +207,9 @@ def import_reference():
     return V, G, D
 
 
-def build_reference_pretrain(visual_cfg, gpt_cfg, num_learnable_token, seed=0, use_contrastive=False):
-    """Instantiate the reference's DistributedGPT3_Pretrain on CPU (fp32, eval, dropout 0)."""
+def build_reference_model(cls_name, visual_cfg, gpt_cfg, num_learnable_token, seed=0, **config_extra):
+    """Instantiate one of the reference's task models (models/distributed_gpt3.py: DistributedGPT3_Pretrain / _Cls /
+    _Caption / _Retrieval / _Retrieval_Cls) on CPU (fp32, eval, dropout 0)."""
     V, G, D = import_reference()
     td = tempfile.mkdtemp(prefix="ymp_ref_")
     gpt_cfg = dict(gpt_cfg, hidden_dropout=0.0, attention_dropout=0.0)
@@ -219,7 +220,14 @@ def build_reference_pretrain(visual_cfg, gpt_cfg, num_learnable_token, seed=0, u
         json.dump(vis, f)
     config = dict(visual_cfg=os.path.join(td, "vis.json"), text_cfg=os.path.join(td, "config.json"),
                   text_decoder=td, megatron_cfg={}, num_learnable_token=num_learnable_token,
-                  use_contrastive=use_contrastive, freeze_text_decoder=True)
+                  use_contrastive=False, freeze_text_decoder=True, num_frames=visual_cfg["num_frames"])
+    config.update(config_extra)
     torch.manual_seed(seed)
-    model = D.DistributedGPT3_Pretrain(config=config, tokenizer=None).eval()
+    model = getattr(D, cls_name)(config=config, tokenizer=None).eval()
     return model, G
+
+
+def build_reference_pretrain(visual_cfg, gpt_cfg, num_learnable_token, seed=0, use_contrastive=False):
+    """Instantiate the reference's DistributedGPT3_Pretrain on CPU (fp32, eval, dropout 0)."""
+    return build_reference_model("DistributedGPT3_Pretrain", visual_cfg, gpt_cfg, num_learnable_token, seed=seed,
+                                 use_contrastive=use_contrastive)

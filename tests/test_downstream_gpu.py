@@ -110,3 +110,55 @@ def test_retrieval_cls_shapes_and_negatives(cuda):
     ref_eval = port.prefix_decoder_pass(qf.repeat_interleave(2, 0), ids, att, pl, rsd, GC)
     ref_gen = (-(ref_eval["losses"] * ref_eval["loss_mask"]).sum(-1)).view(B, 2)
     assert _rel(gen, ref_gen) < 2e-2
+
+
+def test_downstream_models_match_reference_fixture(cuda):
+    """The four downstream task models on the B200 kernels against the UNMODIFIED reference's outputs
+    (tests/golden/tiny_downstream.pt: same seeded weights and inputs, reference run in fp32 on CPU)."""
+    import os
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_downstream.pt"), weights_only=False)
+    assert fx["Q"] == Q and fx["vcfg"] == VC and fx["gcfg"] == GC
+    V = GC["vocab_size"]
+
+    def model(cls_name, extra, **cfg):
+        sd = port.init_state_dict(VC, GC, Q, seed=fx["wseed"], randomize=True)
+        sd.update(extra)
+        return build_pretrain(VC, GC, Q, sd=sd, device=cuda, dtype=torch.bfloat16, cls_name=cls_name, num_frames=VC["num_frames"], **cfg)
+
+    def close(a, b, tol):
+        b = torch.as_tensor(b)
+        return ((a.detach().float().cpu() - b.float()).abs().max() <= tol * (b.float().abs().max() + 1e-12)).item()
+
+    with torch.no_grad():
+        c = fx["cls"]
+        m = model("DistributedGPT3_Cls", c["head"], use_cls=True, num_classes=5)
+        video, ids, att = make_inputs(2, VC, 8, V, c["seeds"][0])
+        _, pids, patt = make_inputs(2, VC, 8, V, c["seeds"][1])
+        vd = video.to(cuda).bfloat16()
+        lc, lk = m(vd, _enc(cuda, input_ids=ids, attention_mask=att, prompt_lengths=c["prompt_lengths"]),
+                   _enc(cuda, input_ids=pids, attention_mask=patt), c["labels"].to(cuda), train=True)
+        assert close(lc, c["loss_caption"], 1e-2) and close(lk, c["loss_cls"], 3e-2)
+        _, cids, catt = make_inputs(2 * c["ncls"], VC, 8, V, c["seeds"][2])
+        gen, cl = m(vd, _enc(cuda, input_ids=cids, attention_mask=catt, prompt_lengths=c["eval_prompt_lengths"]),
+                    _enc(cuda, input_ids=pids, attention_mask=patt), train=False)
+        assert close(gen, c["eval_generation"], 3e-2) and close(cl, c["eval_cls_logits"], 3e-2)
+        m = model("DistributedGPT3_Caption", {})
+        loss = m(vd, _enc(cuda, input_ids=ids, attention_mask=att, prompt_lengths=fx["caption"]["prompt_lengths"]))
+        assert close(loss, fx["caption"]["loss"], 1e-2)
+        r = fx["retrieval"]
+        m = model("DistributedGPT3_Retrieval", dict(r["proj"], temp=torch.tensor(0.07)), contrastive_embed_dim=32)
+        video3, ids3, att3 = make_inputs(3, VC, 8, V, r["seed"])
+        text3 = _enc(cuda, input_ids=ids3, attention_mask=att3)
+        assert close(m.extract_vision_feature(video3.to(cuda).bfloat16()), r["vision_feats"], 2e-2)
+        assert close(m.extract_text_feature(text3), r["text_feats"], 2e-2)
+        assert close(m(video3.to(cuda).bfloat16(), text3, r["idx"].to(cuda)), r["loss"], 3e-2)
+        rc = fx["retrieval_cls"]
+        m = model("DistributedGPT3_Retrieval_Cls", rc["head"], use_cls=True, num_classes=2)
+        videoB, _, _ = make_inputs(2, VC, 8, V, rc["seeds"][0])
+        _, ids4, att4 = make_inputs(4, VC, 8, V, rc["seeds"][1])
+        text4 = _enc(cuda, input_ids=ids4, attention_mask=att4, prompt_lengths=rc["prompt_lengths"])
+        prompt4 = _enc(cuda, input_ids=ids4, attention_mask=att4)
+        lc4, lk4 = m(videoB.to(cuda).bfloat16(), text4, prompt4, rc["negative_indices"].to(cuda), rc["labels"].to(cuda), train=True)
+        assert close(lc4, rc["loss_caption"], 1e-2) and close(lk4, rc["loss_cls"], 3e-2)
+        gen4, cls4 = m(videoB.to(cuda).bfloat16(), text4, prompt4, train=False)
+        assert close(gen4, rc["eval_generation"], 2e-2) and close(cls4, rc["eval_cls"], 3e-2)
