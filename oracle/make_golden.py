@@ -302,7 +302,17 @@ def run_downstream(name, vcfg, gcfg, Q, wseed):
         fix["retrieval_cls"] = dict(seeds=(51, 52), prompt_lengths=pl4, negative_indices=neg, labels=lab4, head={k: sd[k] for k in head2},
                                     loss_caption=lc4, loss_cls=lk4, eval_generation=gen4, eval_cls=cls4)
         del model
-    print(f"[{name}] port == reference for Cls (train/eval), Caption, Retrieval (features/loss), Retrieval_Cls (train/eval)", flush=True)
+        # ---------------- DistributedGPT3_Pretrain with the contrastive branch
+        sd = sd_with(proj)
+        sd["temp"] = torch.tensor(0.07)
+        model, G = load("DistributedGPT3_Pretrain", sd, use_contrastive=True, contrastive_embed_dim=32)
+        lcap, lcon = model(video3, G.BatchEncoding(dict(input_ids=ids3, attention_mask=att3)))
+        chk(port.pretrain_forward(video3, ids3, att3, sd, vcfg, gcfg), lcap, "pretrain(contrastive) loss_caption", 1e-5)
+        chk(port.pretrain_contrastive_loss(video3, ids3, att3, sd, vcfg, gcfg, 0.07), lcon, "pretrain loss_contrastive", 1e-5)
+        fix["pretrain_contrastive"] = dict(seed=41, proj={k: sd[k] for k in proj}, loss_caption=lcap, loss_contrastive=lcon)
+        del model
+    print(f"[{name}] port == reference for Cls (train/eval), Caption, Retrieval (features/loss), Retrieval_Cls (train/eval), "
+          f"Pretrain + contrastive", flush=True)
     path = os.path.join(GOLD, name + ".pt")
     torch.save(fix, path)
     print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)

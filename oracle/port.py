@@ -372,6 +372,22 @@ def cls_eval_scores(query_features, input_ids, attention_mask, prompt_lengths, s
     return (-(out["losses"] * out["loss_mask"]).sum(-1)).view(B, num_cls).softmax(-1)
 
 
+def pretrain_contrastive_loss(video, input_ids, attention_mask, sd, vcfg, gcfg, temp):
+    """Contrastive branch of DistributedGPT3_Pretrain.forward (use_contrastive=True) - models/distributed_gpt3.py:168-217,
+    single process: query-token features [B,Q,E] against the text feature of a text-only decoder pass [B,E],
+    similarity = max over the Q queries, label-smoothed (0.1) CE in both directions with targets arange(B)."""
+    _, _, image_query, _ = visual_prefix(video, sd, vcfg)
+    vfeat = F.normalize(F.linear(image_query, sd["vision_proj.weight"], sd["vision_proj.bias"]), dim=-1)
+    emb_w = sd[GPT_PRE + "embedding.word_embeddings.weight"]
+    hidden = gpt3_decoder(emb_w[input_ids], sd, gcfg)
+    pooled = hidden[torch.arange(hidden.shape[0]), attention_mask.sum(-1) - 1]
+    tfeat = F.normalize(F.linear(pooled, sd["text_proj.weight"], sd["text_proj.bias"]), dim=-1)
+    sim_i2t = torch.einsum("bqe,je->bjq", vfeat, tfeat).max(-1)[0] / temp
+    sim_t2i = torch.einsum("be,jqe->bjq", tfeat, vfeat).max(-1)[0] / temp
+    tgt = torch.arange(video.shape[0])
+    return (F.cross_entropy(sim_i2t, tgt, label_smoothing=0.1) + F.cross_entropy(sim_t2i, tgt, label_smoothing=0.1)) / 2
+
+
 def cls_head(x, sd):
     """nn.Sequential(Linear, ReLU, Linear) head of the Cls / Retrieval_Cls models (models/distributed_gpt3.py:523-529)."""
     return F.linear(torch.relu(F.linear(x, sd["cls_head.0.weight"], sd["cls_head.0.bias"])), sd["cls_head.2.weight"], sd["cls_head.2.bias"])

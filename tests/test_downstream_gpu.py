@@ -162,3 +162,7 @@ def test_downstream_models_match_reference_fixture(cuda):
         assert close(lc4, rc["loss_caption"], 1e-2) and close(lk4, rc["loss_cls"], 3e-2)
         gen4, cls4 = m(videoB.to(cuda).bfloat16(), text4, prompt4, train=False)
         assert close(gen4, rc["eval_generation"], 2e-2) and close(cls4, rc["eval_cls"], 3e-2)
+        pc = fx["pretrain_contrastive"]
+        m = model("DistributedGPT3_Pretrain", dict(pc["proj"], temp=torch.tensor(0.07)), use_contrastive=True, contrastive_embed_dim=32)
+        lcap, lcon = m(video3.to(cuda).bfloat16(), text3)
+        assert close(lcap, pc["loss_caption"], 1e-2) and close(lcon, pc["loss_contrastive"], 3e-2)

@@ -169,12 +169,13 @@ class DistributedGPT3_Pretrain(_PrefixModelBase):
         pooled = outputs_text.last_hidden_state
         pooled = pooled[torch.arange(pooled.shape[0]), text.attention_mask.sum(dim=-1) - 1]
         text_feat = F.normalize(self.text_proj(pooled).float(), dim=-1)
-        vision_feats_all = all_gather_cat(vision_feats)          # [B*W, Q, E]
-        text_feat_all = all_gather_cat(text_feat)                # [B*W, E]
+        dist_on = torch.distributed.is_initialized()
+        vision_feats_all = all_gather_cat(vision_feats) if dist_on else vision_feats   # [B*W, Q, E]
+        text_feat_all = all_gather_cat(text_feat) if dist_on else text_feat            # [B*W, E]
         # sim_q2t[b, j, q] = <vision_feats[b,q], text_all[j]> ; max over queries (:186-202)
         sim_i2t = torch.einsum('bqe,je->bjq', vision_feats, text_feat_all).max(-1)[0] / self.temp
         sim_t2i = torch.einsum('be,jqe->bjq', text_feat, vision_feats_all).max(-1)[0] / self.temp
-        rank = torch.distributed.get_rank()
+        rank = torch.distributed.get_rank() if dist_on else 0
         bs = image.size(0)
         tgt = torch.arange(rank * bs, rank * bs + bs, device=image.device)
         loss_contrastive = (F.cross_entropy(sim_i2t, tgt, label_smoothing=0.1)
