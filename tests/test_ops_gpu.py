@@ -168,6 +168,36 @@ def test_attn_dense_ragged_total_rows(cuda, hd, S, total, causal):
             assert _rel(d[:, i].permute(1, 0, 2)[None], g) < 3e-2, (s, i)
 
 
+@pytest.mark.parametrize("hd,sq,skv", [(64, 70, 200), (96, 256, 33), (96, 129, 256), (64, 128, 128)])
+def test_attn_cross_short_kv(cuda, hd, sq, skv):
+    """Non-causal cross attention with s_q != s_kv inside the tcgen05 kernels' domain (key range <= 256)."""
+    from ymp import ops
+    torch.manual_seed(21)
+    n, heads = 3, 2
+    C = heads * hd
+    qb = (torch.randn(n * sq, C, device=cuda) * 0.7).to(bf16)
+    kvb = (torch.randn(n * skv, 2 * C, device=cuda) * 0.7).to(bf16)
+    out = torch.zeros(n * sq, C, device=cuda, dtype=bf16)
+    mq, mkv = ops.dense_map(sq), ops.dense_map(skv)
+    tq, tk, tv, to = ops.TView(qb, 0, hd, mq), ops.TView(kvb, 0, hd, mkv), ops.TView(kvb, C, hd, mkv), ops.TView(out, 0, hd, mq)
+    kw = dict(n_seq=n, n_heads=heads, head_dim=hd, s_q=sq, s_kv=skv, causal=False, scale=hd ** -0.5)
+    lse = ops.attn_fwd(tq, tk, tv, to, **kw)
+    q = qb.float().view(n, sq, heads, hd).permute(0, 2, 1, 3).contiguous().requires_grad_()
+    kv = kvb.float().view(n, skv, 2, heads, hd)
+    k, v = (kv[:, :, i].permute(0, 2, 1, 3).contiguous().requires_grad_() for i in range(2))
+    ref = _attn_ref(q, k, v, hd ** -0.5, False)
+    assert _rel(out.view(n, sq, heads, hd).permute(0, 2, 1, 3), ref) < 2e-2
+    dout = torch.randn(n * sq, C, device=cuda).to(bf16)
+    ref.backward(dout.float().view(n, sq, heads, hd).permute(0, 2, 1, 3))
+    dqb, dkvb = torch.zeros_like(qb), torch.zeros_like(kvb)
+    ops.attn_bwd(tq, tk, tv, to, lse, ops.TView(dout, 0, hd, mq), ops.TView(dqb, 0, hd, mq), ops.TView(dkvb, 0, hd, mkv),
+                 ops.TView(dkvb, C, hd, mkv), **kw)
+    assert _rel(dqb.view(n, sq, heads, hd).permute(0, 2, 1, 3), q.grad) < 3e-2
+    d = dkvb.float().view(n, skv, 2, heads, hd)
+    assert _rel(d[:, :, 0].permute(0, 2, 1, 3), k.grad) < 3e-2
+    assert _rel(d[:, :, 1].permute(0, 2, 1, 3), v.grad) < 3e-2
+
+
 def test_attn_cross_shared_q(cuda):
     """Abstractor pattern: one shared query block for every sample, long KV with a ragged tail."""
     from ymp import ops
