@@ -173,6 +173,17 @@ def run_generate(name, vcfg, gcfg, Q, B, L, wseed, iseed, beam_size=3, n_new=6, 
         ref_greedy = model.text_decoder.generate(ids.clone(), query_embeds=qf, termination_id=eod, do_sample=True,
                                                  prompt_length=plen.clone())
     del model
+    # the reference's sampling filters on seeded logits (pure torch functions of the reference module)
+    fl = torch.randn(4, 50, generator=torch.Generator().manual_seed(0))
+    a, b = fl.clone(), fl.clone()
+    G.modify_logits_for_top_k_filtering(a, 5)
+    G.modify_logits_for_top_p_filtering(b, 0.7)
+    torch.manual_seed(3)
+    drawn = G.sample(fl, top_k=0, top_p=0.9, temperature=0.7, vocab_size=40)
+    filters = dict(logits=fl, top_k5=a, top_p07=b, sample_seed3_p09_t07_v40=drawn, greedy=G.sample(fl, top_k=1))
+    assert torch.equal(a, port.filter_top_k(fl, 5)) and torch.equal(b, port.filter_top_p(fl, 0.7))
+    torch.manual_seed(3)
+    assert torch.equal(drawn, port.pick_token(fl, top_k=0, top_p=0.9, temperature=0.7, vocab_size=40))
     with torch.no_grad():
         qf_port = port.visual_prefix(video, sd, vcfg)[3]
         assert (qf_port - qf).abs().max() <= 2e-4 * qf.abs().max()
@@ -198,7 +209,7 @@ def run_generate(name, vcfg, gcfg, Q, B, L, wseed, iseed, beam_size=3, n_new=6, 
     fix = dict(name=name, vcfg=vcfg, gcfg=gcfg, Q=Q, B=B, L=L, wseed=wseed, iseed=iseed, beam_size=beam_size, n_new=n_new,
                pos_gain=pos_gain, ln_gain=ln_gain, eod=eod, ids=ids, att=att, prompt_length=plen, video_checksum=float(video.double().abs().sum()),
                query_features=qf.detach(), beam_sequences=[b[0] for b in beams], beam_scores=[b[1] for b in beams], greedy=ref_greedy,
-               steps=steps, torch_version=torch.__version__)
+               steps=steps, filters=filters, torch_version=torch.__version__)
     path = os.path.join(GOLD, name + ".pt")
     torch.save(fix, path)
     print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
