@@ -754,7 +754,8 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
     // 128x256 tile, or 128x128 when even that leaves most SMs idle or N is narrow
     const long t2 = (long)((a->M + 2 * BM - 1) / (2 * BM)) * ((a->N + 255) / 256);
     const long t256 = (long)((a->M + BM - 1) / BM) * ((a->N + 255) / 256);
-    if (a->N >= 256 && a->M >= 256 && (t2 >= sms || (a->accumulate && a->split_k != 1))) bn = 512;
+    // a pair tile occupies two SMs: sms / 2 of them already fill the machine
+    if (a->N >= 256 && a->M >= 256 && (t2 >= sms / 2 || (a->accumulate && a->split_k != 1))) bn = 512;
     else bn = (a->N <= 128 || (t256 < sms && a->split_k <= 1 && !a->accumulate)) ? 128 : 256;
   }
   int split = a->split_k;
