@@ -329,13 +329,91 @@ def run_downstream(name, vcfg, gcfg, Q, wseed):
     print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
 
 
+def run_caption_full(name, vcfg, gcfg, Q, B, L, wseed, iseed, sample_logits=2048):
+    """BASELINE config-4 at its real dims (configs/caption/caption_gpt3_2.7B_youku_v0.yaml:19,30 + BASELINE.json:
+    GPT-3 2.7B = 32 layers x 2560, 32 heads x 80; 16 frames; text 256 -> S = 128 + 256 = 384): the UNMODIFIED
+    reference's DistributedGPT3_Caption.forward + backward (models/distributed_gpt3.py:751-788) on CPU in fp32, the
+    oracle's restatement beside it (asserted equal), and the reference's loss / sampled logits / norms / sampled
+    gradients stored as the fixture."""
+    t0 = time.time()
+    sd = port.init_state_dict(vcfg, gcfg, Q, seed=wseed, randomize=False)
+    ref_vcfg = dict(vcfg, drop_path=0, use_abs_pos_emb=True)
+    model, G = ref_shims.build_reference_model("DistributedGPT3_Caption", ref_vcfg, gcfg, Q)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    video, ids, att = make_inputs(B, vcfg, L, gcfg["vocab_size"], iseed)
+    pl = torch.tensor([5] * B)
+    text = G.BatchEncoding(dict(input_ids=ids, attention_mask=att, prompt_lengths=pl))
+    print(f"[{name}] built in {time.time() - t0:.1f}s; running reference ...", flush=True)
+    inter = {}
+    h1 = model.visual_encoder.register_forward_hook(lambda m, i, o: inter.__setitem__("image_embeds", o[1].detach()))
+    h2 = model.visual_fc.register_forward_hook(lambda m, i, o: inter.__setitem__("query_features", o.detach()))
+    h3 = model.text_decoder.register_forward_hook(lambda m, i, o: inter.__setitem__("gpt", o))
+    t0 = time.time()
+    loss_ref = model(video, text)
+    t_fwd = time.time() - t0
+    t0 = time.time()
+    loss_ref.backward()
+    t_bwd = time.time() - t0
+    for h in (h1, h2, h3):
+        h.remove()
+    out = inter["gpt"]
+    ref_grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    print(f"[{name}] reference loss {loss_ref.item():.6f} fwd {t_fwd:.1f}s bwd {t_bwd:.1f}s", flush=True)
+    lg = out.logits.detach()
+    g = torch.Generator().manual_seed(7)
+    idx = torch.stack([torch.randint(0, n, (sample_logits,), generator=g) for n in lg.shape], dim=1)
+    fix = dict(name=name, vcfg=vcfg, gcfg=gcfg, Q=Q, B=B, L=L, wseed=wseed, iseed=iseed, prompt_lengths=pl,
+               torch_version=torch.__version__,
+               sd_checksum=float(sum(v.double().abs().sum() for v in sd.values())),
+               loss=loss_ref.detach(), losses=out.losses.detach(),
+               logit_idx=idx, logit_vals=lg[idx[:, 0], idx[:, 1], idx[:, 2]].clone(),
+               logits_abs_mean=lg.abs().mean(), logits_absmax=lg.abs().max(),
+               image_embeds_norm=inter["image_embeds"].norm(dim=-1),
+               query_features_norm=inter["query_features"].norm(dim=-1),
+               hidden_norm=out.last_hidden_state.detach().norm(dim=-1),
+               grad_norms={k: v.norm() for k, v in ref_grads.items()},
+               grads={k: sample_grad(ref_grads[k]) for k in GRAD_KEYS if k in ref_grads},
+               ref_fwd_s=t_fwd, ref_bwd_s=t_bwd)
+    del model, lg, inter["gpt"]
+    # ---- the oracle on the same weights / inputs (pins the 2.7B-shape restatement: hd 80, S 384, T 16)
+    train = set(port.trainable_keys(sd))
+    psd = {k: v.clone().requires_grad_(k in train) for k, v in sd.items()}
+    qf = port.visual_prefix(video, psd, vcfg)[3]
+    res = port.prefix_decoder_pass(qf, ids, att, pl, psd, gcfg)
+    res["loss"].backward()
+    worst = 0.0
+
+    def chk(a, b, what, tol=2e-4):
+        err = (a.float() - b.float()).abs().max().item()
+        scale = b.float().abs().max().item() + 1e-12
+        assert err <= tol * scale + 1e-6, f"{name}: port != reference for {what}: {err} (scale {scale})"
+        return err / scale
+
+    worst = max(worst, chk(res["loss"], loss_ref, "loss", 1e-5))
+    worst = max(worst, chk(res["losses"], out.losses, "losses"))
+    worst = max(worst, chk(res["logits"][idx[:, 0], idx[:, 1], idx[:, 2]], fix["logit_vals"], "sampled logits"))
+    for k, gref in ref_grads.items():
+        worst = max(worst, chk(psd[k].grad, gref, "grad " + k, 5e-4))
+    fix["port_vs_ref_worst_rel"] = worst
+    print(f"[{name}] port == reference (worst rel err {worst:.2e}); {len(ref_grads)} grads", flush=True)
+    path = os.path.join(GOLD, name + ".pt")
+    torch.save(fix, path)
+    print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also the real 1.3B / T=8 / B=1 config (~6 GB RAM, minutes)")
+    ap.add_argument("--caption27b", action="store_true", help="only the 2.7B caption config at its real dims (~35 GB RAM, minutes)")
     ap.add_argument("--only-generate", action="store_true", help="only (re)write the generation fixture")
     ap.add_argument("--only-downstream", action="store_true", help="only (re)write the downstream-model fixture")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
+    if a.caption27b:
+        run_caption_full("full_2p7b_caption_T16_B1", dict(port.VCFG_CLIP_B16, num_frames=16), port.GCFG_2_7B, Q=128, B=1, L=256,
+                         wseed=0, iseed=4321)
+        sys.exit(0)
     if a.only_downstream:
         run_downstream("tiny_downstream", port.VCFG_TINY, port.GCFG_TINY, Q=8, wseed=21)
         sys.exit(0)

@@ -325,6 +325,10 @@ VCFG_CLIP_B16 = dict(img_size=224, patch_size=16, embed_dim=768, depth=12, num_h
 GCFG_1_3B = dict(vocab_size=51200, hidden_size=2048, ffn_hidden_size=8192, num_hidden_layers=24,
                  num_attention_heads=32, max_position_embeddings=2048, layernorm_epsilon=1e-5,
                  init_method_std=0.02)
+# configs/models/config_gpt3_2.7B.json (32 layers x 2560, 32 heads x 80: BASELINE config-4)
+GCFG_2_7B = dict(vocab_size=51200, hidden_size=2560, ffn_hidden_size=10240, num_hidden_layers=32,
+                 num_attention_heads=32, max_position_embeddings=2048, layernorm_epsilon=1e-5,
+                 init_method_std=0.02)
 VCFG_TINY = dict(img_size=32, patch_size=16, embed_dim=192, depth=2, num_heads=2, mlp_ratio=4,
                  num_frames=2, clip_model=True)
 GCFG_TINY = dict(vocab_size=512, hidden_size=128, ffn_hidden_size=512, num_hidden_layers=2,

@@ -1,5 +1,7 @@
 """GPU: the downstream task models on the B200 kernels against the
 oracle composed from the same reference-pinned primitives (oracle/port.py)."""
+import os
+
 import pytest
 import torch
 
@@ -9,6 +11,7 @@ from helpers import build_pretrain
 
 pytestmark = pytest.mark.gpu
 VC, GC, Q = port.VCFG_TINY, port.GCFG_TINY, 8
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _rel(a, b):
@@ -166,3 +169,60 @@ def test_downstream_models_match_reference_fixture(cuda):
         m = model("DistributedGPT3_Pretrain", dict(pc["proj"], temp=torch.tensor(0.07)), use_contrastive=True, contrastive_embed_dim=32)
         lcap, lcon = m(video3.to(cuda).bfloat16(), text3)
         assert close(lcap, pc["loss_caption"], 1e-2) and close(lcon, pc["loss_contrastive"], 3e-2)
+
+
+@pytest.mark.skipif(os.environ.get("YMP_SKIP_FULL", "0") == "1", reason="full-size parity disabled")
+def test_full_2p7b_caption_matches_reference_fixture(cuda):
+    """BASELINE config-4 at its real dims (GPT-3 2.7B: 32 layers x 2560, 32 heads x 80; 16 frames; text 256 ->
+    S = 384; B = 1): DistributedGPT3_Caption forward + backward against the UNMODIFIED reference's fp32 outputs
+    (tests/golden/full_2p7b_caption_T16_B1.pt, oracle/make_golden.py --caption27b).  Exercises head_dim 80,
+    key ranges > 256 and T = 16 through the model."""
+    from oracle.make_golden import make_inputs
+    fx = torch.load(os.path.join(GOLD, "full_2p7b_caption_T16_B1.pt"), weights_only=False)
+    torch.set_num_threads(os.cpu_count())
+    sd = port.init_state_dict(fx["vcfg"], fx["gcfg"], fx["Q"], seed=fx["wseed"], randomize=False)
+    cs = float(sum(v.double().abs().sum() for v in sd.values()))
+    assert abs(cs - fx["sd_checksum"]) <= 1e-9 * fx["sd_checksum"]
+    model = build_pretrain(fx["vcfg"], fx["gcfg"], fx["Q"], sd=sd, device=cuda, dtype=torch.bfloat16,
+                           cls_name="DistributedGPT3_Caption", num_frames=fx["vcfg"]["num_frames"])
+    del sd
+    video, ids, att = make_inputs(fx["B"], fx["vcfg"], fx["L"], fx["gcfg"]["vocab_size"], fx["iseed"])
+    v = video.to(cuda).bfloat16()
+    import models.modeling_distributed_gpt3 as G
+    import models.distributed_gpt3 as D
+    text = G.BatchEncoding(dict(input_ids=ids.to(cuda), attention_mask=att.to(cuda), prompt_lengths=fx["prompt_lengths"].to(cuda)))
+    with torch.no_grad():
+        _, image_embeds, _, qf = model.visual_prefix(v)
+        tla = text.attention_mask[:, 1:].clone()
+        for i, ln in enumerate(fx["prompt_lengths"].tolist()):
+            tla[i, :ln] = 0
+        targets, loss_mask = D.build_targets(text.input_ids, tla, fx["Q"])
+        emb = model.text_decoder.dist_model.language_model.embedding.word_embeddings(text.input_ids)
+        out = model.text_decoder(input_embeds=torch.cat([qf, emb.to(qf.dtype)], 1), loss_mask=loss_mask, labels=targets)
+    idx = fx["logit_idx"]
+    got = out.logits[idx[:, 0], idx[:, 1], idx[:, 2]].float().cpu()
+    ref_vals = fx["logit_vals"]
+    err_l2 = ((got - ref_vals).norm() / ref_vals.norm()).item()
+    err_max = (got - ref_vals).abs().max().item() / fx["logits_absmax"].item()
+    print("2.7B caption sampled logits: rel L2 err", err_l2, "max err / max|logit|", err_max, "loss", out.loss.item(),
+          "ref", fx["loss"].item())
+    assert err_l2 < 1e-2 and err_max < 2e-2
+    assert abs(out.loss.item() - fx["loss"].item()) < 5e-3 * fx["loss"].item()
+    assert _rel(out.losses, fx["losses"]) < 2e-2
+    assert _rel(image_embeds.float().norm(dim=-1), fx["image_embeds_norm"]) < 1e-2
+    assert _rel(out.last_hidden_state.float().norm(dim=-1), fx["hidden_norm"]) < 1e-2
+    del out
+    loss = model(v, text)
+    loss.backward()
+    assert abs(loss.item() - fx["loss"].item()) < 5e-3 * fx["loss"].item()
+    params = dict(model.named_parameters())
+    for k, (stride, vals) in fx["grads"].items():
+        g = params[k].grad.float().cpu().flatten()[::stride]
+        if vals.abs().max() > 1e-9:
+            assert _rel(g, vals) < 0.1, k
+    bad = []
+    for k, n in fx["grad_norms"].items():
+        gn = params[k].grad.float().norm().item()
+        if n.item() > 1e-9 and abs(gn - n.item()) > 0.1 * n.item():
+            bad.append((k, gn, n.item()))
+    assert not bad, bad[:5]

@@ -368,9 +368,11 @@ extern "C" int ymp_ce_bwd(const ymp_ce_args* a, void* stream) {
 
 extern "C" int ymp_colsum(const ymp_colsum_args* a, void* stream) {
   YMP_CHECK_ARG(a && a->in && a->out, "ymp_colsum: null pointer");
-  YMP_CHECK_ARG(a->R > 0 && a->C > 0 && a->C % 8 == 0 && a->ld % 8 == 0 && a->ld >= a->C && aligned16(a->in), "ymp_colsum: bad shape/alignment");
+  // C need not be a multiple of 8: rows are read in 8-column vectors, so the row stride must cover the
+  // rounded-up width (the columns beyond C are read and discarded)
+  YMP_CHECK_ARG(a->R > 0 && a->C > 0 && a->ld % 8 == 0 && a->ld >= (a->C + 7) / 8 * 8 && aligned16(a->in), "ymp_colsum: bad shape/alignment");
   YMP_CHECK_ARG(aligned16(a->out), "ymp_colsum: out must be 16-byte aligned");
-  const int gx = (a->C / 8 + 31) / 32;
+  const int gx = ((a->C + 7) / 8 + 31) / 32;
   int splits = max(1, min((a->R + 63) / 64, (num_sms() * 4 + gx - 1) / gx));
   const int rpb = (a->R + splits - 1) / splits;
   splits = (a->R + rpb - 1) / rpb;

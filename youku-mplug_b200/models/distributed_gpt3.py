@@ -25,11 +25,14 @@ class _Linear(nn.Linear):
     """nn.Linear whose forward runs on the tcgen05 GEMM (same parameters / state_dict keys)."""
 
     def forward(self, x):
-        if self.weight.shape[0] % 8 or self.weight.shape[1] % 8:
-            # classifier heads with 2 / 5 / 45 outputs: a few kFLOP, below the GEMM kernel's 16-byte
-            # row-alignment requirement - left to the library GEMM
-            return F.linear(x, self.weight, self.bias)
         return YF.LinearFn.apply(x, self.weight, self.bias)
+
+
+class _VisualNorm(nn.LayerNorm):
+    """visual_norm of `connect_ln` configs (reference :112-116): LayerNormWithForceFP32(text_width)."""
+
+    def forward(self, x):
+        return YF.LayerNormFn.apply(x, self.weight, self.bias, self.eps)
 
 
 def _build_visual_encoder(visual_cfg, num_frames):
@@ -93,9 +96,8 @@ class _PrefixModelBase(nn.Module):
         self.visual_fc = _Linear(self.vision_width, self.text_width)
         with torch.no_grad():
             self.visual_fc.weight.copy_(trunc_normal((self.text_width, self.vision_width), 0.015))
-        if visual_cfg.get('connect_ln', False):
-            raise NotImplementedError("connect_ln (visual_norm) is not wired into the fused path yet")
-        self.visual_norm = nn.Identity()
+        self.connect_ln = bool(visual_cfg.get('connect_ln', False))
+        self.visual_norm = _VisualNorm(self.text_width, eps=1e-6) if self.connect_ln else nn.Identity()
         self.prompt = config.get('prompt', "")
 
     def _word_embedding(self):
@@ -149,7 +151,7 @@ class DistributedGPT3_Pretrain(_PrefixModelBase):
                                       "never set, models/distributed_gpt3.py:118-120,146-148)")
         text_loss_atts = text.attention_mask[:, 1:]
         targets, loss_mask = build_targets(text.input_ids, text_loss_atts, self.num_learnable_token)
-        if not self.use_contrastive:
+        if not self.use_contrastive and not self.connect_ln:
             keys, params = self._fused_params()
             loss_caption, losses = YF.PretrainFn.apply(image, text.input_ids, targets, loss_mask,
                                                        self.visual_encoder.vcfg, self.text_decoder.config.engine_cfg(),
@@ -157,11 +159,14 @@ class DistributedGPT3_Pretrain(_PrefixModelBase):
             self.last_losses = losses
             return loss_caption, loss_caption.new_zeros(())   # device-side (CUDA-graph capturable)
 
-        # ---- contrastive variant (:168-217): component path so that image_query is exposed
+        # ---- contrastive variant (:168-217) / connect_ln: component path so that image_query is exposed
         _, image_embeds, image_query, query_features = self.visual_prefix(image)
         input_embeds = torch.cat([query_features, self._word_embedding()(text.input_ids).to(query_features.dtype)], dim=1)
         outputs = self.text_decoder(input_embeds=input_embeds, loss_mask=loss_mask, labels=targets)
         loss_caption = outputs.loss
+        self.last_losses = None
+        if not self.use_contrastive:
+            return loss_caption, loss_caption.new_zeros(())
         targets_dep = torch.cat([text.input_ids[:, 1:], text.input_ids[:, 1:2]], dim=1)
         outputs_text = self.text_decoder(tokens=text.input_ids, loss_mask=text.attention_mask[:, 1:].clone(),
                                          labels=targets_dep)
@@ -172,9 +177,12 @@ class DistributedGPT3_Pretrain(_PrefixModelBase):
         dist_on = torch.distributed.is_initialized()
         vision_feats_all = all_gather_cat(vision_feats) if dist_on else vision_feats   # [B*W, Q, E]
         text_feat_all = all_gather_cat(text_feat) if dist_on else text_feat            # [B*W, E]
-        # sim_q2t[b, j, q] = <vision_feats[b,q], text_all[j]> ; max over queries (:186-202)
-        sim_i2t = torch.einsum('bqe,je->bjq', vision_feats, text_feat_all).max(-1)[0] / self.temp
-        sim_t2i = torch.einsum('be,jqe->bjq', text_feat, vision_feats_all).max(-1)[0] / self.temp
+        # sim_q2t[b, j, q] = <vision_feats[b,q], text_all[j]> ; max over queries (:186-202).  Both contractions
+        # run on the tcgen05 GEMM (bf16 operands like the reference's bf16 module, fp32 accumulation / output).
+        Bv, Qv, E = vision_feats.shape
+        J = text_feat_all.shape[0]
+        sim_i2t = YF.matmul_nt(vision_feats.reshape(Bv * Qv, E), text_feat_all).view(Bv, Qv, J).max(1)[0] / self.temp
+        sim_t2i = YF.matmul_nt(text_feat, vision_feats_all.reshape(J * Qv, E)).view(Bv, J, Qv).max(-1)[0] / self.temp
         rank = torch.distributed.get_rank() if dist_on else 0
         bs = image.size(0)
         tgt = torch.arange(rank * bs, rank * bs + bs, device=image.device)
@@ -346,8 +354,8 @@ class DistributedGPT3_Retrieval(_PrefixModelBase):
             idx_all = concat_all_gather(idx.view(-1))
         else:
             image_feat_all, text_feat_all, idx_all = image_feat, text_feat, idx.view(-1)
-        sim_i2t = image_feat @ text_feat_all.t() / self.temp
-        sim_t2i = text_feat @ image_feat_all.t() / self.temp
+        sim_i2t = YF.matmul_nt(image_feat, text_feat_all) / self.temp
+        sim_t2i = YF.matmul_nt(text_feat, image_feat_all) / self.temp
         pos = torch.eq(idx.view(-1, 1), idx_all.view(1, -1)).float()
         sim_targets = pos / pos.sum(1, keepdim=True)
         loss_i2t = -torch.sum(F.log_softmax(sim_i2t, dim=1) * sim_targets, dim=1).mean()

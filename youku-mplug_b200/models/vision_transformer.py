@@ -60,6 +60,10 @@ class TimeSformer(nn.Module):
             raise NotImplementedError("only absolute position embeddings are supported (all shipped configs)")
         if not qkv_bias or postnorm or stop_grad_conv1 or in_chans != 3:
             raise NotImplementedError("unsupported TimeSformer option for the B200 path")
+        if init_values:  # layer scale (gamma_1 / gamma_2): no shipped config sets it
+            raise NotImplementedError("layer_scale_init_value > 0 is not supported on the B200 path")
+        # drop_path_rate is accepted and has no effect, exactly like the reference: Block.forward
+        # (models/vision_transformer.py:243-275) never applies self.drop_path.
         self.num_features = self.embed_dim = embed_dim
         self.num_frames = num_frames
         self.img_size, self.patch_size = img_size, patch_size
@@ -130,9 +134,12 @@ class AttentionPool(nn.Module):
     def forward(self, x, k, rel_pos_bias=None, attn_mask=None, queries_param=None):
         """x: learnable_queries.repeat(B,1,1) in the reference call (models/distributed_gpt3.py:134).
         The kernels exploit that every sample shares the same query block, so the un-repeated
-        parameter is passed as `queries_param` by the task models; a generic x falls back to its
-        first sample only if all samples are identical views of it."""
+        parameter is passed as `queries_param` by the task models; a generic x is accepted only when
+        every sample holds the same query block (checked), anything else raises."""
         if queries_param is None:
+            if x.shape[0] > 1 and not bool((x == x[:1]).all()):
+                raise NotImplementedError("AttentionPool on the B200 path needs one query block shared by all samples "
+                                          "(learnable_queries.repeat(B,1,1), models/distributed_gpt3.py:134)")
             queries_param = x[:1]
         keys, params = named_param_list(self, "attn_pool.")
         keys = ["learnable_queries"] + keys

@@ -232,6 +232,8 @@ def vit_bwd(W, G, c, d_out):
     for i in reversed(range(d.depth)):
         dx = vit_block_bwd(W, G, f"{VE}blocks.{i}.", c.blocks[i], dx, d)
         c.blocks[i] = None  # release activations as we go
+        if hasattr(G, "ready"):
+            G.ready(f"{VE}blocks.{i}.")  # this block's weight gradients are final: their all-reduce may start
     if VE + "norm_pre.weight" in W:
         dx0 = ops.layernorm_bwd(dx, c.x0, W[VE + "norm_pre.weight"], c.m0, c.r0,
                                 dgamma=G.get(VE + "norm_pre.weight"), dbeta=G.get(VE + "norm_pre.bias"))

@@ -12,19 +12,21 @@ import torch
 from . import engine, ops
 from .ops import bf16
 
-_cast_cache = {}
-
-
 def as_bf16(p):
-    """Kernels consume bf16.  bf16 params are used in place; fp32 params (module not cast by the
-    caller) are converted once per parameter version."""
+    """Kernels consume bf16.  bf16 params are used in place.  fp32 params (module not cast by the caller):
+    trainable ones are converted on every call (an optimizer that writes through `p.data` does not bump
+    `_version`, so no cache can be trusted for them; 130 M parameters cost ~0.1 ms), frozen ones are converted
+    once and the copy is kept ON the parameter object (it dies with it - no id() reuse, no leak) and
+    re-validated against version / storage / shape / device."""
     if p.dtype == bf16:
         return p.detach()
-    key = id(p)
-    ent = _cast_cache.get(key)
-    if ent is None or ent[0] != p._version or ent[1].device != p.device:
-        ent = (p._version, p.detach().to(bf16))
-        _cast_cache[key] = ent
+    if p.requires_grad:
+        return p.detach().to(bf16)
+    key = (p._version, p.data_ptr(), tuple(p.shape), p.device)
+    ent = getattr(p, "_ymp_bf16", None)
+    if ent is None or ent[0] != key:
+        ent = (key, p.detach().to(bf16))
+        p._ymp_bf16 = ent
     return ent[1]
 
 
@@ -34,18 +36,31 @@ def _require_cuda(t, what):
 
 
 _SINK = None
+_READY = None
 
 
 @contextlib.contextmanager
-def grad_sink(sink):
+def grad_sink(sink, on_ready=None):
     """While active, weight gradients of parameters found in `sink` ({id(param): fp32 flat view}) are
-    accumulated straight into those views and autograd receives None for them (ymp.train.TrainEngine)."""
-    global _SINK
+    accumulated straight into those views and autograd receives None for them (ymp.train.TrainEngine).
+    `on_ready(prefix)` is called from inside the backward as soon as every weight gradient under a
+    state-dict prefix (one TimeSformer block) is final, so that its all-reduce can start while the
+    remaining backward still runs."""
+    global _SINK, _READY
     prev, _SINK = _SINK, sink
+    prev_r, _READY = _READY, on_ready
     try:
         yield
     finally:
-        _SINK = prev
+        _SINK, _READY = prev, prev_r
+
+
+class GradDict(dict):
+    """key -> fp32 accumulator, plus the `ready(prefix)` notification of the active grad sink."""
+
+    def ready(self, prefix):
+        if _READY is not None:
+            _READY(prefix)
 
 
 class _GradStore:
@@ -53,7 +68,7 @@ class _GradStore:
     is one, otherwise carved from one freshly zeroed flat buffer."""
 
     def __init__(self, keys, params, needs, dev):
-        self.G, self.sunk = {}, set()
+        self.G, self.sunk = GradDict(), set()
         local = []
         for k, p, n in zip(keys, params, needs):
             if not n:
@@ -202,25 +217,52 @@ class AttnPoolFn(torch.autograd.Function):
         return (d_img.view(ctx.shape), None, None) + store.grads(ctx.keys, ctx.params)
 
 
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def _padded_cols(t, dtype=bf16):
+    """[M, N] -> a [M, N] view (row stride rounded up to 8 elements) holding t in `dtype`: the GEMM's TMA
+    maps need 16-byte aligned rows; columns beyond N are never read (the tensor map's extent is N)."""
+    M, N = t.shape
+    if N % 8 == 0 and t.dtype == dtype and t.is_contiguous():
+        return t
+    buf = torch.empty((M, _pad8(N)), device=t.device, dtype=dtype)
+    view = buf[:, :N]
+    view.copy_(t)
+    return view
+
+
 class LinearFn(torch.autograd.Function):
-    """y = x W^T + b on the tcgen05 GEMM (visual_fc, projection heads, cls_head layers)."""
+    """y = x W^T + b on the tcgen05 GEMM (visual_fc, projection heads, cls_head layers).  Any out_features:
+    outputs narrower than / not a multiple of 8 columns (the 2 / 5 / 45-way classifier heads) are written
+    into a row-padded buffer and returned as a view."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         _require_cuda(x, "LinearFn")
         x2 = x.reshape(-1, x.shape[-1]).to(bf16).contiguous()
         w = as_bf16(weight)
-        y = ops.gemm(x2, w, bias=as_bf16(bias) if bias is not None else None)
+        N = w.shape[0]
+        if x2.shape[1] % 8:
+            raise ValueError(f"LinearFn: in_features must be a multiple of 8 (got {x2.shape[1]})")
+        b = None
+        if bias is not None:
+            b = as_bf16(bias)
+            if b.data_ptr() % 16:
+                b = b.clone()
+        out = torch.empty((x2.shape[0], _pad8(N)), device=x2.device, dtype=bf16)[:, :N]
+        y = ops.gemm(x2, w, bias=b, out=out)
         ctx.save_for_backward(x2, w)
         ctx.meta = (x.shape, x.dtype, weight.dtype, None if bias is None else bias.dtype)
         ctx.ids = (id(weight), None if bias is None else id(bias))
-        return y.view(*x.shape[:-1], w.shape[0])
+        return y.reshape(*x.shape[:-1], N) if N % 8 == 0 else y.unflatten(0, x.shape[:-1])
 
     @staticmethod
     def backward(ctx, dy):
         x2, w = ctx.saved_tensors
         xshape, xdt, wdt, bdt = ctx.meta
-        dy2 = dy.reshape(-1, dy.shape[-1]).to(bf16).contiguous()
+        dy2 = _padded_cols(dy.reshape(-1, dy.shape[-1]))
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = ops.gemm(dy2, w, b_t=True).view(xshape).to(xdt)
@@ -240,6 +282,66 @@ class LinearFn(torch.autograd.Function):
                 ops.colsum(dy2, db)
                 db = db.to(bdt)
         return dx, dw, db
+
+
+class MatmulNTFn(torch.autograd.Function):
+    """s = x @ y^T in fp32 from bf16 operands on the tcgen05 GEMM, with both gradients: the similarity
+    contractions of the contrastive branches (models/distributed_gpt3.py:186-202, :957-958)."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        _require_cuda(x, "MatmulNTFn")
+        x2, y2 = x.to(bf16).contiguous(), y.to(bf16).contiguous()
+        M, K = x2.shape
+        N = y2.shape[0]
+        if K % 8:
+            raise ValueError(f"MatmulNTFn: the contraction dim must be a multiple of 8 (got {K})")
+        out = torch.empty((M, _pad8(N)), device=x2.device, dtype=torch.float32)[:, :N]
+        ops.gemm(x2, y2, out=out)
+        ctx.save_for_backward(x2, y2)
+        ctx.dts = (x.dtype, y.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, ds):
+        x2, y2 = ctx.saved_tensors
+        dsp = _padded_cols(ds)
+        dx = dy = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(dsp, y2, b_t=True, out_dtype=torch.float32).to(ctx.dts[0])
+        if ctx.needs_input_grad[1]:
+            dy = ops.gemm(dsp, x2, a_t=True, b_t=True, out_dtype=torch.float32).to(ctx.dts[1])
+        return dx, dy
+
+
+def matmul_nt(x, y):
+    return MatmulNTFn.apply(x, y)
+
+
+class LayerNormFn(torch.autograd.Function):
+    """LayerNormWithForceFP32 (models/vision_transformer.py:69-71) on the LayerNorm kernels; used for the
+    optional visual_norm of `connect_ln` configs (models/distributed_gpt3.py:112-116)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        _require_cuda(x, "LayerNormFn")
+        x2 = x.reshape(-1, x.shape[-1]).to(bf16).contiguous()
+        w, b = as_bf16(weight), as_bf16(bias)
+        y, mean, rstd = ops.layernorm_fwd(x2, w, b, eps)
+        ctx.save_for_backward(x2, w, mean, rstd)
+        ctx.meta = (x.shape, x.dtype, weight.dtype, id(weight), id(bias))
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, mean, rstd = ctx.saved_tensors
+        xshape, xdt, wdt, wid, bid = ctx.meta
+        D = x2.shape[1]
+        sunk = _SINK is not None and wid in _SINK
+        dg = _SINK[wid] if sunk else torch.zeros(D, device=dy.device, dtype=torch.float32)
+        db = _SINK[bid] if sunk else torch.zeros(D, device=dy.device, dtype=torch.float32)
+        dx = ops.layernorm_bwd(dy.reshape(-1, D).to(bf16).contiguous(), x2, w, mean, rstd, dgamma=dg, dbeta=db)
+        return dx.view(xshape).to(xdt), (None if sunk else dg.to(wdt)), (None if sunk else db.to(wdt)), None
 
 
 class GptFn(torch.autograd.Function):

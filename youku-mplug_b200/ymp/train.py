@@ -22,13 +22,16 @@ from . import ops
 
 
 def default_param_groups(model, weight_decay, skip_list=(), visual_backbone_scale=False):
-    """Same grouping rule as the reference's optim/optim_factory.py:219-265 (no decay for 1-D / bias /
-    skip_list names; optional 0.1 lr scale for non-temporal visual_encoder weights)."""
+    """Same grouping rule as the reference's optim/optim_factory.py:219-265 (no decay for 1-D / `.bias` /
+    skip_list names / any name containing "bias" or "LayerNorm.weight" - check_keywords_in_name, :226 - so the
+    3-D attn_pool.attn.bias_k / bias_v rows are decay-free too; optional 0.1 lr scale for non-temporal
+    visual_encoder weights)."""
     groups = {}
     for name, p in model.named_parameters():
         if not p.requires_grad:
             continue
-        no_decay = p.dim() == 1 or name.endswith(".bias") or name in skip_list
+        no_decay = (p.dim() == 1 or name.endswith(".bias") or name in skip_list
+                    or "bias" in name or "LayerNorm.weight" in name)
         scaled = visual_backbone_scale and "visual_encoder." in name and "temporal" not in name
         key = (no_decay, scaled)
         g = groups.setdefault(key, dict(params=[], names=[], weight_decay=0.0 if no_decay else weight_decay,
@@ -49,8 +52,9 @@ class _Optimizer:
 
 class TrainEngine:
     def __init__(self, model, optimizer_params=None, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.05,
-                 clip_grad=3.0, process_group=None):
+                 clip_grad=3.0, process_group=None, gradient_accumulation_steps=1, overlap_comm=True):
         self.module = model
+        self.gas = max(1, int(gradient_accumulation_steps))
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         if optimizer_params is None:
@@ -64,13 +68,21 @@ class TrainEngine:
         total = sum((p.numel() + 7) // 8 * 8 for p in params)
         self.flat_param = torch.zeros(total, device=dev, dtype=torch.bfloat16)
         self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        # fp32 master weights come from the parameters as handed in (an fp32 model keeps its low bits; a
+        # bf16 model gives exactly its bf16 values)
+        self.master = torch.zeros(total, device=dev, dtype=torch.float32)
         self._sink = {}
+        self._params = params
+        names = {id(p): n for n, p in model.named_parameters()}
+        spans = []  # (name, start, end) in flat order
         off = 0
         groups = []
         for g in optimizer_params:
             start = off
             for p in g["params"]:
                 n = p.numel()
+                spans.append((names.get(id(p), ""), off, off + (n + 7) // 8 * 8))
+                self.master[off:off + n].copy_(p.data.reshape(-1))
                 view = self.flat_param[off:off + n].view(p.shape)
                 view.copy_(p.data)
                 p.data = view
@@ -79,7 +91,6 @@ class TrainEngine:
             groups.append(dict(params=g["params"], weight_decay=g.get("weight_decay", weight_decay),
                                lr_scale=g.get("lr_scale", 1.0), lr=lr * g.get("lr_scale", 1.0), betas=list(betas),
                                eps=eps, _range=(start, off)))
-        self.master = self.flat_param.float()
         self.exp_avg = torch.zeros_like(self.master)
         self.exp_avg_sq = torch.zeros_like(self.master)
         self._sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
@@ -87,6 +98,26 @@ class TrainEngine:
         self.micro_steps = 0
         self.global_steps = 0
         self._graphs = {}
+        # ---- bucketed, overlapped gradient all-reduce (the reference's ZeRO-1 reduce buckets,
+        # utils.py:528-529): the contiguous flat ranges of each TimeSformer block (>= 1 MB) are all-reduced as
+        # soon as the block's backward has produced them, on NCCL's own stream, while the remaining blocks still
+        # run; everything else (abstractor, embeddings, biases: the gaps) goes in step().
+        self.overlap_comm = overlap_comm and self.world > 1
+        self._buckets, self._pending, self._reduced = {}, [], []
+        if self.overlap_comm:
+            import re
+            cur = None
+            for name, a, b in spans:
+                m = re.match(r"(visual_encoder\.blocks\.\d+\.)", name)
+                key = m.group(1) if m else None
+                if cur is not None and key is not None and cur[0] == key and cur[2] == a:
+                    cur[2] = b
+                else:
+                    if cur is not None and cur[0] is not None and cur[2] - cur[1] >= (1 << 18):
+                        self._buckets.setdefault(cur[0], []).append((cur[1], cur[2]))
+                    cur = [key, a, b]
+            if cur is not None and cur[0] is not None and cur[2] - cur[1] >= (1 << 18):
+                self._buckets.setdefault(cur[0], []).append((cur[1], cur[2]))
 
     # ---- nn.Module-like surface -----------------------------------------------------------
     def __call__(self, *args, **kwargs):
@@ -110,21 +141,65 @@ class TrainEngine:
         return self.module.state_dict()
 
     # ---- training step ----------------------------------------------------------------------
-    def backward(self, loss):
-        with YF.grad_sink(self._sink):
+    def _on_ready(self, prefix):
+        """Called from inside the backward when the weight gradients under `prefix` are final."""
+        if (self.micro_steps + 1) % self.gas:      # not the boundary micro-step: keep accumulating locally
+            return
+        for a, b in self._buckets.get(prefix, ()):
+            self._pending.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._reduced.append((a, b))
+
+    def _join_comm(self):
+        for w in self._pending:
+            w.wait()   # stream-level: the compute stream waits for NCCL's stream, the host does not block
+        self._pending = []
+
+    def allreduce_gradients(self):
+        """Sum the flat gradient over the data-parallel ranks: whatever the in-backward buckets have not
+        already covered (all of it without overlap_comm)."""
+        if self.world == 1:
+            return
+        self._join_comm()
+        pos = 0
+        for a, b in sorted(self._reduced) + [(self.flat_grad.numel(), self.flat_grad.numel())]:
+            if a > pos:
+                dist.all_reduce(self.flat_grad[pos:a], op=dist.ReduceOp.SUM, group=self.group)
+            pos = max(pos, b)
+        self._reduced = []
+
+    def _backward(self, loss):
+        with YF.grad_sink(self._sink, self._on_ready if self.overlap_comm else None):
             loss.backward()
+        # Parameters whose gradient comes from ordinary autograd rather than from the ymp Functions (the
+        # contrastive `temp`, classifier heads too narrow for the 16-byte-aligned GEMM, ...) arrive in
+        # p.grad: fold them into the flat buffer so that step() sees every trainable parameter.
+        for p in self._params:
+            if p.grad is not None:
+                self._sink[id(p)].add_(p.grad.reshape(-1))
+                p.grad = None
+
+    def backward(self, loss):
+        """DeepSpeed engine semantics (the reference calls model.backward(loss / update_freq),
+        run_pretrain_distributed_gpt3.py:134-136): the loss is additionally scaled by
+        1 / gradient_accumulation_steps and gradients accumulate until the boundary micro-step."""
+        if self.gas > 1:
+            loss = loss / self.gas
+        self._backward(loss)
         self.micro_steps += 1
 
     def zero_grad(self):
         self.flat_grad.zero_()
 
+    def is_gradient_accumulation_boundary(self):
+        return self.micro_steps % self.gas == 0
+
     def step(self):
-        if self.world > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+        if not self.is_gradient_accumulation_boundary():
+            return  # keep accumulating: no all-reduce, no AdamW, no zeroing
+        self.allreduce_gradients()
         self.global_steps += 1
         self._sumsq.zero_()
-        if self.clip_grad and self.clip_grad > 0:
-            ops.sumsq(self.flat_grad, self._sumsq)
+        ops.sumsq(self.flat_grad, self._sumsq)  # always: the loop logs the norm even without clipping
         scale = 1.0 / self.world
         for g in self.optimizer.param_groups:
             a, b = g["_range"]
@@ -138,17 +213,21 @@ class TrainEngine:
         self.flat_grad.zero_()
 
     def train_step(self, video, text, use_graph=True, graph_warmup=2):
-        """One full iteration (forward + backward + step) and the loss tensor.
+        """One full iteration (forward + backward + step); returns loss_caption + loss_contrastive
+        (run_pretrain_distributed_gpt3.py:113) as a detached tensor.
 
         Shapes are static in pre-training (`padding='max_length'`, run_pretrain_distributed_gpt3.py:100),
         so after `graph_warmup` eager iterations the ~900 kernel launches of forward+backward are
-        captured ONCE into a CUDA graph per input signature and replayed; the all-reduce and the
-        optimizer stay outside the graph.  Inputs are copied into the graph's static buffers (the copy
+        captured ONCE into a CUDA graph per input signature and replayed; the all-reduce, the
+        grad-norm and the fused AdamW (6 launches) stay outside the graph.  Inputs are copied into the graph's static buffers (the copy
         also casts fp32 frames to bf16), so callers may pass fresh tensors every step."""
         key = (tuple(video.shape), tuple(text.input_ids.shape))
         st = self._graphs.setdefault(key, dict(calls=0))
+        if self.gas > 1:
+            use_graph = False   # boundary / non-boundary micro-steps differ (all-reduce, step): run eagerly
         if not use_graph or st["calls"] < graph_warmup:
-            loss, _ = self.module(video, text)
+            loss_caption, loss_ita = self.module(video, text)
+            loss = loss_caption + loss_ita
             self.backward(loss)
             self.step()
             st["calls"] += 1
@@ -165,15 +244,17 @@ class TrainEngine:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                loss, _ = self.module(st["video"], static_text)
-                with YF.grad_sink(self._sink):
-                    loss.backward()
-            st["graph"], st["loss"] = g, loss.detach()
+                loss_caption, loss_ita = self.module(st["video"], static_text)
+                loss = loss_caption + loss_ita
+                self._backward(loss / self.gas if self.gas > 1 else loss)
+                self._join_comm()   # the bucket all-reduces are part of the graph (fork/join on NCCL's stream)
+            st["graph"], st["loss"], st["reduced"] = g, loss.detach(), list(self._reduced)
         else:
             st["video"].copy_(video, non_blocking=True)
             st["ids"].copy_(text.input_ids, non_blocking=True)
             st["att"].copy_(text.attention_mask, non_blocking=True)
         st["graph"].replay()
+        self._reduced = list(st["reduced"])
         self.micro_steps += 1
         self.step()
         return st["loss"]
@@ -190,6 +271,8 @@ class TrainEngine:
                        os.path.join(save_dir, str(tag), "mp_rank_00_model_states.pt"))
             with open(os.path.join(save_dir, "latest"), "w") as f:
                 f.write(str(tag))
+        if dist.is_initialized():
+            dist.barrier(group=self.group)  # nobody reads `latest` / the tag directory before it is complete
 
     def load_checkpoint(self, load_dir, tag=None):
         import os
@@ -197,7 +280,7 @@ class TrainEngine:
             with open(os.path.join(load_dir, "latest")) as f:
                 tag = f.read().strip()
         ck = torch.load(os.path.join(load_dir, str(tag), "mp_rank_00_model_states.pt"), map_location="cpu", weights_only=False)
-        self.module.load_state_dict(ck["module"])
+        self.module.load_state_dict(ck["module"])   # parameters are views of flat_param: refreshed in place
         self.master.copy_(ck["master"])
         self.exp_avg.copy_(ck["exp_avg"])
         self.exp_avg_sq.copy_(ck["exp_avg_sq"])
