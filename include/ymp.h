@@ -196,6 +196,14 @@ typedef struct ymp_attn_bwd_args {
   ymp_seqmap map_do, map_dq, map_dkv;
 } ymp_attn_bwd_args;
 int ymp_attn_bwd(const ymp_attn_bwd_args* a, void* stream);
+/* Diagnostic: which kernel family served the last ymp_attn_fwd / ymp_attn_bwd call of this thread (-1: none yet).
+ * tcgen05 tiles serve head_dim 64 / 80 / 88 / 96 at any key range; warp-per-sequence kernels the packed
+ * block-diagonal (temporal, T <= 16) case; the mma.sync kernels remain for head_dim 128 and for a few query
+ * rows against a long cache (single-token decoding). */
+#define YMP_ATTN_PATH_MMA_SYNC 0
+#define YMP_ATTN_PATH_TCGEN05 1
+#define YMP_ATTN_PATH_SMALL 2
+int ymp_attn_last_path(void);
 
 /* ------------------------------------------------------------------------------------------
  * Patch-embedding im2col: video [B,C,T,H,W] bf16 -> patches [(b,n,t), C*P*P] (the A operand of

@@ -124,3 +124,46 @@ def test_gemm_large_persistent(cuda):
     out2 = ops.gemm(big[:, K:2 * K], b)
     ref2, _ = _ref(big[:, K:2 * K], b, False, False)
     _close(out2, ref2, 1e-2)
+
+
+@pytest.mark.parametrize("M", [1000, 2560 + 37])
+def test_gemm_pair_tile_tma_epilogue_variants(cuda, M):
+    """CTA-pair kernel, epilogue staged through swizzled smem and written with bulk tensor stores / reduce-adds:
+    ragged M (rows clipped by the tensor map), fp32 residual stream in and out, bf16 + act' pairs, row-strided
+    outputs, split-K accumulation into a non-zero buffer, several tiles per CTA pair (staging-buffer reuse)."""
+    from ymp import ops
+    torch.manual_seed(5)
+    N, K = 768, 320
+    a = torch.randn(M, K, device=cuda).bfloat16()
+    b = (torch.randn(N, K, device=cuda) * 0.1).bfloat16()
+    bias = torch.randn(N, device=cuda).bfloat16()
+    # fp32 stream: out = x + (a b^T + bias)
+    x = torch.randn(M, N, device=cuda)
+    out = ops.gemm(a, b, bias=bias, residual=x, out_dtype=torch.float32, tile_n=512)
+    ref, _ = _ref(a, b, False, False, bias=bias)
+    _close(out, ref + x, 1e-3 * 8)
+    # in place on the stream buffer itself (engine: residual and D may alias)
+    x2 = x.clone()
+    ops.gemm(a, b, bias=bias, residual=x2, out=x2, tile_n=512)
+    _close(x2, ref + x, 1e-3 * 8)
+    # bf16 + act' into row-strided views of wider buffers
+    wide = torch.zeros(M, 2 * N, device=cuda, dtype=torch.bfloat16)
+    wide_aux = torch.zeros(M, 2 * N, device=cuda, dtype=torch.bfloat16)
+    for act in (1, 2):
+        ops.gemm(a, b, bias=bias, act=act, aux_out=wide_aux[:, N:], out=wide[:, N:], tile_n=512)
+        r2, pre = _ref(a, b, False, False, bias=bias, act=act)
+        _close(wide[:, N:], r2)
+        _close(wide_aux[:, N:], pre)
+        assert float(wide[:, :N].abs().max()) == 0.0 and float(wide_aux[:, :N].abs().max()) == 0.0
+    # activation backward: multiplier read per element
+    mul = torch.randn(M, K, device=cuda).bfloat16()
+    g = ops.gemm(a.new_empty(M, N).normal_().bfloat16(), b, b_t=True, aux_in=mul, act=1, tile_n=512)
+    assert g.shape == (M, K)
+    # split-K wgrad: fp32 accumulate (bulk reduce-add) into a running buffer
+    dy = torch.randn(M, N, device=cuda).bfloat16()
+    acc = torch.full((N, K), 0.5, device=cuda)
+    ops.gemm(dy, a, a_t=True, b_t=True, out=acc, accumulate=True, split_k=3, tile_n=512)
+    _close(acc, dy.float().t() @ a.float() + 0.5, 2e-3)
+    # many tiles per pair
+    big = torch.randn(40000, K, device=cuda).bfloat16()
+    _close(ops.gemm(big, b, bias=bias, tile_n=512), big.float() @ b.float().t() + bias.float(), 1e-2)

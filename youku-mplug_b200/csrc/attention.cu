@@ -729,6 +729,9 @@ int attn_small_fwd_try(const ymp_attn_args* a, cudaStream_t st);
 int attn_small_bwd_try(const ymp_attn_bwd_args* b, cudaStream_t st);
 }
 
+static thread_local int g_attn_path = -1;
+extern "C" int ymp_attn_last_path(void) { return g_attn_path; }
+
 extern "C" int ymp_attn_fwd(const ymp_attn_args* a, void* stream) {
   using namespace ymp;
   AttnKParams p = {};
@@ -740,10 +743,11 @@ extern "C" int ymp_attn_fwd(const ymp_attn_args* a, void* stream) {
   static const bool legacy = [] { const char* e = getenv("YMP_ATTN_LEGACY"); return e && e[0] == '1'; }();
   if (!legacy) {
     rc = attn_small_fwd_try(a, st);  // short dense block-diagonal sequences (attention_small.cu)
-    if (rc != YMP_ENOSUP) return rc;
+    if (rc != YMP_ENOSUP) { g_attn_path = YMP_ATTN_PATH_SMALL; return rc; }
     rc = attn_tc_fwd_try(a, st);
-    if (rc != YMP_ENOSUP) return rc;
+    if (rc != YMP_ENOSUP) { g_attn_path = YMP_ATTN_PATH_TCGEN05; return rc; }
   }
+  g_attn_path = YMP_ATTN_PATH_MMA_SYNC;
   switch (a->head_dim) {
     case 64: return launch_fwd<64>(p, st);
     case 80: return launch_fwd<80>(p, st);
@@ -771,10 +775,11 @@ extern "C" int ymp_attn_bwd(const ymp_attn_bwd_args* b, void* stream) {
   static const bool legacy = [] { const char* e = getenv("YMP_ATTN_LEGACY"); return e && e[0] == '1'; }();
   if (!legacy) {
     rc = attn_small_bwd_try(b, st);
-    if (rc != YMP_ENOSUP) return rc;
+    if (rc != YMP_ENOSUP) { g_attn_path = YMP_ATTN_PATH_SMALL; return rc; }
     rc = attn_tc_bwd_try(b, st);
-    if (rc != YMP_ENOSUP) return rc;
+    if (rc != YMP_ENOSUP) { g_attn_path = YMP_ATTN_PATH_TCGEN05; return rc; }
   }
+  g_attn_path = YMP_ATTN_PATH_MMA_SYNC;
   switch (a->head_dim) {
     case 64: return launch_bwd<64>(p, st);
     case 80: return launch_bwd<80>(p, st);

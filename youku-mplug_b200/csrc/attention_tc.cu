@@ -1,4 +1,7 @@
-// tcgen05 attention for short key ranges (s_kv <= 256, head_dim 64 / 96): ViT spatial (197) and GPT causal (256).
+// tcgen05 attention, head_dim 64 / 96 natively and 80 / 88 zero-padded to 96 inside shared memory (the 2.7B
+// decoder and EVA-g): ViT spatial (197 keys), GPT causal (256, 384), the abstractor's 1570-key cross attention.
+// Key ranges <= 256 take the single-pass kernel below; longer ranges run the same tile code in a loop over
+// 256-key blocks with an online softmax (<LONG>: running row max / sum, O re-scaled in registers).
 // Forward, one CTA (256 threads) = 128 query rows of one (sequence, head):
 //   1. cp.async gathers Q [128 x HD], K, V [Nkv x HD] through the seqmap into shared memory laid out
 //      exactly as the UMMA canonical SWIZZLE_128B (first 64 head-dim columns) / SWIZZLE_64B (columns
@@ -10,7 +13,7 @@
 //   4. O[128 x HD] = P V  with A = P read from TMEM and B = V as an MN-major smem operand (two issuer threads
 //      for the 64- and 32-column parts)
 //   5. tcgen05.ld O, scale by 1/l, 16-byte row stores + lse
-// No online-softmax rescaling, no KV loop, no register-resident accumulators.  TMEM use is 256 columns
+// Short ranges: no online-softmax rescaling, no KV loop, no register-resident accumulators.  TMEM use is 256 columns
 // (S, then P in [0,64) and [128,192), O in [64,128) and [192,224)), shared memory ~80-113 KB, so two CTAs
 // share an SM and overlap each other's load / MMA / softmax phases.  The backward kernel is described below.
 #include <math_constants.h>
@@ -53,7 +56,8 @@ struct AttnTcParams {
   int n_seq, n_heads, s_q, s_kv, mask, mask_block;
   long total_rows;
   float scale_log2, scale;
-  int kv_rows;  // rows of the K/V smem tiles = round32(s_kv)
+  int kv_rows;  // rows of the K/V smem tiles = round32(min(s_kv, 256))
+  int hd;       // real head_dim (<= HD): columns [hd, HD) are zero-filled in shared memory and never stored
 };
 
 __device__ __forceinline__ void cp16(void* smem, const void* gmem) {
@@ -103,30 +107,6 @@ constexpr int LAYOUT_SW128 = 2, LAYOUT_SW64 = 4;
 // Load `rows` rows x HD columns into the swizzled blocks (rows beyond n_valid are zero-filled).
 // thread -> (row = tid/4 within a 32-row pass, 16-byte chunks tid%4 + 4j): one row pointer per thread and
 // pass, 4 consecutive lanes fetch 64 contiguous bytes.
-template <int HD>
-__device__ __forceinline__ void tc_load(uint8_t* blk0, uint8_t* blk1, const TcMat& m, int r0, int rows, int n_valid) {
-  constexpr int CPT = HD / 32;  // chunks per thread per row
-  const int rl = threadIdx.x >> 2, c0 = threadIdx.x & 3;
-  for (int rb = 0; rb < rows; rb += 32) {
-    const int r = rb + rl;
-    if (r >= rows) break;
-    if (r0 + r < n_valid) {
-      const __nv_bfloat16* g = tc_row(m, r0 + r);
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const int c = c0 + 4 * j;
-        cp16((c < 8) ? blk0 + sw128_off(r, c) : blk1 + sw64_off(r, c - 8), g + c * 8);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const int c = c0 + 4 * j;
-        *reinterpret_cast<uint4*>((c < 8) ? blk0 + sw128_off(r, c) : blk1 + sw64_off(r, c - 8)) = make_uint4(0, 0, 0, 0);
-      }
-    }
-  }
-}
-
 #ifdef YMP_ATTN_DBG
 __device__ unsigned long long ymp_attn_dbg_buf[256];
 #define TDBG(k)                                                                                        \
@@ -138,34 +118,30 @@ __device__ unsigned long long ymp_attn_dbg_buf[256];
 #define TDBG(k)
 #endif
 
-// 256-thread tile loader: thread -> (row = tid/4 of a 64-row pass, 16-byte chunks tid%4 + 4j)
+// 256-thread tile loader: thread -> (row = tid/4 of a 64-row pass, 16-byte chunks tid%4 + 4j).  Rows beyond
+// n_valid and head-dim columns beyond `hd` (head_dim 80 / 88 padded to 96) are zero-filled.
 template <int HD>
-__device__ __forceinline__ void tc_load256(uint8_t* blk0, uint8_t* blk1, const TcMat& m, int r0, int rows, int n_valid) {
+__device__ __forceinline__ void tc_load256(uint8_t* blk0, uint8_t* blk1, const TcMat& m, int r0, int rows, int n_valid, int hd) {
   constexpr int CPT = HD / 32;
   const int rl = threadIdx.x >> 2, c0 = threadIdx.x & 3;
   for (int rb = 0; rb < rows; rb += 64) {
     const int r = rb + rl;
     if (r >= rows) break;
-    if (r0 + r < n_valid) {
-      const __nv_bfloat16* g = tc_row(m, r0 + r);
+    const bool rv = r0 + r < n_valid;
+    const __nv_bfloat16* g = rv ? tc_row(m, r0 + r) : nullptr;
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const int c = c0 + 4 * j;
-        cp16((c < 8) ? blk0 + sw128_off(r, c) : blk1 + sw64_off(r, c - 8), g + c * 8);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const int c = c0 + 4 * j;
-        *reinterpret_cast<uint4*>((c < 8) ? blk0 + sw128_off(r, c) : blk1 + sw64_off(r, c - 8)) = make_uint4(0, 0, 0, 0);
-      }
+    for (int j = 0; j < CPT; ++j) {
+      const int c = c0 + 4 * j;
+      uint8_t* dst = (c < 8) ? blk0 + sw128_off(r, c) : blk1 + sw64_off(r, c - 8);
+      if (rv && c * 8 < hd) cp16(dst, g + c * 8);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
     }
   }
 }
 
-template <int HD>
+template <int HD, bool LONG>
 __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) {
-  static_assert(HD == 64 || HD == 96, "head_dim 64 or 96");
+  static_assert(HD == 64 || HD == 96, "head_dim 64 or 96 (80 / 88 are padded to 96)");
   constexpr bool TWO = (HD == 96);
   // TMEM columns (256 allocated): S in [0, nkv); the two warpgroups own the key-column halves [0,128) / [128,256):
   // P (bf16 pairs) of half 0 lands in [0,64), of half 1 in [128,192) - always inside columns its own threads
@@ -202,8 +178,8 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) 
   if (q0 >= sq) return;
   // key range this tile needs
   int kv_end = skv;
-  if (p.mask == TC_MASK_CAUSAL) kv_end = min(skv, q0 + 128);
-  const int nkv = (kv_end + 31) & ~31;  // MMA N / K extent (multiple of 32, <= 256)
+  if (p.mask == TC_MASK_CAUSAL) kv_end = min(skv, q0 + 128 + (p.s_kv - p.s_q));
+  const int nblk = LONG ? (kv_end + 255) >> 8 : 1;   // 256-key blocks (short ranges: exactly one)
 
   if (warp == 0) tmem_alloc<256>(tmem_ptr);
   if (threadIdx.x == 32) {
@@ -211,13 +187,14 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) 
     mbar_init(&bar[1], TWO ? 2 : 1);
     fence_mbar_init();
   }
+  const TcMat Mk = tc_mat(p.k, p.mkv, s, p.ldk, h * p.hsk);
+  const TcMat Mv = tc_mat(p.v, p.mkv, s, p.ldv, h * p.hsv);
   {
     const TcMat Mq = tc_mat(p.q, p.mq, s, p.ldq, h * p.hsq);
-    const TcMat Mk = tc_mat(p.k, p.mkv, s, p.ldk, h * p.hsk);
-    const TcMat Mv = tc_mat(p.v, p.mkv, s, p.ldv, h * p.hsv);
-    tc_load256<HD>(q0s, q1s, Mq, q0, 128, sq);
-    tc_load256<HD>(k0s, k1s, Mk, 0, nkv, kv_end);
-    tc_load256<HD>(v0s, v1s, Mv, 0, nkv, kv_end);
+    const int kend0 = min(kv_end, 256);
+    tc_load256<HD>(q0s, q1s, Mq, q0, 128, sq, p.hd);
+    tc_load256<HD>(k0s, k1s, Mk, 0, (kend0 + 31) & ~31, kv_end, p.hd);
+    tc_load256<HD>(v0s, v1s, Mv, 0, (kend0 + 31) & ~31, kv_end, p.hd);
   }
   TDBG(1);
   asm volatile("cp.async.wait_all;" ::: "memory");
@@ -228,124 +205,169 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) 
   const uint32_t tmem = *tmem_ptr;
   TDBG(2);
 
-  // ---- S = Q K^T
-  if (threadIdx.x == 0) {
-    const uint32_t idesc = make_idesc_bf16(128, nkv, 0, 0);
-#pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks) {
-      uint64_t ad, bd;
-      if (ks < 4) {
-        ad = desc_sw(smem_u32(q0s) + ks * 32, 1024, LAYOUT_SW128);
-        bd = desc_sw(smem_u32(k0s) + ks * 32, 1024, LAYOUT_SW128);
-      } else {
-        ad = desc_sw(smem_u32(q1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
-        bd = desc_sw(smem_u32(k1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
-      }
-      umma_bf16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
-    }
-    umma_commit(&bar[0]);
-  }
-  TDBG(3);
-  mbar_wait(&bar[0], 0);
-  tc_fence_after();
-  TDBG(4);
-
-  // ---- exact softmax: two threads per query row (= TMEM lane), one per key-column half
   const int rl = wq * 32 + lane;  // row inside the tile
   const int row = q0 + rl;
   const uint32_t tl = tmem + ((uint32_t)(wq * 32) << 16);
   // valid key columns of this row form one interval [lo, hi): bounds + causal + block-diagonal masks
   int lo = 0, hi = kv_end;
-  if (p.mask == TC_MASK_CAUSAL) hi = min(hi, row + 1);
+  if (p.mask == TC_MASK_CAUSAL) hi = min(hi, row + 1 + (p.s_kv - p.s_q));
   if (p.mask == TC_MASK_BLOCK) { lo = (row / p.mask_block) * p.mask_block; hi = min(hi, lo + p.mask_block); }
-  const int nch = nkv / 32;
-  const int c1 = nch > 4 ? 4 : (nch + 1) / 2;                  // first chunk of the second half
-  const uint32_t P1_COL = 32 * c1;                              // where the second half's packed P starts
-  const uint32_t O0_COL = nch > 4 ? 64 : 128, O1_COL = 192;
-  const int c_lo = half ? c1 : 0, c_hi = half ? nch : c1;       // this thread's 32-column chunks
-  float mx = -CUDART_INF_F;
-  for (int c = c_lo; c < c_hi; ++c) {
-    // tcgen05.ld is .sync.aligned: the skip decision must be warp-uniform
-    if (__all_sync(0xffffffffu, c * 32 >= hi || c * 32 + 32 <= lo)) continue;
-    uint32_t r[32];
-    tmem_ld32(tl + c * 32, r);
-    tmem_ld_wait();
-    if (c * 32 >= lo && c * 32 + 32 <= hi) {           // fully valid: no per-element masking
+
+  float m_run = -CUDART_INF_F, l_run = 0.f;   // running row max (raw scores) and row sum
+  float oacc[LONG ? 2 : 1][LONG ? 32 : 1];    // LONG: this thread's O chunks (chunk c of HD/32 belongs to warpgroup c & 1)
+  if (LONG) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int col = c * 32 + i;
-        if (col >= lo && col < hi) mx = fmaxf(mx, __uint_as_float(r[i]));
-      }
-    }
+    for (int i = 0; i < 32; ++i) { oacc[0][i] = 0.f; oacc[LONG ? 1 : 0][i] = 0.f; }
   }
-  xch[half * 128 + rl] = mx;
-  __syncthreads();
-  mx = fmaxf(mx, xch[(half ^ 1) * 128 + rl]);
-  __syncthreads();  // both halves have read the maxima: the buffer is reused for the sums
-  TDBG(5);
-  const float ms = (mx == -CUDART_INF_F) ? 0.f : mx * p.scale_log2;
-  float lsum = 0.f;
-  for (int c = c_lo; c < c_hi; ++c) {
-    uint32_t pk[16];
-    if (__all_sync(0xffffffffu, c * 32 >= hi || c * 32 + 32 <= lo)) {   // warp-uniform
+  uint32_t O0_COL = 64, O1_COL = 192;
+
+#pragma unroll 1
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int k0 = kb << 8;
+    const int kend_b = min(kv_end - k0, 256);     // valid keys of this block
+    const int nkv = (kend_b + 31) & ~31;          // MMA N / K extent (multiple of 32, <= 256)
+    const uint32_t par = kb & 1;
+    if (LONG && kb > 0) {
+      // every thread has passed bar[1] of the previous block (its S and P V MMAs are complete, so K / V may be
+      // overwritten) and has finished reading its O chunks out of TMEM
+      tc_load256<HD>(k0s, k1s, Mk, k0, nkv, kv_end, p.hd);
+      tc_load256<HD>(v0s, v1s, Mv, k0, nkv, kv_end, p.hd);
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    }
+    // ---- S = Q K^T
+    if (threadIdx.x == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, nkv, 0, 0);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) pk[i] = 0u;
-    } else {
+      for (int ks = 0; ks < HD / 16; ++ks) {
+        uint64_t ad, bd;
+        if (ks < 4) {
+          ad = desc_sw(smem_u32(q0s) + ks * 32, 1024, LAYOUT_SW128);
+          bd = desc_sw(smem_u32(k0s) + ks * 32, 1024, LAYOUT_SW128);
+        } else {
+          ad = desc_sw(smem_u32(q1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
+          bd = desc_sw(smem_u32(k1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
+        }
+        umma_bf16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      }
+      umma_commit(&bar[0]);
+    }
+    TDBG(3);
+    mbar_wait(&bar[0], par);
+    tc_fence_after();
+    TDBG(4);
+
+    // ---- softmax of this block: two threads per query row (= TMEM lane), one per key-column half
+    const int lo_b = lo - k0, hi_b = min(hi - k0, kend_b);   // valid interval in block-local columns
+    const int nch = nkv / 32;
+    const int c1 = nch > 4 ? 4 : (nch + 1) / 2;                  // first chunk of the second half
+    const uint32_t P1_COL = 32 * c1;                              // where the second half's packed P starts
+    O0_COL = nch > 4 ? 64 : 128;
+    const int c_lo = half ? c1 : 0, c_hi = half ? nch : c1;       // this thread's 32-column chunks
+    float mx = -CUDART_INF_F;
+    for (int c = c_lo; c < c_hi; ++c) {
+      // tcgen05.ld is .sync.aligned: the skip decision must be warp-uniform
+      if (__all_sync(0xffffffffu, c * 32 >= hi_b || c * 32 + 32 <= lo_b)) continue;
       uint32_t r[32];
       tmem_ld32(tl + c * 32, r);
       tmem_ld_wait();
-      float pv[32];
-      if (c * 32 >= lo && c * 32 + 32 <= hi) {
+      if (c * 32 >= lo_b && c * 32 + 32 <= hi_b) {           // fully valid: no per-element masking
 #pragma unroll
-        for (int i = 0; i < 32; ++i) pv[i] = exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -ms));
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int col = c * 32 + i;
-          pv[i] = (col >= lo && col < hi) ? exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -ms)) : 0.f;
+          if (col >= lo_b && col < hi_b) mx = fmaxf(mx, __uint_as_float(r[i]));
         }
       }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) lsum += pv[i];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
     }
-    // P (bf16 pairs) overwrites S columns this thread has already consumed
-    tmem_st16(tl + half * P1_COL + (c - c_lo) * 16, pk);
-  }
-  xch[half * 128 + rl] = lsum;
-  TDBG(6);
-  tmem_st_wait();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  lsum += xch[(half ^ 1) * 128 + rl];
-  TDBG(7);
+    xch[half * 128 + rl] = mx;
+    __syncthreads();
+    mx = fmaxf(mx, xch[(half ^ 1) * 128 + rl]);
+    __syncthreads();  // both halves have read the maxima: the buffer is reused for the sums
+    TDBG(5);
+    const float m_new = fmaxf(m_run, mx);
+    const float ms = (m_new == -CUDART_INF_F) ? 0.f : m_new * p.scale_log2;
+    // re-scaling factor of what has been accumulated so far (online softmax; 1 block: unused)
+    const float alpha = (m_run == -CUDART_INF_F) ? 0.f : exp2f(fmaf(m_run, p.scale_log2, -ms));
+    float lsum = 0.f;
+    for (int c = c_lo; c < c_hi; ++c) {
+      uint32_t pk[16];
+      if (__all_sync(0xffffffffu, c * 32 >= hi_b || c * 32 + 32 <= lo_b)) {   // warp-uniform
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+      } else {
+        uint32_t r[32];
+        tmem_ld32(tl + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+        if (c * 32 >= lo_b && c * 32 + 32 <= hi_b) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pv[i] = exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -ms));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = c * 32 + i;
+            pv[i] = (col >= lo_b && col < hi_b) ? exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -ms)) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) lsum += pv[i];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+      }
+      // P (bf16 pairs) overwrites S columns this thread has already consumed
+      tmem_st16(tl + half * P1_COL + (c - c_lo) * 16, pk);
+    }
+    xch[half * 128 + rl] = lsum;
+    TDBG(6);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    lsum += xch[(half ^ 1) * 128 + rl];
+    l_run = l_run * alpha + lsum;
+    m_run = m_new;
+    TDBG(7);
 
-  // ---- O = P V   (A = P from TMEM, B = V MN-major): thread 0 issues the 64-column part, thread 32 the rest
-  if (threadIdx.x == 0 || (TWO && threadIdx.x == 32)) {
-    const bool second = threadIdx.x == 32;
-    const uint32_t idesc = second ? make_idesc_bf16(128, 32, 0, 1) : make_idesc_bf16(128, 64, 0, 1);
-    const uint32_t ocol = tmem + (second ? O1_COL : O0_COL);
-    const uint32_t vb = smem_u32(second ? v1s : v0s);
-    const int nks = nkv / 16;
-    for (int ks = 0; ks < nks; ++ks) {
-      const uint32_t acol = tmem + (ks < 2 * c1 ? ks * 8 : P1_COL + (ks - 2 * c1) * 8);  // 16 keys = 8 packed columns
-      umma_ts(ocol, acol, second ? desc_sw(vb + ks * 1024, 512, LAYOUT_SW64) : desc_sw(vb + ks * 2048, 1024, LAYOUT_SW128), idesc,
-              ks > 0 ? 1u : 0u);
+    // ---- O = P V   (A = P from TMEM, B = V MN-major): thread 0 issues the 64-column part, thread 32 the rest
+    if (threadIdx.x == 0 || (TWO && threadIdx.x == 32)) {
+      const bool second = threadIdx.x == 32;
+      const uint32_t idesc = second ? make_idesc_bf16(128, 32, 0, 1) : make_idesc_bf16(128, 64, 0, 1);
+      const uint32_t ocol = tmem + (second ? O1_COL : O0_COL);
+      const uint32_t vb = smem_u32(second ? v1s : v0s);
+      const int nks = nkv / 16;
+      for (int ks = 0; ks < nks; ++ks) {
+        const uint32_t acol = tmem + (ks < 2 * c1 ? ks * 8 : P1_COL + (ks - 2 * c1) * 8);  // 16 keys = 8 packed columns
+        umma_ts(ocol, acol, second ? desc_sw(vb + ks * 1024, 512, LAYOUT_SW64) : desc_sw(vb + ks * 2048, 1024, LAYOUT_SW128), idesc,
+                ks > 0 ? 1u : 0u);
+      }
+      umma_commit(&bar[1]);
     }
-    umma_commit(&bar[1]);
+    TDBG(8);
+    mbar_wait(&bar[1], par);
+    tc_fence_after();
+    TDBG(9);
+    if (LONG) {
+      // O_acc = O_acc * alpha + (P V of this block), kept in registers across the key blocks
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        if ((c & 1) != half) continue;
+        uint32_t r[32];
+        tmem_ld32(tl + (c < 2 ? O0_COL + c * 32 : O1_COL), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) oacc[LONG ? (c >> 1) : 0][LONG ? i : 0] = fmaf(oacc[LONG ? (c >> 1) : 0][LONG ? i : 0], alpha, __uint_as_float(r[i]));
+      }
+    }
   }
-  TDBG(8);
-  mbar_wait(&bar[1], 0);
-  tc_fence_after();
-  TDBG(9);
 
   // ---- epilogue: 32-column chunk c of O is read by warpgroup c & 1
-  const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+  const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
   const bool valid = row < sq;
   __nv_bfloat16* orow = nullptr;
   if (valid) {
@@ -355,22 +377,31 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) 
 #pragma unroll
   for (int c = 0; c < HD / 32; ++c) {
     if ((c & 1) != half) continue;
-    uint32_t r[32];
-    tmem_ld32(tl + (c < 2 ? O0_COL + c * 32 : O1_COL), r);
-    tmem_ld_wait();
+    float f[32];
+    if (LONG) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = oacc[LONG ? (c >> 1) : 0][LONG ? i : 0];
+    } else {
+      uint32_t r[32];
+      tmem_ld32(tl + (c < 2 ? O0_COL + c * 32 : O1_COL), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
+    }
     if (valid) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+        if (c * 32 + j * 8 >= p.hd) break;   // padded head_dim columns are not stored
         uint4 o;
-        o.x = pack_bf16(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-        o.y = pack_bf16(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-        o.z = pack_bf16(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-        o.w = pack_bf16(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+        o.x = pack_bf16(f[8 * j + 0] * inv, f[8 * j + 1] * inv);
+        o.y = pack_bf16(f[8 * j + 2] * inv, f[8 * j + 3] * inv);
+        o.z = pack_bf16(f[8 * j + 4] * inv, f[8 * j + 5] * inv);
+        o.w = pack_bf16(f[8 * j + 6] * inv, f[8 * j + 7] * inv);
         *reinterpret_cast<uint4*>(orow + c * 32 + j * 8) = o;
       }
     }
   }
-  if (valid && half == 0 && p.lse) p.lse[((size_t)s * p.n_heads + h) * p.s_q + row] = mx * p.scale + logf(lsum);
+  if (valid && half == 0 && p.lse) p.lse[((size_t)s * p.n_heads + h) * p.s_q + row] = m_run * p.scale + logf(l_run);
   TDBG(10);
   tc_fence_before();
   __syncthreads();
@@ -381,7 +412,8 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) 
 }
 
 // ======================================================================================================
-// tcgen05 attention backward for s_q, s_kv <= 256.  One CTA (256 threads) = one (sequence, head).
+// tcgen05 attention backward, any s_kv, s_q <= 2048 (per-query statistics live in shared memory).
+// One CTA (256 threads) = one (sequence, head).
 // Everything is computed in the TRANSPOSED frame (TMEM lane = key row, TMEM column = query row) so that
 // P^T and dS^T feed the dV / dK MMAs straight from TMEM:
 //   for key block j (128 keys):  load K_j, V_j
@@ -391,8 +423,9 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) 
 //              written back over consumed S^T / dP^T columns, dS^T additionally into smem)
 //       dV_j += P^T dO_i,  dK_j += dS^T Q_i                 (A from TMEM, B = the same dO_i / Q_i tiles MN-major)
 //       dQ_i(j) = dS K_j                                    (A = dS^T tile read MN-major, B = K_j MN-major)
-//       dQ_i: the first key block's partial is parked (bf16, unscaled) in the dq rows themselves; the thread
-//             that wrote it reads it back, adds the last key block's partial and stores the result
+//       dQ_i: the running partial over the key blocks seen so far is parked (bf16, unscaled) in the dq rows
+//             themselves; every later key block reads it back (coalesced), adds its own partial and parks
+//             it again - the last one applies the softmax scale
 //     Q_i / dO_i tiles are double-buffered: the next step's tiles are fetched behind the current MMAs
 //     store dK_j (x scale), dV_j
 // delta = rowsum(dO o O) is computed in the prologue; no global workspace, no atomics, deterministic.
@@ -408,6 +441,7 @@ struct AttnTcBwdParams {
   int n_seq, n_heads, s_q, s_kv, mask;
   long total_rows;
   float scale_log2, scale;
+  int hd;  // real head_dim (<= HD), see AttnTcParams
 };
 
 __device__ __forceinline__ float ex2_fast(float x) {
@@ -429,7 +463,7 @@ __device__ __forceinline__ uint64_t desc_sw_lbo(uint32_t saddr, uint32_t lbo, ui
 // Row-staging buffers ([128 rows][HD*2 + 16 B], the pad spreads the banks) make every global access of
 // the dQ / dK / dV outputs coalesced: 4 consecutive lanes move 64 contiguous bytes of one row.
 template <int HD>
-__device__ __forceinline__ void tc_rows_store256(const uint8_t* stage, const TcMat& m, int r0, int n_valid) {
+__device__ __forceinline__ void tc_rows_store256(const uint8_t* stage, const TcMat& m, int r0, int n_valid, int hd) {
   constexpr int PITCH = HD * 2 + 16, CPT = HD / 32;
   const int rl = threadIdx.x >> 2, c0 = threadIdx.x & 3;
 #pragma unroll
@@ -440,13 +474,13 @@ __device__ __forceinline__ void tc_rows_store256(const uint8_t* stage, const TcM
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
         const int c = c0 + 4 * j;
-        *reinterpret_cast<uint4*>(g + c * 8) = *reinterpret_cast<const uint4*>(stage + r * PITCH + c * 16);
+        if (c * 8 < hd) *reinterpret_cast<uint4*>(g + c * 8) = *reinterpret_cast<const uint4*>(stage + r * PITCH + c * 16);
       }
     }
   }
 }
 template <int HD>
-__device__ __forceinline__ void tc_rows_load256(uint8_t* stage, const TcMat& m, int r0, int n_valid) {
+__device__ __forceinline__ void tc_rows_load256(uint8_t* stage, const TcMat& m, int r0, int n_valid, int hd) {
   constexpr int PITCH = HD * 2 + 16, CPT = HD / 32;
   const int rl = threadIdx.x >> 2, c0 = threadIdx.x & 3;
 #pragma unroll
@@ -457,7 +491,7 @@ __device__ __forceinline__ void tc_rows_load256(uint8_t* stage, const TcMat& m, 
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
         const int c = c0 + 4 * j;
-        cp16(stage + r * PITCH + c * 16, g + c * 8);
+        if (c * 8 < hd) cp16(stage + r * PITCH + c * 16, g + c * 8);
       }
     }
   }
@@ -485,8 +519,8 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
   uint8_t* q1s = v1s + T1;
   uint8_t* d1s = q1s + 2 * T1;
   uint8_t* pst = d1s + 2 * T1;            // [128][PITCH] row staging: parked dQ read-back, dK store
-  float2* stats = reinterpret_cast<float2*>(pst + 128 * PITCH);  // [256] (lse * log2e, delta)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(stats + 256);  // [2]
+  float2* stats = reinterpret_cast<float2*>(pst + 128 * PITCH);  // [round128(s_q)] (lse * log2e, delta)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stats + ((p.s_q + 127) & ~127));  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -518,15 +552,14 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
   const TcMat Mdo = tc_mat(p.dout, p.mdo, s, p.lddo, h * p.hsdo);
   const TcMat Mdq = tc_mat(p.dq, p.mdq, s, p.lddq, h * p.hsdq);
   // the first tiles are in flight while the per-query statistics are computed
-  tc_load256<HD>(k0s, k1s, Mk, 0, 128, skv);
-  tc_load256<HD>(v0s, v1s, Mv, 0, 128, skv);
+  tc_load256<HD>(k0s, k1s, Mk, 0, 128, skv, p.hd);
+  tc_load256<HD>(v0s, v1s, Mv, 0, 128, skv, p.hd);
   {
     const int nq0 = min(128, (sq + 31) & ~31);
-    tc_load256<HD>(q0s, q1s, Mq, 0, nq0, sq);
-    tc_load256<HD>(d0s, d1s, Mdo, 0, nq0, sq);
+    tc_load256<HD>(q0s, q1s, Mq, 0, nq0, sq, p.hd);
+    tc_load256<HD>(d0s, d1s, Mdo, 0, nq0, sq, p.hd);
   }
-  {
-    const int r = threadIdx.x;
+  for (int r = threadIdx.x; r < nqb * 128; r += 256) {
     float2 st = make_float2(1e30f, 0.f);  // rows that do not exist: P = exp2(x - 1e30) = 0
     if (r < sq) {
       const TcMat Mo = tc_mat(p.o, p.mo, s, p.ldo, h * p.hso);
@@ -535,6 +568,7 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
       float acc = 0.f;
 #pragma unroll
       for (int c = 0; c < HD / 8; ++c) {
+        if (c * 8 >= p.hd) break;
         const uint4 a = __ldg(po + c), b = __ldg(pd + c);
         acc += bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) + bf16_hi(a.y) * bf16_hi(b.y) +
                bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) + bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
@@ -557,8 +591,8 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
     const int kj0 = j * 128;
     const int nk = min(128, (skv - kj0 + 31) & ~31);  // key extent of this block used as an MMA K dimension
     if (j > 0) {  // every MMA that read the previous key block has completed (bar[1] of its last step)
-      tc_load256<HD>(k0s, k1s, Mk, kj0, 128, skv);
-      tc_load256<HD>(v0s, v1s, Mv, kj0, 128, skv);
+      tc_load256<HD>(k0s, k1s, Mk, kj0, 128, skv, p.hd);
+      tc_load256<HD>(v0s, v1s, Mv, kj0, 128, skv, p.hd);
     }
     const int i0 = causal ? j : 0;
     for (int i = i0; i < nqb; ++i, ++it) {
@@ -602,15 +636,15 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
         if (ni >= nqb) { nj = j + 1; ni = causal ? nj : 0; }
         if (nj < nkb && ni < nqb) {
           const int nqn = min(128, (sq - ni * 128 + 31) & ~31);
-          tc_load256<HD>(q0s + (sb ^ 1) * T0, q1s + (sb ^ 1) * T1, Mq, ni * 128, nqn, sq);
-          tc_load256<HD>(d0s + (sb ^ 1) * T0, d1s + (sb ^ 1) * T1, Mdo, ni * 128, nqn, sq);
+          tc_load256<HD>(q0s + (sb ^ 1) * T0, q1s + (sb ^ 1) * T1, Mq, ni * 128, nqn, sq, p.hd);
+          tc_load256<HD>(d0s + (sb ^ 1) * T0, d1s + (sb ^ 1) * T1, Mdo, ni * 128, nqn, sq, p.hd);
         }
       }
-      // ---- dQ bookkeeping: the first key block's partial is parked (bf16, unscaled) in the dq output rows
-      // themselves; the step that processes the last contributing key block reads it back (coalesced) into pst
+      // ---- dQ bookkeeping: the partial over key blocks 0..j-1 is parked (bf16, unscaled) in the dq output rows
+      // themselves; every later key block reads it back (coalesced) into pst and adds its own
       const int jl = causal ? min(i, nkb - 1) : nkb - 1;
       const bool last_kb = (j == jl);
-      if (j > 0 && last_kb) tc_rows_load256<HD>(pst, Mdq, qi0, sq);
+      if (j > 0) tc_rows_load256<HD>(pst, Mdq, qi0, sq, p.hd);
       TDBG(14);
       mbar_wait(&bar[0], it & 1);
       tc_fence_after();
@@ -689,7 +723,7 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
 
       // ---- dQ_i: TMEM lane = query row; chunk c of HD/32 handled by warpgroup c & 1.  The rows are staged in
       // the (now idle) dS area and stored with coalesced 16-byte accesses.
-      if (j > 0 && last_kb) {
+      if (j > 0) {
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();  // parked rows were fetched by other threads
       }
@@ -706,7 +740,7 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[8 * g + e]);
-            if (j > 0 && last_kb) {
+            if (j > 0) {
               const uint4 q4 = *reinterpret_cast<const uint4*>(pst + kr * PITCH + c * 64 + g * 16);
               f[0] += bf16_lo(q4.x); f[1] += bf16_hi(q4.x); f[2] += bf16_lo(q4.y); f[3] += bf16_hi(q4.y);
               f[4] += bf16_lo(q4.z); f[5] += bf16_hi(q4.z); f[6] += bf16_lo(q4.w); f[7] += bf16_hi(q4.w);
@@ -718,7 +752,7 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
       }
       tc_fence_before();
       __syncthreads();
-      tc_rows_store256<HD>(dss, Mdq, qi0, sq);
+      tc_rows_store256<HD>(dss, Mdq, qi0, sq, p.hd);
     }
     TDBG(20);
     // ---- dV_j (warpgroup 0, staged in the dS area) and dK_j x scale (warpgroup 1, staged in pst)
@@ -741,8 +775,8 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
       __syncthreads();
       const TcMat Mdv = tc_mat(p.dv, p.mdkv, s, p.lddv, h * p.hsdv);
       const TcMat Mdk = tc_mat(p.dk, p.mdkv, s, p.lddk, h * p.hsdk);
-      tc_rows_store256<HD>(dss, Mdv, kj0, skv);
-      tc_rows_store256<HD>(pst, Mdk, kj0, skv);
+      tc_rows_store256<HD>(dss, Mdv, kj0, skv, p.hd);
+      tc_rows_store256<HD>(pst, Mdk, kj0, skv, p.hd);
     }
   }
   TDBG(21);
@@ -763,25 +797,33 @@ static TcSeqMap tc_map(const ymp_seqmap& m) {
   return r;
 }
 
-template <int HD>
+template <int HD, bool LONG>
 static int launch_tc(const AttnTcParams& p, cudaStream_t st) {
   const int kvr = p.kv_rows;
   const int smem = 128 * 128 + 2 * kvr * 128 + (HD == 96 ? 128 * 64 + 2 * kvr * 64 : 0) + 1024 + 64 + 1024;
   static int cur = 0;
-  if (smem > cur) { YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cur = smem; }
+  if (smem > cur) {
+    YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<HD, LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cur = smem;
+  }
   dim3 grid((p.s_q + 127) / 128, p.n_heads, p.n_seq);
-  attn_tc_fwd_kernel<HD><<<grid, 256, smem, st>>>(p);
+  attn_tc_fwd_kernel<HD, LONG><<<grid, 256, smem, st>>>(p);
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }
 
+static bool tc_head_dim(int hd) { return hd == 64 || hd == 80 || hd == 88 || hd == 96; }
+
 // Returns YMP_ENOSUP (without setting an error) when the configuration is outside this kernel's domain.
 int attn_tc_fwd_try(const ymp_attn_args* a, cudaStream_t st) {
-  if (!(a->head_dim == 64 || a->head_dim == 96) || a->s_kv > 256) return YMP_ENOSUP;
+  if (!tc_head_dim(a->head_dim)) return YMP_ENOSUP;
+  // a handful of query rows against a long cache (single-token decoding) is an HBM-bound GEMV: the 16-row
+  // mma.sync tiles waste far less than a 128-row tcgen05 tile would
+  if (a->s_q < 16 && a->s_kv > 256) return YMP_ENOSUP;
   // packed block-diagonal (temporal) sequences use 1/8 of each score tile: the mma.sync kernel,
   // which skips the masked chunks per warp, measured faster there (0.113 vs 0.128 ms)
   if (a->mask == YMP_MASK_BLOCK) return YMP_ENOSUP;
-  if (a->q_head_stride % 8 || a->ldo % 8 || a->o_head_stride % 8) return YMP_ENOSUP;
+  if (a->q_head_stride % 8 || a->k_head_stride % 8 || a->v_head_stride % 8 || a->ldo % 8 || a->o_head_stride % 8) return YMP_ENOSUP;
   AttnTcParams p = {};
   p.q = (const __nv_bfloat16*)a->q; p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v;
   p.o = (__nv_bfloat16*)a->o; p.lse = a->lse;
@@ -791,15 +833,18 @@ int attn_tc_fwd_try(const ymp_attn_args* a, cudaStream_t st) {
   p.n_seq = a->n_seq; p.n_heads = a->n_heads; p.s_q = a->s_q; p.s_kv = a->s_kv;
   p.mask = a->mask; p.mask_block = a->mask_block > 0 ? a->mask_block : 1; p.total_rows = a->total_rows;
   p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
-  p.kv_rows = (a->s_kv + 31) & ~31;
-  return a->head_dim == 64 ? launch_tc<64>(p, st) : launch_tc<96>(p, st);
+  p.hd = a->head_dim;
+  const bool lng = a->s_kv > 256;
+  p.kv_rows = lng ? 256 : ((a->s_kv + 31) & ~31);
+  if (a->head_dim == 64) return lng ? launch_tc<64, true>(p, st) : launch_tc<64, false>(p, st);
+  return lng ? launch_tc<96, true>(p, st) : launch_tc<96, false>(p, st);
 }
 
 template <int HD>
 static int launch_tc_bwd(const AttnTcBwdParams& p, cudaStream_t st) {
-  const int smem = 8 * 16384 + (HD == 96 ? 6 * 8192 : 0) + 128 * (HD * 2 + 16) + 256 * 8 + 64 + 1024;
-  static bool set = false;
-  if (!set) { YMP_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+  const int smem = 8 * 16384 + (HD == 96 ? 6 * 8192 : 0) + 128 * (HD * 2 + 16) + ((p.s_q + 127) & ~127) * 8 + 64 + 1024;
+  static int cur = 0;
+  if (smem > cur) { YMP_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cur = smem; }
   dim3 grid(p.n_heads, p.n_seq);
   attn_tc_bwd_kernel<HD><<<grid, 256, smem, st>>>(p);
   YMP_LAUNCH_CHECK();
@@ -809,10 +854,10 @@ static int launch_tc_bwd(const AttnTcBwdParams& p, cudaStream_t st) {
 // Backward counterpart of attn_tc_fwd_try: YMP_ENOSUP when outside the kernel's domain.
 int attn_tc_bwd_try(const ymp_attn_bwd_args* b, cudaStream_t st) {
   const ymp_attn_args* a = &b->fwd;
-  if (!(a->head_dim == 64 || a->head_dim == 96) || a->s_kv > 256 || a->s_q > 256) return YMP_ENOSUP;
+  if (!tc_head_dim(a->head_dim) || a->s_q > 2048) return YMP_ENOSUP;
   if (a->mask == YMP_MASK_BLOCK) return YMP_ENOSUP;
   if (a->mask == YMP_MASK_CAUSAL && a->s_q != a->s_kv) return YMP_ENOSUP;
-  if (a->q_head_stride % 8 || a->ldo % 8 || a->o_head_stride % 8 || b->do_head_stride % 8 || b->dq_head_stride % 8 ||
+  if (a->q_head_stride % 8 || a->k_head_stride % 8 || a->v_head_stride % 8 || a->ldo % 8 || a->o_head_stride % 8 || b->do_head_stride % 8 || b->dq_head_stride % 8 ||
       b->dk_head_stride % 8 || b->dv_head_stride % 8)
     return YMP_ENOSUP;
   AttnTcBwdParams p = {};
@@ -828,6 +873,7 @@ int attn_tc_bwd_try(const ymp_attn_bwd_args* b, cudaStream_t st) {
   p.n_seq = a->n_seq; p.n_heads = a->n_heads; p.s_q = a->s_q; p.s_kv = a->s_kv;
   p.mask = a->mask; p.total_rows = a->total_rows;
   p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.hd = a->head_dim;
   return a->head_dim == 64 ? launch_tc_bwd<64>(p, st) : launch_tc_bwd<96>(p, st);
 }
 

@@ -36,6 +36,8 @@ struct GemmKParams {
   int n_fast;                      // tile order: consecutive units walk N first (A streamed once) or M first
   bool v32_d, v32_aux, v32_res, v32_bias;  // 32-byte aligned -> 256-bit accesses
   float alpha;
+  int epi_tma;                     // CTA-pair kernel: outputs staged in swizzled smem and written by TMA (bulk tensor
+                                   // store; bulk reduce-add for the fp32 split-K accumulation)
 };
 
 template <int BN>
@@ -259,6 +261,115 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
   }
 }
 
+// ---------------------------------------------------------------- TMA epilogue (CTA-pair kernel)
+// Every epilogue warp owns two 4 KB staging buffers [32 rows][128 B] in the SWIZZLE_128B layout of the output
+// tensor maps.  A lane (= accumulator row) writes its 16-byte chunks at chunk ^ (row & 7): conflict-free for the
+// row-per-lane TMEM read-out, and the bulk tensor store turns it into full 128-byte row segments in HBM - instead
+// of one 32-byte sector per lane per store instruction (l1tex-bound: profiles/r01_ncu_full_summary.md).
+constexpr int EPI_BUF_BYTES = 32 * 128;
+constexpr int EPI_SMEM_BYTES = NUM_EPI_WARPS * 2 * EPI_BUF_BYTES;
+
+__device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// The arithmetic of epilogue_chunk for one full 32-column chunk, in place on the accumulator registers:
+// pre-activation (alpha, bias), then either the whole epilogue (epilogue_post: no aux_out) or, 8 columns at a
+// time, the activation together with its derivative (epilogue_act8) - keeping the two results of all 32 columns
+// live at once would spill.
+__device__ __forceinline__ void epilogue_pre(const GemmKParams& p, uint32_t (&r)[32], const EpiPrefetch& pf) {
+  if (p.alpha != 1.0f) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * p.alpha);
+  }
+  if (p.bias) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      r[2 * i] = __float_as_uint(__uint_as_float(r[2 * i]) + bf16_lo(pf.bias[i]));
+      r[2 * i + 1] = __float_as_uint(__uint_as_float(r[2 * i + 1]) + bf16_hi(pf.bias[i]));
+    }
+  }
+}
+__device__ __forceinline__ void epilogue_post(const GemmKParams& p, uint32_t (&r)[32], const EpiPrefetch& pf) {
+  if (p.aux_in) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      r[2 * i] = __float_as_uint(__uint_as_float(r[2 * i]) * bf16_lo(pf.aux[i]));
+      r[2 * i + 1] = __float_as_uint(__uint_as_float(r[2 * i + 1]) * bf16_hi(pf.aux[i]));
+    }
+  } else if (p.act == YMP_ACT_GELU_ERF) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(gelu_erf(__uint_as_float(r[i])));
+  } else if (p.act == YMP_ACT_GELU_TANH) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(gelu_tanh(__uint_as_float(r[i])));
+  }
+  if (p.residual) {
+    if (p.res_f32) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(pf.res[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        r[2 * i] = __float_as_uint(__uint_as_float(r[2 * i]) + bf16_lo(pf.res[i]));
+        r[2 * i + 1] = __float_as_uint(__uint_as_float(r[2 * i + 1]) + bf16_hi(pf.res[i]));
+      }
+    }
+  }
+}
+// columns [8j, 8j+8) of a chunk: value and aux (act' or, without an activation, the value) as packed bf16
+__device__ __forceinline__ void epilogue_act8(const GemmKParams& p, const uint32_t (&r)[32], const EpiPrefetch& pf, int j,
+                                              uint32_t (&vo)[4], uint32_t (&ao)[4]) {
+  float v[8], d[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float x = __uint_as_float(r[8 * j + e]);
+    if (p.act == YMP_ACT_GELU_ERF) v[e] = gelu_erf_both(x, d[e]);
+    else if (p.act == YMP_ACT_GELU_TANH) v[e] = gelu_tanh_both(x, d[e]);
+    else { v[e] = x; d[e] = x; }
+  }
+  if (p.residual) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = 8 * j + e;
+      v[e] += p.res_f32 ? __uint_as_float(pf.res[i]) : ((i & 1) ? bf16_hi(pf.res[i >> 1]) : bf16_lo(pf.res[i >> 1]));
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { vo[e] = pack_bf16(v[2 * e], v[2 * e + 1]); ao[e] = pack_bf16(d[2 * e], d[2 * e + 1]); }
+}
+// 32 bf16 values of lane-row `lr` into 16-byte chunks [cbase, cbase+4) of its 128-byte row
+__device__ __forceinline__ void stage_bf16(uint8_t* buf, int lr, int cbase, const uint32_t (&f)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    st_shared_v4(buf + lr * 128 + (((cbase + j) ^ (lr & 7)) << 4),
+                 pack_bf16(__uint_as_float(f[8 * j]), __uint_as_float(f[8 * j + 1])),
+                 pack_bf16(__uint_as_float(f[8 * j + 2]), __uint_as_float(f[8 * j + 3])),
+                 pack_bf16(__uint_as_float(f[8 * j + 4]), __uint_as_float(f[8 * j + 5])),
+                 pack_bf16(__uint_as_float(f[8 * j + 6]), __uint_as_float(f[8 * j + 7])));
+}
+__device__ __forceinline__ void stage_f32(uint8_t* buf, int lr, const uint32_t (&f)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    st_shared_v4(buf + lr * 128 + ((j ^ (lr & 7)) << 4), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
@@ -432,10 +543,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
 // L2->SM traffic per flop drops by a third.  The leader CTA issues all MMAs; completion is multicast
 // to both CTAs' mbarriers; both CTAs run their own producer and epilogue warps.
 constexpr int BN2 = 256;
-constexpr int NSTAGE2 = 6;
+constexpr int NSTAGE2 = 5;   // 5 x 32 KB operand stages + 64 KB of epilogue staging = 225 KB of the 227 KB per SM
 constexpr int B2_STAGE_BYTES = (BN2 / 2) * BK * 2;
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;
-constexpr int SMEM2_BYTES = NSTAGE2 * STAGE2_BYTES + 256 + 1024;
+constexpr int SMEM2_BYTES = NSTAGE2 * STAGE2_BYTES + EPI_SMEM_BYTES + 256 + 1024;
 
 #ifdef YMP_GEMM_DBG
 // [0] MMA warp: total cycles, [1] waiting for a free accumulator, [2] waiting for smem stages, [3] tiles
@@ -446,15 +557,19 @@ __device__ unsigned long long ymp_gemm_dbg_buf[16];
 #define GDBG_T() 0ll
 #endif
 
+template <bool TMA_EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
-                              const __grid_constant__ CUtensorMap tma_b, const GemmKParams p) {
+                              const __grid_constant__ CUtensorMap tma_b,
+                              const __grid_constant__ CUtensorMap tma_d,
+                              const __grid_constant__ CUtensorMap tma_aux, const GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + NSTAGE2 * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGE2 * STAGE2_BYTES);
+  uint8_t* smem_epi = smem + NSTAGE2 * STAGE2_BYTES;   // 1024-byte aligned: SWIZZLE_128B staging buffers
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + EPI_SMEM_BYTES);
   uint64_t* empty_bar = full_bar + NSTAGE2;
   uint64_t* tfull_bar = empty_bar + NSTAGE2;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -473,6 +588,10 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (TMA_EPI) {
+      tma_prefetch_desc(&tma_d);
+      if (p.aux_out) tma_prefetch_desc(&tma_aux);
+    }
   }
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < NSTAGE2; ++i) {
@@ -587,6 +706,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
     constexpr int CHUNKS = BN2 / 2 / 32;
     int as = 0;
     uint32_t aphase = 0;
+    uint32_t ebox = 0;   // running count of this warp's bulk stores (staging buffer parity)
     for (int u = pair; u < num_units; u += num_pairs) {
       const int t = u / p.split_k;
       const int m0 = (p.n_fast ? t / num_n : t % num_m) * 2 * BM + (int)rank * BM;
@@ -601,6 +721,83 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
       if (blockIdx.x == 0 && warp_idx == 4 && lane == 0) ymp_gemm_dbg_buf[5] += te1 - te0;
 #endif
       const int row = m0 + q * 32 + lane;
+      if constexpr (TMA_EPI) {
+        // ---- outputs staged in swizzled smem, written by bulk tensor stores (one box = 32 rows x 128 bytes)
+        uint8_t* ebuf = smem_epi + (warp_idx - 4) * 2 * EPI_BUF_BYTES;
+        const int row0 = m0 + q * 32;
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS; ++c) {
+          const int coff = half * (BN2 / 2) + c * 32;
+          const int col0 = n_blk * BN2 + coff;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN2 + coff), r);
+          EpiPrefetch pf;
+          epilogue_prefetch(p, row, col0, pf);
+          tmem_ld_wait();
+          if (c == CHUNKS - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // always on the leader's barrier
+          }
+          epilogue_pre(p, r, pf);
+          if (!p.aux_out) epilogue_post(p, r, pf);
+          if (p.out_f32) {
+            // one box per chunk (32 fp32 columns = 128 bytes per row); the two buffers alternate
+            uint8_t* buf = ebuf + (ebox & 1) * EPI_BUF_BYTES;
+            if (lane == 0) bulk_wait_read<1>();   // the store issued two boxes ago has finished reading this buffer
+            __syncwarp();
+            stage_f32(buf, lane, r);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.accumulate) tma_reduce_add_2d(&tma_d, buf, col0, row0);
+              else tma_store_2d(&tma_d, buf, col0, row0);
+              bulk_commit();
+            }
+            ++ebox;
+          } else if (p.aux_out) {
+            // two bf16 outputs (activation and act'): D through buffer 0, aux_out through buffer 1, one box each per
+            // pair of chunks (64 bf16 columns = 128 bytes per row)
+            if ((c & 1) == 0) {
+              if (lane == 0) bulk_wait_read<0>();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t vo[4], ao[4];
+              epilogue_act8(p, r, pf, j, vo, ao);
+              const int off = lane * 128 + ((((c & 1) * 4 + j) ^ (lane & 7)) << 4);
+              st_shared_v4(ebuf + off, vo[0], vo[1], vo[2], vo[3]);
+              st_shared_v4(ebuf + EPI_BUF_BYTES + off, ao[0], ao[1], ao[2], ao[3]);
+            }
+            if (c & 1) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tma_d, ebuf, col0 - 32, row0);
+                tma_store_2d(&tma_aux, ebuf + EPI_BUF_BYTES, col0 - 32, row0);
+                bulk_commit();
+              }
+            }
+          } else {
+            uint8_t* buf = ebuf + (ebox & 1) * EPI_BUF_BYTES;
+            if ((c & 1) == 0) {
+              if (lane == 0) bulk_wait_read<1>();
+              __syncwarp();
+            }
+            stage_bf16(buf, lane, (c & 1) * 4, r);
+            if (c & 1) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tma_d, buf, col0 - 32, row0);
+                bulk_commit();
+              }
+              ++ebox;
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         const int coff = half * (BN2 / 2) + c * 32;
@@ -616,11 +813,13 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
         }
         epilogue_chunk(p, r, row, n_blk * BN2 + coff, pf);
       }
+      }
 #ifdef YMP_GEMM_DBG
       if (blockIdx.x == 0 && warp_idx == 4 && lane == 0) ymp_gemm_dbg_buf[6] += GDBG_T() - te1;
 #endif
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (TMA_EPI && lane == 0) bulk_wait_all();   // staged rows are read asynchronously: drain before smem goes away
   }
 
   tc_fence_before();
@@ -672,6 +871,23 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t ou
   return YMP_OK;
 }
 
+// 2D output tensor map (bf16 or fp32), box = 128 bytes x 32 rows, SWIZZLE_128B
+static int make_out_map(CUtensorMap* m, const void* ptr, bool f32, uint64_t inner, uint64_t outer, uint64_t ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(YMP_ECUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {f32 ? 32u : 64u, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(YMP_ECUDA, "cuTensorMapEncodeTiled (output) failed (%d): inner=%llu outer=%llu ld=%llu", (int)r,
+                     (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+  return YMP_OK;
+}
+
 template <int BN>
 static int launch_gemm(const ymp_gemm_args* a, const GemmKParams& kp, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -698,9 +914,23 @@ static int launch_gemm(const ymp_gemm_args* a, const GemmKParams& kp, cudaStream
   return YMP_OK;
 }
 
-static int launch_gemm_2cta(const ymp_gemm_args* a, const GemmKParams& kp, cudaStream_t stream) {
-  CUtensorMap ta, tb;
+static int launch_gemm_2cta(const ymp_gemm_args* a, GemmKParams kp, cudaStream_t stream) {
+  CUtensorMap ta, tb, td, tx;
   int rc;
+  // TMA epilogue: plain row mapping, whole 64-column boxes, 16-byte aligned rows
+  static const bool no_tma_epi = [] { const char* e = getenv("YMP_GEMM_LEGACY_EPI"); return e && e[0] == '1'; }();
+  const bool f32 = a->out_dtype == YMP_DT_F32;
+  kp.epi_tma = (!no_tma_epi && a->N % 64 == 0 && a->d_row_block == 0 && (a->ldd * (f32 ? 4 : 2)) % 16 == 0 &&
+                !(f32 && a->aux_out)) ? 1 : 0;
+  if (kp.epi_tma) {
+    rc = make_out_map(&td, a->D, f32, a->N, a->M, a->ldd);
+    if (rc) return rc;
+    if (a->aux_out) {
+      rc = make_out_map(&tx, a->aux_out, false, a->N, a->M, a->ldd);
+      if (rc) return rc;
+    }
+  }
+
   if (!a->a_mn_major) rc = make_map(&ta, a->A, a->K, a->M, a->lda, BK, BM);
   else rc = make_map(&ta, a->A, a->M, a->K, a->lda, 64, BK);
   if (rc) return rc;
@@ -709,13 +939,20 @@ static int launch_gemm_2cta(const ymp_gemm_args* a, const GemmKParams& kp, cudaS
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
     attr_set = true;
   }
   const int num_m = (a->M + 2 * BM - 1) / (2 * BM), num_n = (a->N + BN2 - 1) / BN2;
   const int units = num_m * num_n * kp.split_k;
   const int pairs = min(units, num_sms() / 2);
-  gemm_bf16_tcgen05_2cta_kernel<<<2 * pairs, GEMM_THREADS, SMEM2_BYTES, stream>>>(ta, tb, kp);
+  if (!kp.epi_tma) {
+    td = tx = ta;        // never dereferenced
+    gemm_bf16_tcgen05_2cta_kernel<false><<<2 * pairs, GEMM_THREADS, SMEM2_BYTES, stream>>>(ta, tb, td, tx, kp);
+  } else {
+    if (!a->aux_out) tx = td;
+    gemm_bf16_tcgen05_2cta_kernel<true><<<2 * pairs, GEMM_THREADS, SMEM2_BYTES, stream>>>(ta, tb, td, tx, kp);
+  }
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }
@@ -797,6 +1034,7 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
   // keep the larger operand streaming once from HBM: the smaller one is the re-read (L2-resident) side
   kp.n_fast = ((long)a->M >= (long)a->N) ? 1 : 0;
   kp.res_row_mod = a->res_row_mod; kp.d_row_block = a->d_row_block; kp.d_row_stride = a->d_row_stride;
+  kp.epi_tma = 0;
   auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
   const int esz = kp.out_f32 ? 4 : 2;
   kp.v32_d = al32(a->D) && (a->ldd * esz) % 32 == 0;

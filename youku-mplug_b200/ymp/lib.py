@@ -129,6 +129,8 @@ class AdamwArgs(C.Structure):
 lib.ymp_last_error.restype = C.c_char_p
 lib.ymp_abi_version.restype = C.c_int
 lib.ymp_launch_count.restype = C.c_uint64
+lib.ymp_attn_last_path.restype = C.c_int
+ATTN_PATH_MMA_SYNC, ATTN_PATH_TCGEN05, ATTN_PATH_SMALL = 0, 1, 2
 
 
 def _declare(name, argstruct):
@@ -163,6 +165,11 @@ def check(rc, what):
 
 def launch_count():
     return int(lib.ymp_launch_count())
+
+
+def attn_last_path():
+    """Kernel family of the last attention call on this thread (ATTN_PATH_*)."""
+    return int(lib.ymp_attn_last_path())
 
 
 def ptr(t):
