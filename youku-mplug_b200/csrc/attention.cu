@@ -672,8 +672,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnKParams p)
 
 static int fill_params(const ymp_attn_args* a, AttnKParams& p, const char* who) {
   YMP_CHECK_ARG(a && a->q && a->k && a->v, "%s: null q/k/v", who);
-  YMP_CHECK_ARG(a->head_dim == 64 || a->head_dim == 80 || a->head_dim == 96 || a->head_dim == 128,
-                "%s: head_dim %d not in {64,80,96,128}", who, a->head_dim);
+  YMP_CHECK_ARG(a->head_dim == 64 || a->head_dim == 80 || a->head_dim == 88 || a->head_dim == 96 || a->head_dim == 128,
+                "%s: head_dim %d not in {64,80,88,96,128}", who, a->head_dim);
   YMP_CHECK_ARG(a->n_seq > 0 && a->n_heads > 0 && a->s_q > 0 && a->s_kv > 0, "%s: bad sizes", who);
   YMP_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0, "%s: row strides must be multiples of 8", who);
   YMP_CHECK_ARG(a->q_head_stride % 8 == 0 && a->k_head_stride % 8 == 0 && a->v_head_stride % 8 == 0 && a->o_head_stride % 8 == 0, "%s: head strides must be multiples of 8", who);
@@ -748,6 +748,7 @@ extern "C" int ymp_attn_fwd(const ymp_attn_args* a, void* stream) {
     if (rc != YMP_ENOSUP) { g_attn_path = YMP_ATTN_PATH_TCGEN05; return rc; }
   }
   g_attn_path = YMP_ATTN_PATH_MMA_SYNC;
+  if (a->head_dim == 88) return set_error(YMP_ENOSUP, "ymp_attn_fwd: head_dim 88 is served by the tcgen05 kernels only (dense or cross attention, s_q >= 16)");
   switch (a->head_dim) {
     case 64: return launch_fwd<64>(p, st);
     case 80: return launch_fwd<80>(p, st);
@@ -780,6 +781,7 @@ extern "C" int ymp_attn_bwd(const ymp_attn_bwd_args* b, void* stream) {
     if (rc != YMP_ENOSUP) { g_attn_path = YMP_ATTN_PATH_TCGEN05; return rc; }
   }
   g_attn_path = YMP_ATTN_PATH_MMA_SYNC;
+  if (a->head_dim == 88) return set_error(YMP_ENOSUP, "ymp_attn_bwd: head_dim 88 is served by the tcgen05 kernels only");
   switch (a->head_dim) {
     case 64: return launch_bwd<64>(p, st);
     case 80: return launch_bwd<80>(p, st);

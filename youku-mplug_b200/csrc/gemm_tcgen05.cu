@@ -543,10 +543,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
 // L2->SM traffic per flop drops by a third.  The leader CTA issues all MMAs; completion is multicast
 // to both CTAs' mbarriers; both CTAs run their own producer and epilogue warps.
 constexpr int BN2 = 256;
-constexpr int NSTAGE2 = 5;   // 5 x 32 KB operand stages + 64 KB of epilogue staging = 225 KB of the 227 KB per SM
 constexpr int B2_STAGE_BYTES = (BN2 / 2) * BK * 2;
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;
-constexpr int SMEM2_BYTES = NSTAGE2 * STAGE2_BYTES + EPI_SMEM_BYTES + 256 + 1024;
+// operand ring: 6 x 32 KB with the direct (register) epilogue, 5 x 32 KB + 64 KB of staging with the TMA epilogue
+// (225 KB of the 227 KB per SM)
+template <bool TMA_EPI> struct Pair {
+  static constexpr int NSTAGE = TMA_EPI ? 5 : 6;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE2_BYTES + (TMA_EPI ? EPI_SMEM_BYTES : 0) + 256 + 1024;
+};
 
 #ifdef YMP_GEMM_DBG
 // [0] MMA warp: total cycles, [1] waiting for a free accumulator, [2] waiting for smem stages, [3] tiles
@@ -563,13 +567,14 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
                               const __grid_constant__ CUtensorMap tma_b,
                               const __grid_constant__ CUtensorMap tma_d,
                               const __grid_constant__ CUtensorMap tma_aux, const GemmKParams p) {
+  constexpr int NSTAGE2 = Pair<TMA_EPI>::NSTAGE;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + NSTAGE2 * A_STAGE_BYTES;
   uint8_t* smem_epi = smem + NSTAGE2 * STAGE2_BYTES;   // 1024-byte aligned: SWIZZLE_128B staging buffers
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + EPI_SMEM_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + (TMA_EPI ? EPI_SMEM_BYTES : 0));
   uint64_t* empty_bar = full_bar + NSTAGE2;
   uint64_t* tfull_bar = empty_bar + NSTAGE2;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -919,8 +924,9 @@ static int launch_gemm_2cta(const ymp_gemm_args* a, GemmKParams kp, cudaStream_t
   int rc;
   // TMA epilogue: plain row mapping, whole 64-column boxes, 16-byte aligned rows
   static const bool no_tma_epi = [] { const char* e = getenv("YMP_GEMM_LEGACY_EPI"); return e && e[0] == '1'; }();
+  static const int tma_epi_max_k = [] { const char* e = getenv("YMP_GEMM_TMA_EPI_MAXK"); return e ? atoi(e) : (1 << 30); }();
   const bool f32 = a->out_dtype == YMP_DT_F32;
-  kp.epi_tma = (!no_tma_epi && a->N % 64 == 0 && a->d_row_block == 0 && (a->ldd * (f32 ? 4 : 2)) % 16 == 0 &&
+  kp.epi_tma = (!no_tma_epi && a->K <= tma_epi_max_k && a->N % 64 == 0 && a->d_row_block == 0 && (a->ldd * (f32 ? 4 : 2)) % 16 == 0 &&
                 !(f32 && a->aux_out)) ? 1 : 0;
   if (kp.epi_tma) {
     rc = make_out_map(&td, a->D, f32, a->N, a->M, a->ldd);
@@ -939,8 +945,8 @@ static int launch_gemm_2cta(const ymp_gemm_args* a, GemmKParams kp, cudaStream_t
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair<true>::SMEM_BYTES));
+    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair<false>::SMEM_BYTES));
     attr_set = true;
   }
   const int num_m = (a->M + 2 * BM - 1) / (2 * BM), num_n = (a->N + BN2 - 1) / BN2;
@@ -948,10 +954,10 @@ static int launch_gemm_2cta(const ymp_gemm_args* a, GemmKParams kp, cudaStream_t
   const int pairs = min(units, num_sms() / 2);
   if (!kp.epi_tma) {
     td = tx = ta;        // never dereferenced
-    gemm_bf16_tcgen05_2cta_kernel<false><<<2 * pairs, GEMM_THREADS, SMEM2_BYTES, stream>>>(ta, tb, td, tx, kp);
+    gemm_bf16_tcgen05_2cta_kernel<false><<<2 * pairs, GEMM_THREADS, Pair<false>::SMEM_BYTES, stream>>>(ta, tb, td, tx, kp);
   } else {
     if (!a->aux_out) tx = td;
-    gemm_bf16_tcgen05_2cta_kernel<true><<<2 * pairs, GEMM_THREADS, SMEM2_BYTES, stream>>>(ta, tb, td, tx, kp);
+    gemm_bf16_tcgen05_2cta_kernel<true><<<2 * pairs, GEMM_THREADS, Pair<true>::SMEM_BYTES, stream>>>(ta, tb, td, tx, kp);
   }
   YMP_LAUNCH_CHECK();
   return YMP_OK;
