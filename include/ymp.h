@@ -37,6 +37,29 @@ int ymp_abi_version(void);
 uint64_t ymp_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
+ * Dropout of the GPT-3 decoder (the reference keeps the frozen decoder in train() mode, so
+ * hidden_dropout / attention_dropout = 0.1 are live: models/modeling_distributed_gpt3.py:631 embedding,
+ * :732 attention probabilities, :1056-1078 the two bias-dropout-adds).  No mask tensor exists: a keep
+ * decision is Philox4x32-10(key = seed, counter = (column >> 2, row, site, offset)).word[column & 3]
+ * >= floor(p * 2^32), kept values are scaled by 1 / (1 - p), and the backward kernels regenerate the same
+ * bits (csrc/philox.cuh; CPU restatement for the parity tests: oracle/philox.py).
+ *   rng    : DEVICE pointer to {seed, offset} (uint64 x 2), read when the kernel runs - a captured CUDA
+ *            graph therefore draws fresh masks on every replay; NULL (or p == 0) disables dropout
+ *   site   : which dropout call of the decoder pass (YMP_DROP_SITE_*)
+ *   row / column: logical coordinates - hidden states [B*S, H]: row = b*S + s, column = feature;
+ *            attention probabilities: row = (seq*heads + head)*s_q + query, column = key
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ymp_dropout_spec {
+  const uint64_t* rng;
+  uint32_t site;
+  float p;
+} ymp_dropout_spec;
+#define YMP_DROP_SITE_EMBED 0u                              /* embedding dropout (:631) */
+#define YMP_DROP_SITE_ATTN(layer) (4u * (layer) + 1u)       /* attention probabilities of layer (:732) */
+#define YMP_DROP_SITE_BDA_ATTN(layer) (4u * (layer) + 2u)   /* bias-dropout-add after attention (:1056-1062) */
+#define YMP_DROP_SITE_BDA_MLP(layer) (4u * (layer) + 3u)    /* bias-dropout-add after the MLP (:1072-1078) */
+
+/* ------------------------------------------------------------------------------------------
  * GEMM  D[M,N] = epilogue( alpha * op(A)[M,K] . op(B)[N,K]^T )          tcgen05 + TMA + TMEM
  *
  * Replaces: F.linear in ViT Attention qkv/proj (models/vision_transformer.py:171-176,205),
@@ -58,6 +81,7 @@ uint64_t ymp_launch_count(void);
  *   v = act(v)                           (YMP_ACT_*; skipped when aux_in is set)
  *   if aux_in:  v *= aux_in[m,n]         (backward of an activation: aux_in is the act' saved above,
  *                                          so the backward epilogue needs no transcendental)
+ *   if drop:    v = dropout(v)           (row = m, column = n; bias-dropout-add: residual + dropout(x + bias))
  *   v += residual[m,n]                   (bf16 or fp32 [M,N], row stride ldr, optional)
  *   D[m,n] = v  (bf16 or fp32) ; or atomically D[m,n] += v (fp32, accumulate=1, used by split-K)
  * ------------------------------------------------------------------------------------------ */
@@ -90,6 +114,7 @@ typedef struct ymp_gemm_args {
   int32_t d_row_block;  /* >0: D row = (m / d_row_block) * d_row_stride + m % d_row_block           */
   int32_t d_row_stride; /*     (writes [B*Q] rows into a [B, S>=Q] buffer without a copy)           */
   int32_t residual_dtype; /* YMP_DT_BF16 (default) | YMP_DT_F32: the residual streams are kept in fp32 */
+  ymp_dropout_spec drop;  /* dropout before the residual add (not together with aux_out) */
 } ymp_gemm_args;
 
 int ymp_gemm(const ymp_gemm_args* a, void* stream);
@@ -130,6 +155,10 @@ typedef struct ymp_layernorm_bwd_args {
   const int32_t* in_rows;
   int32_t rows, D, ldx, lddy, ldadd;
   int32_t x_dtype;    /* dtype of x (dx is always bf16, same row stride in elements) */
+  void* dx_drop;      /* optional second output, bf16, indexed like dx: dropout_backward(dx) = dx * mask / (1-p) for the
+                         dropout site that produced this LayerNorm's input stream (row = x row, column = feature):
+                         the A operand of the dgrad GEMM below that bias-dropout-add */
+  ymp_dropout_spec drop;
 } ymp_layernorm_bwd_args;
 int ymp_layernorm_bwd(const ymp_layernorm_bwd_args* a, void* stream);
 
@@ -181,6 +210,8 @@ typedef struct ymp_attn_args {
   int64_t total_rows;  /* >0 (dense packed sequences only): rows beyond total_rows do not exist, so
                           the last sequence may be shorter than s_q */
   float scale;
+  ymp_dropout_spec drop;  /* dropout of the attention probabilities (tcgen05 kernels only): O = dropout(P) V, the
+                             softmax statistics (lse) stay those of the undropped P */
 } ymp_attn_args;
 int ymp_attn_fwd(const ymp_attn_args* a, void* stream);
 
@@ -234,6 +265,18 @@ typedef struct ymp_clip_args {
   int32_t B, T, H, W, C;
 } ymp_clip_args;
 int ymp_clip_normalize(const ymp_clip_args* a, void* stream);
+
+/* y = dropout(x) over a [rows, cols] matrix (bf16 or fp32, in place allowed): the embedding dropout
+ * (models/modeling_distributed_gpt3.py:631; logical row = row0 + r) and the mask export used by the parity tests. */
+typedef struct ymp_dropout_args {
+  const void* x;
+  void* y;
+  int32_t rows, cols, ldx, ldy;
+  int32_t dtype;   /* YMP_DT_BF16 | YMP_DT_F32 (both x and y) */
+  int64_t row0;
+  ymp_dropout_spec drop;
+} ymp_dropout_args;
+int ymp_dropout(const ymp_dropout_args* a, void* stream);
 
 /* Word-embedding gather + learned position add, written straight into the decoder input
  * buffer [B, S, hidden] at rows row_offset..row_offset+L-1 of each sample.  Replaces

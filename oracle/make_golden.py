@@ -139,6 +139,66 @@ def run(name, vcfg, gcfg, Q, B, L, wseed, iseed, randomize, sample_logits=None, 
     print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
 
 
+def run_dropout(name, vcfg, gcfg, Q, B, L, wseed, iseed, p_hidden=0.1, p_attn=0.1, seed=20240924, offset=0):
+    """Decoder dropout (the ★ row of the coverage table): the UNMODIFIED reference's DistributedGPT3_Pretrain in
+    train() mode with hidden_dropout / attention_dropout live (as in real training: the frozen decoder stays in
+    train mode), its F.dropout masks drawn from the B200 kernels' Philox convention (ref_shims.philox_dropout).
+    The oracle's restatement with the same masks must agree (pins port.gpt3_layer(drop=...)); the reference's
+    outputs and gradients become the fixture the GPU kernels are checked against WITH dropout active."""
+    sd = port.init_state_dict(vcfg, gcfg, Q, seed=wseed, randomize=True)
+    ref_vcfg = dict(vcfg, drop_path=0, use_abs_pos_emb=True)
+    # bias_dropout_fusion=False: the same bias_dropout_add arithmetic (:953-957) through the plain Python function
+    # instead of its torch.jit.script twin (:968-979), whose dropout a Python-level patch cannot reach
+    model, G = ref_shims.build_reference_model("DistributedGPT3_Pretrain", ref_vcfg, dict(gcfg, bias_dropout_fusion=False), Q,
+                                               dropout=(p_hidden, p_attn))
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    model.train()
+    video, ids, att = make_inputs(B, vcfg, L, gcfg["vocab_size"], iseed)
+    text = G.BatchEncoding(dict(input_ids=ids, attention_mask=att))
+    inter = {}
+    h3 = model.text_decoder.register_forward_hook(lambda m, i, o: inter.__setitem__("gpt", o))
+    with ref_shims.philox_dropout(seed, offset) as pd:
+        loss_ref, _ = model(video, text)
+        loss_ref.backward()
+    h3.remove()
+    n_layers = gcfg["num_hidden_layers"]
+    assert pd.calls == 1 + 3 * n_layers, pd.calls
+    out = inter["gpt"]
+    ref_grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    # the same forward without dropout differs (the masks really were applied)
+    model.eval()
+    with torch.no_grad():
+        loss_eval, _ = model(video, text)
+    assert abs(loss_eval.item() - loss_ref.item()) > 1e-4 * abs(loss_eval.item())
+    del model
+    drop = dict(seed=seed, offset=offset, p_hidden=p_hidden, p_attn=p_attn)
+    psd = {k: v.clone().requires_grad_(k in port.trainable_keys(sd)) for k, v in sd.items()}
+    res = port.pretrain_forward(video, ids, att, psd, vcfg, gcfg, return_all=True, drop=drop)
+    res["loss"].backward()
+
+    def chk(a, b, what, tol=2e-4):
+        err = (a.float() - b.float()).abs().max().item()
+        scale = b.float().abs().max().item() + 1e-12
+        assert err <= tol * scale + 1e-6, f"{name}: port != reference for {what}: {err} (scale {scale})"
+        return err / scale
+
+    worst = max(chk(res["loss"], loss_ref, "loss", 1e-5), chk(res["logits"], out.logits, "logits"),
+                chk(res["losses"][:, :-1], out.losses, "losses"), chk(res["hidden"], out.last_hidden_state, "hidden"))
+    for k, gref in ref_grads.items():
+        worst = max(worst, chk(psd[k].grad, gref, "grad " + k, 5e-4))
+    print(f"[{name}] reference (train mode, Philox masks) loss {loss_ref.item():.6f} vs eval {loss_eval.item():.6f}; "
+          f"port == reference (worst rel err {worst:.2e}); {len(ref_grads)} grads", flush=True)
+    fix = dict(name=name, vcfg=vcfg, gcfg=gcfg, Q=Q, B=B, L=L, wseed=wseed, iseed=iseed, drop=drop, loss=loss_ref.detach(),
+               loss_eval=loss_eval.detach(), losses=out.losses.detach(), logits=out.logits.detach(),
+               hidden=out.last_hidden_state.detach(), grad_norms={k: v.norm() for k, v in ref_grads.items()},
+               grads={k: sample_grad(ref_grads[k]) for k in GRAD_KEYS if k in ref_grads},
+               port_vs_ref_worst_rel=worst, torch_version=torch.__version__)
+    path = os.path.join(GOLD, name + ".pt")
+    torch.save(fix, path)
+    print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
+
+
 def run_generate(name, vcfg, gcfg, Q, B, L, wseed, iseed, beam_size=3, n_new=6, pos_gain=30.0, ln_gain=16.0, stop_after=3):
     """Golden vectors for the generation path: the UNMODIFIED reference's per-sample beam
     search and batched greedy sampling over its KV cache, with the visual prefix, next to the oracle's
@@ -406,6 +466,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also the real 1.3B / T=8 / B=1 config (~6 GB RAM, minutes)")
     ap.add_argument("--caption27b", action="store_true", help="only the 2.7B caption config at its real dims (~35 GB RAM, minutes)")
+    ap.add_argument("--only-dropout", action="store_true", help="only (re)write the decoder-dropout fixture")
     ap.add_argument("--only-generate", action="store_true", help="only (re)write the generation fixture")
     ap.add_argument("--only-downstream", action="store_true", help="only (re)write the downstream-model fixture")
     a = ap.parse_args()
@@ -414,6 +475,9 @@ if __name__ == "__main__":
         run_caption_full("full_2p7b_caption_T16_B1", dict(port.VCFG_CLIP_B16, num_frames=16), port.GCFG_2_7B, Q=128, B=1, L=256,
                          wseed=0, iseed=4321)
         sys.exit(0)
+    if a.only_dropout:
+        run_dropout("tiny_pretrain_dropout", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=2, L=8, wseed=61, iseed=62)
+        sys.exit(0)
     if a.only_downstream:
         run_downstream("tiny_downstream", port.VCFG_TINY, port.GCFG_TINY, Q=8, wseed=21)
         sys.exit(0)
@@ -421,6 +485,7 @@ if __name__ == "__main__":
     if a.only_generate:
         sys.exit(0)
     run_downstream("tiny_downstream", port.VCFG_TINY, port.GCFG_TINY, Q=8, wseed=21)
+    run_dropout("tiny_pretrain_dropout", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=2, L=8, wseed=61, iseed=62)
     run("tiny_pretrain", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=2, L=8, wseed=11, iseed=12, randomize=True)
     run("tiny_pretrain_refinit", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=1, L=6, wseed=13, iseed=14, randomize=False)
     if a.full:

@@ -127,12 +127,25 @@ def gelu_tanh(x):
 GPT_PRE = "text_decoder.dist_model.language_model."
 
 
-def gpt3_layer(x, sd, pre, heads, layer_number, eps):
+def _drop(t2d, drop, site, p):
+    """Dropout with the B200 kernels' Philox mask convention (oracle/philox.py) on a [rows, cols] view."""
+    if drop is None or p <= 0.0:
+        return t2d
+    from oracle import philox
+    return philox.dropout(t2d, drop["seed"], drop["offset"], site, p)
+
+
+def gpt3_layer(x, sd, pre, heads, layer_number, eps, drop=None):
     """GPT3ParallelTransformerLayer.forward - models/modeling_distributed_gpt3.py:1034-1089 with
     GPT3ParallelAttention (:868-938) and GPT3CoreAttention (:734-817).  x is [B,S,h] here (the
     reference uses [S,B,h]; the arithmetic per (b, head) is identical).  QKV rows are grouped per
-    head as [q|k|v]; scores = q.k / (sqrt(hn)*layer) * layer; causal fill value -10000."""
+    head as [q|k|v]; scores = q.k / (sqrt(hn)*layer) * layer; causal fill value -10000.
+    drop = dict(seed, offset, p_hidden, p_attn): train-mode dropout of the attention probabilities (:772-780)
+    and the two bias-dropout-adds (:1051-1078), masks as the B200 kernels draw them (site = 4*layer + 1/2/3)."""
     B, S, H = x.shape
+    li = layer_number - 1
+    ph = drop["p_hidden"] if drop else 0.0
+    pa = drop["p_attn"] if drop else 0.0
     hn = H // heads
     ln1 = layer_norm(x, sd[pre + "input_layernorm.weight"], sd[pre + "input_layernorm.bias"], eps)
     qkv = F.linear(ln1, sd[pre + "self_attention.query_key_value.weight"],
@@ -145,23 +158,27 @@ def gpt3_layer(x, sd, pre, heads, layer_number, eps):
     mask = torch.ones(S, S, dtype=torch.bool, device=x.device).triu(1)
     scores = scores.masked_fill(mask, -10000.0)
     probs = scores.softmax(dim=-1).to(x.dtype)
+    probs = _drop(probs.reshape(B * heads * S, S), drop, 4 * li + 1, pa).reshape(B, heads, S, S)
     ctx = (probs @ v).transpose(1, 2).reshape(B, S, H)
     attn_out = F.linear(ctx, sd[pre + "self_attention.dense.weight"]) + sd[pre + "self_attention.dense.bias"]
-    x = x + attn_out  # bias-dropout-add with p=0 (:1051-1062)
+    x = x + _drop(attn_out.reshape(B * S, H), drop, 4 * li + 2, ph).reshape(B, S, H)  # bias-dropout-add (:1051-1062)
     ln2 = layer_norm(x, sd[pre + "post_attention_layernorm.weight"], sd[pre + "post_attention_layernorm.bias"], eps)
     h = gelu_tanh(F.linear(ln2, sd[pre + "mlp.dense_h_to_4h.weight"]) + sd[pre + "mlp.dense_h_to_4h.bias"])
     mlp_out = F.linear(h, sd[pre + "mlp.dense_4h_to_h.weight"]) + sd[pre + "mlp.dense_4h_to_h.bias"]
-    return x + mlp_out
+    return x + _drop(mlp_out.reshape(B * S, H), drop, 4 * li + 3, ph).reshape(B, S, H)
 
 
-def gpt3_decoder(input_embeds, sd, gcfg, pre=GPT_PRE):
-    """GPT3Embedding.forward (:640-666, position ids = arange(S) incl. the visual prefix) +
-    GPT3ParallelTransformer.forward (:1140-1186).  Returns final-LN hidden states [B,S,h]."""
+def gpt3_decoder(input_embeds, sd, gcfg, pre=GPT_PRE, drop=None):
+    """GPT3Embedding.forward (:640-666, position ids = arange(S) incl. the visual prefix; embedding dropout :631
+    at site 0 when `drop` is given) + GPT3ParallelTransformer.forward (:1140-1186).  Returns final-LN hidden
+    states [B,S,h]."""
     B, S, H = input_embeds.shape
     eps = gcfg.get("layernorm_epsilon", 1e-12)
     x = input_embeds + sd[pre + "embedding.position_embeddings.weight"][:S][None]
+    if drop is not None:
+        x = _drop(x.reshape(B * S, H), drop, 0, drop["p_hidden"]).reshape(B, S, H)
     for i in range(gcfg["num_hidden_layers"]):
-        x = gpt3_layer(x, sd, f"{pre}encoder.layers.{i}.", gcfg["num_attention_heads"], i + 1, eps)
+        x = gpt3_layer(x, sd, f"{pre}encoder.layers.{i}.", gcfg["num_attention_heads"], i + 1, eps, drop)
     return layer_norm(x, sd[pre + "encoder.final_layernorm.weight"], sd[pre + "encoder.final_layernorm.bias"], eps)
 
 
@@ -191,8 +208,9 @@ def masked_mean_loss(losses, loss_mask):
     return torch.sum(losses[:, :-1].reshape(-1).float() * lm) / lm.sum()
 
 
-def pretrain_forward(video, input_ids, attention_mask, sd, vcfg, gcfg, return_all=False):
-    """DistributedGPT3_Pretrain.forward (use_contrastive=False) - models/distributed_gpt3.py:130-166."""
+def pretrain_forward(video, input_ids, attention_mask, sd, vcfg, gcfg, return_all=False, drop=None):
+    """DistributedGPT3_Pretrain.forward (use_contrastive=False) - models/distributed_gpt3.py:130-166.
+    drop: see gpt3_layer (decoder dropout in train() mode)."""
     image_embeds = timesformer(video, sd, vcfg)
     B = video.shape[0]
     image_query = attention_pool(sd["learnable_queries"].expand(B, -1, -1), image_embeds, sd, vcfg["num_heads"])
@@ -201,7 +219,7 @@ def pretrain_forward(video, input_ids, attention_mask, sd, vcfg, gcfg, return_al
     targets, loss_mask = build_targets(input_ids, attention_mask, Q)
     emb_w = sd[GPT_PRE + "embedding.word_embeddings.weight"]
     input_embeds = torch.cat([query_features, emb_w[input_ids]], dim=1)
-    hidden = gpt3_decoder(input_embeds, sd, gcfg)
+    hidden = gpt3_decoder(input_embeds, sd, gcfg, drop=drop)
     logits, losses = lm_head_losses(hidden, emb_w, targets)
     loss = masked_mean_loss(losses, loss_mask)
     if return_all:

@@ -207,12 +207,12 @@ def import_reference():
     return V, G, D
 
 
-def build_reference_model(cls_name, visual_cfg, gpt_cfg, num_learnable_token, seed=0, **config_extra):
+def build_reference_model(cls_name, visual_cfg, gpt_cfg, num_learnable_token, seed=0, dropout=(0.0, 0.0), **config_extra):
     """Instantiate one of the reference's task models (models/distributed_gpt3.py: DistributedGPT3_Pretrain / _Cls /
-    _Caption / _Retrieval / _Retrieval_Cls) on CPU (fp32, eval, dropout 0)."""
+    _Caption / _Retrieval / _Retrieval_Cls) on CPU (fp32, eval; dropout = (hidden, attention), 0 by default)."""
     V, G, D = import_reference()
     td = tempfile.mkdtemp(prefix="ymp_ref_")
-    gpt_cfg = dict(gpt_cfg, hidden_dropout=0.0, attention_dropout=0.0)
+    gpt_cfg = dict(gpt_cfg, hidden_dropout=dropout[0], attention_dropout=dropout[1])
     with open(os.path.join(td, "config.json"), "w") as f:
         json.dump(gpt_cfg, f)
     vis = dict(visual_cfg, pretrained_ckpt=None, grad_ckpt=False)
@@ -231,3 +231,42 @@ def build_reference_pretrain(visual_cfg, gpt_cfg, num_learnable_token, seed=0, u
     """Instantiate the reference's DistributedGPT3_Pretrain on CPU (fp32, eval, dropout 0)."""
     return build_reference_model("DistributedGPT3_Pretrain", visual_cfg, gpt_cfg, num_learnable_token, seed=seed,
                                  use_contrastive=use_contrastive)
+
+
+class philox_dropout:
+    """Context manager: while active, torch.nn.functional.dropout (hence nn.Dropout and the reference's
+    bias_dropout_add, models/modeling_distributed_gpt3.py:1056-1078) draws its masks from the B200 kernels' Philox
+    convention (oracle/philox.py) instead of torch's generator, so the UNMODIFIED reference can be run in train()
+    mode with exactly the masks the kernels will use.  Call sites of one decoder pass are identified by call order:
+    embedding dropout ([s,b,h], :631) -> site 0, then per layer attention probabilities ([b,np,sq,sk], :732) ->
+    4l+1, bias-dropout-add after attention ([s,b,h]) -> 4l+2, after the MLP -> 4l+3."""
+
+    def __init__(self, seed, offset):
+        self.seed, self.offset, self.calls = seed, offset, 0
+
+    def _dropout(self, input, p=0.5, training=True, inplace=False):
+        from oracle import philox
+        if not training or p <= 0.0:
+            return input
+        n = self.calls
+        self.calls += 1
+        site = 0 if n == 0 else 4 * ((n - 1) // 3) + 1 + (n - 1) % 3
+        if input.dim() == 4:                     # attention probabilities [b, np, sq, sk]
+            assert (n - 1) % 3 == 0, "call order: attention dropout expected"
+            b, h, sq, sk = input.shape
+            return philox.dropout(input.reshape(b * h * sq, sk), self.seed, self.offset, site, p).reshape(input.shape)
+        assert input.dim() == 3                  # hidden states [s, b, h]: logical row = b*S + s
+        S, B, H = input.shape
+        x = input.permute(1, 0, 2).reshape(B * S, H)
+        return philox.dropout(x, self.seed, self.offset, site, p).reshape(B, S, H).permute(1, 0, 2)
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self._orig = F.dropout
+        F.dropout = self._dropout
+        return self
+
+    def __exit__(self, *exc):
+        import torch.nn.functional as F
+        F.dropout = self._orig
+        return False

@@ -5,10 +5,11 @@ import tempfile
 import torch
 
 
-def make_model_dir(vcfg, gcfg):
+def make_model_dir(vcfg, gcfg, dropout=(0.0, 0.0)):
+    """dropout = (hidden_dropout, attention_dropout) of the decoder; 0 = parity mode (the reference default is 0.1)."""
     td = tempfile.mkdtemp(prefix="ymp_model_")
     with open(os.path.join(td, "config.json"), "w") as f:
-        json.dump(dict(gcfg, hidden_dropout=0.0, attention_dropout=0.0), f)
+        json.dump(dict(gcfg, hidden_dropout=dropout[0], attention_dropout=dropout[1]), f)
     with open(os.path.join(td, "vis.json"), "w") as f:
         json.dump(dict(vcfg, pretrained_ckpt=None, grad_ckpt=False), f)
     return td
@@ -22,10 +23,11 @@ def pretrain_config(td, Q, **extra):
     return cfg
 
 
-def build_pretrain(vcfg, gcfg, Q, sd=None, device="cpu", dtype=None, cls_name="DistributedGPT3_Pretrain", **extra):
+def build_pretrain(vcfg, gcfg, Q, sd=None, device="cpu", dtype=None, cls_name="DistributedGPT3_Pretrain", dropout=(0.0, 0.0),
+                   **extra):
     os.environ["YMP_ALLOW_RANDOM_INIT"] = "1"
     import models.distributed_gpt3 as D
-    td = make_model_dir(vcfg, gcfg)
+    td = make_model_dir(vcfg, gcfg, dropout)
     model = getattr(D, cls_name)(config=pretrain_config(td, Q, **extra), tokenizer=None)
     if sd is not None:
         missing, unexpected = model.load_state_dict(sd, strict=False)

@@ -82,6 +82,7 @@ if __name__ == '__main__':
                                             visual_backbone_scale=vcfg.get("clip_model", False))
     model, optimizer, _, _ = ds_init(args=args, model=model, model_parameters=optimizer_params, dist_init_required=False, mpu=mpu)
     p0 = {k: v.detach().float().clone() for k, v in model.module.named_parameters() if v.requires_grad}
+    master0 = model.master.clone()
 
     T, R = vcfg["num_frames"], vcfg["img_size"]
     g = torch.Generator().manual_seed(1 + rank)
@@ -116,8 +117,9 @@ if __name__ == '__main__':
     model.save_checkpoint(save_dir=args.output_dir, tag="checkpoint-0", client_state={'epoch': 0})
     _, client_states = model.load_checkpoint(args.output_dir, tag='checkpoint-0')
     changed = sum(int(not torch.equal(v.detach().float(), p0[k])) for k, v in model.module.named_parameters() if v.requires_grad)
+    master_changed = float((model.master != master0).float().mean())
     if rank == 0:
-        print("MINI " + json.dumps(dict(log=log, changed=changed, trainable=len(p0), client=client_states,
+        print("MINI " + json.dumps(dict(log=log, changed=changed, trainable=len(p0), client=client_states, master_changed=master_changed,
                                         engine=type(model).__module__ + "." + type(model).__name__,
                                         model_file=os.path.abspath(__import__("models").__file__))), flush=True)
     dist.destroy_process_group()

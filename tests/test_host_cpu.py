@@ -22,7 +22,7 @@ def test_abi_exports_every_declared_symbol():
     for n in sorted(names):
         assert hasattr(lib, n), f"{n} declared in include/ymp.h but not exported"
     lib.ymp_abi_version.restype = ctypes.c_int
-    assert lib.ymp_abi_version() == 1
+    assert lib.ymp_abi_version() == 2
 
 
 def test_ctypes_structs_match_header_field_order():
@@ -32,7 +32,8 @@ def test_ctypes_structs_match_header_field_order():
     mirrors = {"ymp_gemm_args": L.GemmArgs, "ymp_layernorm_args": L.LayerNormArgs, "ymp_layernorm_bwd_args": L.LayerNormBwdArgs,
                "ymp_seqmap": L.SeqMap, "ymp_attn_args": L.AttnArgs, "ymp_attn_bwd_args": L.AttnBwdArgs,
                "ymp_adamw_args": L.AdamwArgs, "ymp_im2col_args": L.Im2colArgs, "ymp_clip_args": L.ClipArgs, "ymp_embed_args": L.EmbedArgs,
-               "ymp_ce_args": L.CeArgs, "ymp_colsum_args": L.ColsumArgs, "ymp_group_args": L.GroupArgs}
+               "ymp_ce_args": L.CeArgs, "ymp_colsum_args": L.ColsumArgs, "ymp_group_args": L.GroupArgs,
+               "ymp_dropout_spec": L.DropoutSpec, "ymp_dropout_args": L.DropoutArgs}
     for name, cls in mirrors.items():
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)

@@ -741,12 +741,17 @@ extern "C" int ymp_attn_fwd(const ymp_attn_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // short key ranges run on the tcgen05 kernel (attention_tc.cu); YMP_ATTN_LEGACY=1 forces mma.sync
   static const bool legacy = [] { const char* e = getenv("YMP_ATTN_LEGACY"); return e && e[0] == '1'; }();
-  if (!legacy) {
-    rc = attn_small_fwd_try(a, st);  // short dense block-diagonal sequences (attention_small.cu)
-    if (rc != YMP_ENOSUP) { g_attn_path = YMP_ATTN_PATH_SMALL; return rc; }
+  const bool dropped = a->drop.rng && a->drop.p > 0.f;
+  YMP_CHECK_ARG(!dropped || a->drop.p < 1.f, "ymp_attn_fwd: dropout p must be < 1");
+  if (!legacy || dropped) {
+    if (!dropped) {
+      rc = attn_small_fwd_try(a, st);  // short dense block-diagonal sequences (attention_small.cu)
+      if (rc != YMP_ENOSUP) { g_attn_path = YMP_ATTN_PATH_SMALL; return rc; }
+    }
     rc = attn_tc_fwd_try(a, st);
     if (rc != YMP_ENOSUP) { g_attn_path = YMP_ATTN_PATH_TCGEN05; return rc; }
   }
+  if (dropped) return set_error(YMP_ENOSUP, "ymp_attn_fwd: dropout of the probabilities is implemented by the tcgen05 kernels only");
   g_attn_path = YMP_ATTN_PATH_MMA_SYNC;
   if (a->head_dim == 88) return set_error(YMP_ENOSUP, "ymp_attn_fwd: head_dim 88 is served by the tcgen05 kernels only (dense or cross attention, s_q >= 16)");
   switch (a->head_dim) {
@@ -774,12 +779,16 @@ extern "C" int ymp_attn_bwd(const ymp_attn_bwd_args* b, void* stream) {
   p.mdo = to_map(b->map_do); p.mdq = to_map(b->map_dq); p.mdkv = to_map(b->map_dkv);
   cudaStream_t st = (cudaStream_t)stream;
   static const bool legacy = [] { const char* e = getenv("YMP_ATTN_LEGACY"); return e && e[0] == '1'; }();
-  if (!legacy) {
-    rc = attn_small_bwd_try(b, st);
-    if (rc != YMP_ENOSUP) { g_attn_path = YMP_ATTN_PATH_SMALL; return rc; }
+  const bool dropped = a->drop.rng && a->drop.p > 0.f;
+  if (!legacy || dropped) {
+    if (!dropped) {
+      rc = attn_small_bwd_try(b, st);
+      if (rc != YMP_ENOSUP) { g_attn_path = YMP_ATTN_PATH_SMALL; return rc; }
+    }
     rc = attn_tc_bwd_try(b, st);
     if (rc != YMP_ENOSUP) { g_attn_path = YMP_ATTN_PATH_TCGEN05; return rc; }
   }
+  if (dropped) return set_error(YMP_ENOSUP, "ymp_attn_bwd: dropout of the probabilities is implemented by the tcgen05 kernels only");
   g_attn_path = YMP_ATTN_PATH_MMA_SYNC;
   if (a->head_dim == 88) return set_error(YMP_ENOSUP, "ymp_attn_bwd: head_dim 88 is served by the tcgen05 kernels only");
   switch (a->head_dim) {

@@ -19,6 +19,7 @@
 #include <math_constants.h>
 
 #include "common.h"
+#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace ymp {
@@ -58,6 +59,8 @@ struct AttnTcParams {
   float scale_log2, scale;
   int kv_rows;  // rows of the K/V smem tiles = round32(min(s_kv, 256))
   int hd;       // real head_dim (<= HD): columns [hd, HD) are zero-filled in shared memory and never stored
+  DropSpec drop;  // dropout of the probabilities (has_drop): row = (seq*heads + head)*s_q + query, column = key
+  int has_drop;
 };
 
 __device__ __forceinline__ void cp16(void* smem, const void* gmem) {
@@ -213,6 +216,9 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) 
   if (p.mask == TC_MASK_CAUSAL) hi = min(hi, row + 1 + (p.s_kv - p.s_q));
   if (p.mask == TC_MASK_BLOCK) { lo = (row / p.mask_block) * p.mask_block; hi = min(hi, lo + p.mask_block); }
 
+  DropState ds = {};
+  if (p.has_drop) ds = drop_state(p.drop);
+  const uint32_t drow = ((uint32_t)s * p.n_heads + h) * p.s_q + row;   // logical row of the probability matrix
   float m_run = -CUDART_INF_F, l_run = 0.f;   // running row max (raw scores) and row sum
   float oacc[LONG ? 2 : 1][LONG ? 32 : 1];    // LONG: this thread's O chunks (chunk c of HD/32 belongs to warpgroup c & 1)
   if (LONG) {
@@ -317,6 +323,10 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) 
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) lsum += pv[i];
+        if (p.has_drop) {  // O = dropout(P) V; the normaliser stays that of the undropped P (:772-780: softmax, then dropout)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) drop4(ds, drow, (uint32_t)(k0 + c * 32 + 4 * j), pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
       }
@@ -442,6 +452,8 @@ struct AttnTcBwdParams {
   long total_rows;
   float scale_log2, scale;
   int hd;  // real head_dim (<= HD), see AttnTcParams
+  DropSpec drop;
+  int has_drop;
 };
 
 __device__ __forceinline__ float ex2_fast(float x) {
@@ -584,6 +596,9 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
   const uint32_t tmem = *tmem_ptr;
   const uint32_t tl = tmem + ((uint32_t)(wq * 32) << 16);
   const int kr = wq * 32 + lane;  // this thread's TMEM lane: key row (softmax, dK/dV) or query row (dQ)
+  DropState ds = {};
+  if (p.has_drop) ds = drop_state(p.drop);
+  const uint32_t drow0 = ((uint32_t)s * p.n_heads + h) * p.s_q;  // logical row of query 0 in the probability matrix
   TDBG(1);
 
   int it = 0;
@@ -662,6 +677,24 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
         tmem_ld_wait();
         uint32_t ppk[16], dpk[16];
         const float4* st4 = reinterpret_cast<const float4*>(stats + qi0 + c * 32);
+        // dropout bits of (32 queries of this chunk) x (this lane's key): a Philox call yields the words of 4
+        // consecutive KEYS of one query, so the 4 lanes of a key group split the 32 queries (8 calls each) and
+        // exchange their packed keep-bits - 8 calls + 4 shuffles per chunk instead of 32 calls
+        uint32_t kb[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (p.has_drop) {
+          uint32_t mine = 0;
+          const uint32_t kg = (uint32_t)(kj0 + kr) >> 2;
+#pragma unroll
+          for (int jq = 0; jq < 8; ++jq) {
+            const uint4 w = drop_words(ds, drow0 + (uint32_t)(qi0 + c * 32 + (lane & 3) * 8 + jq), kg);
+            const uint32_t bits = (w.x >= ds.thresh ? 1u : 0u) | (w.y >= ds.thresh ? 2u : 0u) | (w.z >= ds.thresh ? 4u : 0u) |
+                                  (w.w >= ds.thresh ? 8u : 0u);
+            mine |= bits << (4 * jq);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) kb[i] = __shfl_sync(0xffffffffu, mine, (lane & ~3) + i) >> (lane & 3);
+        }
+        const float dsc = p.has_drop ? ds.scale : 1.f;
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float4 st = st4[e];  // (lse2, delta) of two consecutive queries, warp-broadcast
@@ -671,9 +704,12 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
             if (c * 32 + 2 * e < kr) p0 = 0.f;
             if (c * 32 + 2 * e + 1 < kr) p1 = 0.f;
           }
-          const float d0 = p0 * (__uint_as_float(dr[2 * e]) - st.y);
-          const float d1 = p1 * (__uint_as_float(dr[2 * e + 1]) - st.w);
-          ppk[e] = pack_bf16(p0, p1);
+          // query 2e (2e+1) of the chunk: word kb[(2e) >> 3], bit 4 * ((2e) & 7) (already shifted by this lane's key)
+          const bool k0 = (kb[e >> 2] >> (4 * ((2 * e) & 7))) & 1u, k1 = (kb[e >> 2] >> (4 * ((2 * e + 1) & 7))) & 1u;
+          const float dp0 = k0 ? __uint_as_float(dr[2 * e]) * dsc : 0.f, dp1 = k1 ? __uint_as_float(dr[2 * e + 1]) * dsc : 0.f;
+          const float d0 = p0 * (dp0 - st.y);
+          const float d1 = p1 * (dp1 - st.w);
+          ppk[e] = pack_bf16(k0 ? p0 * dsc : 0.f, k1 ? p1 * dsc : 0.f);   // dV += dropout(P)^T dO
           dpk[e] = pack_bf16(d0, d1);
         }
         const uint32_t pc = half * 64 + cc * 16;  // packed pairs land inside this warp's consumed columns
@@ -834,6 +870,8 @@ int attn_tc_fwd_try(const ymp_attn_args* a, cudaStream_t st) {
   p.mask = a->mask; p.mask_block = a->mask_block > 0 ? a->mask_block : 1; p.total_rows = a->total_rows;
   p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
   p.hd = a->head_dim;
+  p.has_drop = (a->drop.rng && a->drop.p > 0.f) ? 1 : 0;
+  p.drop.rng = a->drop.rng; p.drop.site = a->drop.site; p.drop.p = a->drop.p;
   const bool lng = a->s_kv > 256;
   p.kv_rows = lng ? 256 : ((a->s_kv + 31) & ~31);
   if (a->head_dim == 64) return lng ? launch_tc<64, true>(p, st) : launch_tc<64, false>(p, st);
@@ -874,6 +912,8 @@ int attn_tc_bwd_try(const ymp_attn_bwd_args* b, cudaStream_t st) {
   p.mask = a->mask; p.total_rows = a->total_rows;
   p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
   p.hd = a->head_dim;
+  p.has_drop = (a->drop.rng && a->drop.p > 0.f) ? 1 : 0;
+  p.drop.rng = a->drop.rng; p.drop.site = a->drop.site; p.drop.p = a->drop.p;
   return a->head_dim == 64 ? launch_tc_bwd<64>(p, st) : launch_tc_bwd<96>(p, st);
 }
 

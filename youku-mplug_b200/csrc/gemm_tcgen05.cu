@@ -8,6 +8,7 @@
 #include <cuda.h>
 
 #include "common.h"
+#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace ymp {
@@ -36,6 +37,8 @@ struct GemmKParams {
   int n_fast;                      // tile order: consecutive units walk N first (A streamed once) or M first
   bool v32_d, v32_aux, v32_res, v32_bias;  // 32-byte aligned -> 256-bit accesses
   float alpha;
+  DropSpec drop;                   // dropout before the residual add (has_drop)
+  int has_drop;
   int epi_tma;                     // CTA-pair kernel: outputs staged in swizzled smem and written by TMA (bulk tensor
                                    // store; bulk reduce-add for the fp32 split-K accumulation)
 };
@@ -141,7 +144,7 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmKParams& p, int row,
 
 // Epilogue for one thread: 32 consecutive columns of one output row.
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint32_t (&r)[32],
-                                               int row, int col0, const EpiPrefetch& pf) {
+                                               int row, int col0, const EpiPrefetch& pf, const DropState& ds) {
   if (row >= p.M || col0 >= p.N) return;
   const bool full = (col0 + 32 <= p.N);
   const int drow = p.d_row_block ? (row / p.d_row_block) * p.d_row_stride + row % p.d_row_block : row;
@@ -192,6 +195,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
     } else if (p.aux_out) {
       store16(p.aux_out + off, p.v32_aux, v);
       store16(p.aux_out + off + 16, p.v32_aux, v + 16);
+    }
+    if (p.has_drop) {  // bias-dropout-add: residual + dropout(x + bias)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) drop4(ds, (uint32_t)row, (uint32_t)(col0 + 4 * j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
     if (p.residual) {
       if (p.res_f32) {  // fp32 residual stream
@@ -250,6 +257,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
         } else if (p.aux_out) {
           p.aux_out[off] = __float2bfloat16(x);
         }
+        if (p.has_drop) {
+          const uint4 w = drop_words(ds, (uint32_t)row, (uint32_t)col >> 2);
+          const uint32_t wc = (col & 3) == 0 ? w.x : (col & 3) == 1 ? w.y : (col & 3) == 2 ? w.z : w.w;
+          x = wc >= ds.thresh ? x * ds.scale : 0.f;
+        }
         if (p.residual)
           x += p.res_f32 ? reinterpret_cast<const float*>(p.residual)[(size_t)rrow * p.ldr + col]
                          : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[(size_t)rrow * p.ldr + col]);
@@ -306,7 +318,8 @@ __device__ __forceinline__ void epilogue_pre(const GemmKParams& p, uint32_t (&r)
     }
   }
 }
-__device__ __forceinline__ void epilogue_post(const GemmKParams& p, uint32_t (&r)[32], const EpiPrefetch& pf) {
+__device__ __forceinline__ void epilogue_post(const GemmKParams& p, uint32_t (&r)[32], const EpiPrefetch& pf, const DropState& ds,
+                                              int row, int col0) {
   if (p.aux_in) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -319,6 +332,16 @@ __device__ __forceinline__ void epilogue_post(const GemmKParams& p, uint32_t (&r
   } else if (p.act == YMP_ACT_GELU_TANH) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(gelu_tanh(__uint_as_float(r[i])));
+  }
+  if (p.has_drop) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 w = drop_words(ds, (uint32_t)row, (uint32_t)(col0 >> 2) + j);
+      r[4 * j] = w.x >= ds.thresh ? __float_as_uint(__uint_as_float(r[4 * j]) * ds.scale) : 0u;
+      r[4 * j + 1] = w.y >= ds.thresh ? __float_as_uint(__uint_as_float(r[4 * j + 1]) * ds.scale) : 0u;
+      r[4 * j + 2] = w.z >= ds.thresh ? __float_as_uint(__uint_as_float(r[4 * j + 2]) * ds.scale) : 0u;
+      r[4 * j + 3] = w.w >= ds.thresh ? __float_as_uint(__uint_as_float(r[4 * j + 3]) * ds.scale) : 0u;
+    }
   }
   if (p.residual) {
     if (p.res_f32) {
@@ -499,6 +522,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     const int q = warp_idx & 3;              // TMEM lane quarter this warp may access
     const int half = (warp_idx - 4) >> 2;    // which half of the BN columns
     constexpr int CHUNKS = BN / 2 / 32;
+    DropState ds = {};
+    if (p.has_drop) ds = drop_state(p.drop);
     int as = 0;
     uint32_t aphase = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -522,7 +547,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
-        epilogue_chunk(p, r, row, n_blk * BN + coff, pf);
+        epilogue_chunk(p, r, row, n_blk * BN + coff, pf, ds);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -709,6 +734,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
     const int q = warp_idx & 3;
     const int half = (warp_idx - 4) >> 2;
     constexpr int CHUNKS = BN2 / 2 / 32;
+    DropState ds = {};
+    if (p.has_drop) ds = drop_state(p.drop);
     int as = 0;
     uint32_t aphase = 0;
     uint32_t ebox = 0;   // running count of this warp's bulk stores (staging buffer parity)
@@ -745,7 +772,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
             if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // always on the leader's barrier
           }
           epilogue_pre(p, r, pf);
-          if (!p.aux_out) epilogue_post(p, r, pf);
+          if (!p.aux_out) epilogue_post(p, r, pf, ds, row, col0);
           if (p.out_f32) {
             // one box per chunk (32 fp32 columns = 128 bytes per row); the two buffers alternate
             uint8_t* buf = ebuf + (ebox & 1) * EPI_BUF_BYTES;
@@ -816,7 +843,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // always on the leader's barrier
         }
-        epilogue_chunk(p, r, row, n_blk * BN2 + coff, pf);
+        epilogue_chunk(p, r, row, n_blk * BN2 + coff, pf, ds);
       }
       }
 #ifdef YMP_GEMM_DBG
@@ -922,9 +949,12 @@ static int launch_gemm(const ymp_gemm_args* a, const GemmKParams& kp, cudaStream
 static int launch_gemm_2cta(const ymp_gemm_args* a, GemmKParams kp, cudaStream_t stream) {
   CUtensorMap ta, tb, td, tx;
   int rc;
-  // TMA epilogue: plain row mapping, whole 64-column boxes, 16-byte aligned rows
+  // TMA epilogue (5 operand stages + staging) for the short-K, epilogue-bound GEMMs of the ViT (K = 768); the
+  // register epilogue with 6 operand stages stays faster when the main loop dominates (measured on one box,
+  // profiles/r02c_*: K >= 2048 shapes lose 5-8 % with 5 stages, K = 768 shapes gain 3-10 % from the bulk stores).
+  // Conditions: plain row mapping, whole 64-column boxes, 16-byte aligned rows
   static const bool no_tma_epi = [] { const char* e = getenv("YMP_GEMM_LEGACY_EPI"); return e && e[0] == '1'; }();
-  static const int tma_epi_max_k = [] { const char* e = getenv("YMP_GEMM_TMA_EPI_MAXK"); return e ? atoi(e) : (1 << 30); }();
+  static const int tma_epi_max_k = [] { const char* e = getenv("YMP_GEMM_TMA_EPI_MAXK"); return e ? atoi(e) : 1024; }();
   const bool f32 = a->out_dtype == YMP_DT_F32;
   kp.epi_tma = (!no_tma_epi && a->K <= tma_epi_max_k && a->N % 64 == 0 && a->d_row_block == 0 && (a->ldd * (f32 ? 4 : 2)) % 16 == 0 &&
                 !(f32 && a->aux_out)) ? 1 : 0;
@@ -986,6 +1016,8 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
                 "ymp_gemm: accumulate mode supports only alpha and bias-free linear epilogue");
   YMP_CHECK_ARG(a->res_row_mod >= 0 && a->d_row_block >= 0 && (a->d_row_block == 0 || a->d_row_stride >= a->d_row_block),
                 "ymp_gemm: bad res_row_mod / d_row_block / d_row_stride");
+  YMP_CHECK_ARG(!(a->drop.rng && a->drop.p > 0.f) || (a->drop.p < 1.f && !a->aux_out && !a->accumulate),
+                "ymp_gemm: dropout needs 0 < p < 1 and is not combined with aux_out / accumulate");
   YMP_CHECK_ARG(a->tile_n == 0 || a->tile_n == 128 || a->tile_n == 256 || a->tile_n == 512,
                 "ymp_gemm: tile_n must be 0 (auto), 128, 256 (1-CTA tiles) or 512 (= 256x256 CTA-pair tile)");
 
@@ -1041,6 +1073,8 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
   kp.n_fast = ((long)a->M >= (long)a->N) ? 1 : 0;
   kp.res_row_mod = a->res_row_mod; kp.d_row_block = a->d_row_block; kp.d_row_stride = a->d_row_stride;
   kp.epi_tma = 0;
+  kp.has_drop = (a->drop.rng && a->drop.p > 0.f) ? 1 : 0;
+  kp.drop.rng = a->drop.rng; kp.drop.site = a->drop.site; kp.drop.p = a->drop.p;
   auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
   const int esz = kp.out_f32 ? 4 : 2;
   kp.v32_d = al32(a->D) && (a->ldd * esz) % 32 == 0;

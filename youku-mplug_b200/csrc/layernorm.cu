@@ -1,6 +1,7 @@
 // LayerNorm forward / backward: one warp per row, 128-bit coalesced loads, fp32 statistics,
 // warp-shuffle reductions.  HBM-bound (reads x once, writes y once).
 #include "common.h"
+#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace ymp {
@@ -123,6 +124,8 @@ struct LnBwdParams {
   float* dbeta;
   const int32_t* in_rows;
   int rows, D, ldx, lddy, ldadd;
+  __nv_bfloat16* dx_drop;  // optional: dx with the dropout mask of the site that produced x applied
+  DropSpec drop;
 };
 
 template <int VPL, bool WGRAD, bool XF32>
@@ -138,6 +141,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, WGRAD ? (VPL <= 4 ? 3 : 1) : 4)
       for (int e = 0; e < 8; ++e) { dg[j][e] = 0.f; db[j][e] = 0.f; }
   }
   const uint4* g4 = reinterpret_cast<const uint4*>(p.gamma);
+  DropState ds = {};
+  if (p.dx_drop) ds = drop_state(p.drop);
   for (int row = blockIdx.x * LN_WARPS + warp; row < p.rows; row += gridDim.x * LN_WARPS) {
     const int irow = p.in_rows ? p.in_rows[row] : row;
     if (irow < 0) continue;  // padding slot of the forward: no input row behind it
@@ -184,6 +189,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32, WGRAD ? (VPL <= 4 ? 3 : 1) : 4)
           for (int e = 0; e < 8; ++e) o[e] += a[e];
         }
         dxr[vi] = pack8(o);
+        if (p.dx_drop) {  // gradient w.r.t. the pre-dropout branch output: same mask bits as the forward epilogue
+          drop4(ds, (uint32_t)irow, (uint32_t)(vi * 8), o[0], o[1], o[2], o[3]);
+          drop4(ds, (uint32_t)irow, (uint32_t)(vi * 8 + 4), o[4], o[5], o[6], o[7]);
+          reinterpret_cast<uint4*>(p.dx_drop + (size_t)irow * p.ldx)[vi] = pack8(o);
+        }
       }
     }
   }
@@ -259,6 +269,10 @@ extern "C" int ymp_layernorm_bwd(const ymp_layernorm_bwd_args* a, void* stream) 
   p.mean = a->mean; p.rstd = a->rstd; p.add = (const __nv_bfloat16*)a->add; p.dx = (__nv_bfloat16*)a->dx;
   p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.in_rows = a->in_rows;
   p.rows = a->rows; p.D = a->D; p.ldx = a->ldx; p.lddy = a->lddy; p.ldadd = a->ldadd;
+  const bool dropped = a->dx_drop && a->drop.rng && a->drop.p > 0.f;
+  YMP_CHECK_ARG(!a->dx_drop || (dropped && a->drop.p < 1.f && aligned16(a->dx_drop)), "ymp_layernorm_bwd: dx_drop needs a dropout spec with 0 < p < 1");
+  p.dx_drop = dropped ? (__nv_bfloat16*)a->dx_drop : nullptr;
+  p.drop.rng = a->drop.rng; p.drop.site = a->drop.site; p.drop.p = a->drop.p;
   cudaStream_t st = (cudaStream_t)stream;
   const int vpl = (a->D / 8 + 31) / 32;
   const bool wg = a->dgamma != nullptr;

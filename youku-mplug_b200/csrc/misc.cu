@@ -4,6 +4,7 @@
 #include <math_constants.h>
 
 #include "common.h"
+#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace ymp {
@@ -298,9 +299,50 @@ __global__ void __launch_bounds__(256) clip_normalize_kernel(const uint8_t* __re
   }
 }
 
+// ------------------------------------------------------------------------------ elementwise dropout
+// y[r, c] = dropout(x[r, c]) with the decoder's Philox convention (logical row = row0 + r): the embedding
+// dropout of GPT3Embedding.forward (models/modeling_distributed_gpt3.py:631).  HBM-bound, 4 columns per thread.
+template <bool F32>
+__global__ void __launch_bounds__(256) dropout_kernel(const void* __restrict__ x, void* __restrict__ y, int rows, int cols,
+                                                       int ldx, int ldy, long row0, const DropSpec d) {
+  const DropState ds = drop_state(d);
+  const int c4n = cols >> 2;
+  const long total = (long)rows * c4n;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / c4n), c4 = (int)(idx - (long)r * c4n);
+    float a, b, c, e;
+    if (F32) {
+      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + (size_t)r * ldx + 4 * c4);
+      a = v.x; b = v.y; c = v.z; e = v.w;
+    } else {
+      const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + (size_t)r * ldx + 4 * c4);
+      a = bf16_lo(v.x); b = bf16_hi(v.x); c = bf16_lo(v.y); e = bf16_hi(v.y);
+    }
+    drop4(ds, (uint32_t)(row0 + r), (uint32_t)(4 * c4), a, b, c, e);
+    if (F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + (size_t)r * ldy + 4 * c4) = make_float4(a, b, c, e);
+    else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + (size_t)r * ldy + 4 * c4) = make_uint2(pack_bf16(a, b), pack_bf16(c, e));
+  }
+}
+
 }  // namespace ymp
 
 using namespace ymp;
+
+extern "C" int ymp_dropout(const ymp_dropout_args* a, void* stream) {
+  YMP_CHECK_ARG(a && a->x && a->y && a->rows > 0 && a->cols > 0 && a->cols % 4 == 0, "ymp_dropout: bad args (cols must be a multiple of 4)");
+  YMP_CHECK_ARG(a->ldx % 4 == 0 && a->ldy % 4 == 0 && a->ldx >= a->cols && a->ldy >= a->cols, "ymp_dropout: bad ld");
+  YMP_CHECK_ARG(aligned16(a->x) && aligned16(a->y), "ymp_dropout: 16-byte alignment required");
+  YMP_CHECK_ARG(a->drop.rng && a->drop.p > 0.f && a->drop.p < 1.f, "ymp_dropout: needs rng and 0 < p < 1");
+  DropSpec d; d.rng = a->drop.rng; d.site = a->drop.site; d.p = a->drop.p;
+  const long total = (long)a->rows * (a->cols / 4);
+  const int blocks = (int)min((total + 255) / 256, (long)num_sms() * 8);
+  if (a->dtype == YMP_DT_F32)
+    dropout_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(a->x, a->y, a->rows, a->cols, a->ldx, a->ldy, (long)a->row0, d);
+  else
+    dropout_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(a->x, a->y, a->rows, a->cols, a->ldx, a->ldy, (long)a->row0, d);
+  YMP_LAUNCH_CHECK();
+  return YMP_OK;
+}
 
 extern "C" int ymp_im2col(const ymp_im2col_args* a, void* stream) {
   YMP_CHECK_ARG(a && a->video && a->out, "ymp_im2col: null pointer");

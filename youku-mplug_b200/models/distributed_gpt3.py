@@ -154,7 +154,7 @@ class DistributedGPT3_Pretrain(_PrefixModelBase):
         if not self.use_contrastive and not self.connect_ln:
             keys, params = self._fused_params()
             loss_caption, losses = YF.PretrainFn.apply(image, text.input_ids, targets, loss_mask,
-                                                       self.visual_encoder.vcfg, self.text_decoder.config.engine_cfg(),
+                                                       self.visual_encoder.vcfg, self.text_decoder.config.engine_cfg(self.text_decoder.training),
                                                        keys, *params)
             self.last_losses = losses
             return loss_caption, loss_caption.new_zeros(())   # device-side (CUDA-graph capturable)

@@ -79,10 +79,13 @@ class GPT3Config:
     def to_dict(self):
         return dict(self.__dict__)
 
-    def engine_cfg(self):
+    def engine_cfg(self, training=False):
+        """Dims + the dropout setting of one decoder pass: hidden_dropout / attention_dropout are live only in
+        train() mode (the reference keeps the frozen decoder in train mode during training)."""
         return dict(vocab_size=self.vocab_size, hidden_size=self.hidden_size, ffn_hidden_size=self.ffn_hidden_size,
                     num_hidden_layers=self.num_hidden_layers, num_attention_heads=self.num_attention_heads,
-                    max_position_embeddings=self.max_position_embeddings, layernorm_epsilon=self.layernorm_epsilon)
+                    max_position_embeddings=self.max_position_embeddings, layernorm_epsilon=self.layernorm_epsilon,
+                    hidden_dropout=self.hidden_dropout, attention_dropout=self.attention_dropout, training=bool(training))
 
 
 # ------------------------------------------------------------------------------------------ tokenizer
@@ -527,7 +530,7 @@ class DistributedGPT3(nn.Module):
         if labels is None:
             return self._decode(tokens, input_embeds, 0 if query_embeds is None else query_embeds.size(1))
         keys, params = self._param_list()
-        logits, losses, hidden = YF.GptFn.apply(input_embeds, labels.contiguous(), self.config.engine_cfg(), True,
+        logits, losses, hidden = YF.GptFn.apply(input_embeds, labels.contiguous(), self.config.engine_cfg(self.training), True,
                                                 keys, *params)
         if loss_mask is None:
             loss_mask = attention_mask[:, 1:].contiguous()

@@ -372,6 +372,27 @@ def attn_pool_bwd(W, G, c, dout):
 # ------------------------------------------------------------------------------------------
 # GPT-3 decoder
 # ------------------------------------------------------------------------------------------
+class GptDrop:
+    """Dropout of one decoder pass (the reference runs the frozen decoder in train() mode: hidden_dropout on the
+    embeddings and the two bias-dropout-adds, attention_dropout on the probabilities - modeling_distributed_gpt3.py:
+    631,732,1056-1078).  `rng` is the pass's {seed, offset} device tensor; the backward regenerates the same masks."""
+
+    def __init__(self, rng, p_hidden, p_attn):
+        self.rng, self.p_hidden, self.p_attn = rng, float(p_hidden), float(p_attn)
+
+    def embed(self):
+        return ops.Drop(self.rng, ops.site_embed(), self.p_hidden) if self.p_hidden > 0 else None
+
+    def attn(self, i):
+        return ops.Drop(self.rng, ops.site_attn(i), self.p_attn) if self.p_attn > 0 else None
+
+    def bda_attn(self, i):
+        return ops.Drop(self.rng, ops.site_bda_attn(i), self.p_hidden) if self.p_hidden > 0 else None
+
+    def bda_mlp(self, i):
+        return ops.Drop(self.rng, ops.site_bda_mlp(i), self.p_hidden) if self.p_hidden > 0 else None
+
+
 class GptDims:
     def __init__(self, gcfg):
         self.H = gcfg["hidden_size"]
@@ -385,65 +406,83 @@ class GptDims:
         self.scale = 1.0 / math.sqrt(self.hd)
 
 
-def gpt_layer_fwd(W, pre, x, g, B, S, train_w=False):
+def gpt_layer_fwd(W, pre, x, g, B, S, train_w=False, drop=None, li=0):
     """GPT3ParallelTransformerLayer.forward - models/modeling_distributed_gpt3.py:1034-1089
-    (dropout p=0; causal mask over the whole [prefix|text] sequence, :1329-1332)."""
+    (causal mask over the whole [prefix|text] sequence, :1329-1332; `drop`: GptDrop or None, li: layer index)."""
     H, hd = g.H, g.hd
     c = Ctx()
+    d_at = drop.attn(li) if drop else None
+    d_b1 = drop.bda_attn(li) if drop else None
+    d_b2 = drop.bda_mlp(li) if drop else None
     ln1, c.m1, c.r1 = ops.layernorm_fwd(x, W[pre + "input_layernorm.weight"], W[pre + "input_layernorm.bias"], g.eps)
     qkv = ops.gemm(ln1, W[pre + "self_attention.query_key_value.weight"], bias=W[pre + "self_attention.query_key_value.bias"])
     att = torch.empty((B * S, H), device=x.device, dtype=bf16)
     m = ops.dense_map(S)
     q, k, v = (TView(qkv, i * hd, 3 * hd, m) for i in range(3))  # rows grouped per head as [q|k|v] (:894-902)
     c.lse = ops.attn_fwd(q, k, v, TView(att, 0, hd, m), n_seq=B, n_heads=g.heads, head_dim=hd, s_q=S, s_kv=S,
-                         causal=True, scale=g.scale)
+                         causal=True, scale=g.scale, drop=d_at)
     x1 = ops.gemm(att, W[pre + "self_attention.dense.weight"], bias=W[pre + "self_attention.dense.bias"], residual=x,
-                  out_dtype=torch.float32)
+                  out_dtype=torch.float32, drop=d_b1)
     ln2, c.m2, c.r2 = ops.layernorm_fwd(x1, W[pre + "post_attention_layernorm.weight"], W[pre + "post_attention_layernorm.bias"], g.eps)
     dact = torch.empty((B * S, g.F), device=x.device, dtype=bf16)
     h = ops.gemm(ln2, W[pre + "mlp.dense_h_to_4h.weight"], bias=W[pre + "mlp.dense_h_to_4h.bias"], act=ACT_GELU_TANH, aux_out=dact)
     out = ops.gemm(h, W[pre + "mlp.dense_4h_to_h.weight"], bias=W[pre + "mlp.dense_4h_to_h.bias"], residual=x1,
-                   out_dtype=torch.float32)
+                   out_dtype=torch.float32, drop=d_b2)
     c.update(x=x, qkv=qkv, att=att, x1=x1, dact=dact)
     if train_w:
         c.update(ln1=ln1, ln2=ln2, h=h)
     return out, c
 
 
-def gpt_layer_bwd(W, G, pre, c, dout, g, B, S):
+def gpt_layer_bwd(W, G, pre, c, dout, g, B, S, drop=None, li=0, dout_d=None):
+    """dout: gradient of the layer output (residual stream).  With dropout, dout_d = dropout_backward(dout) for this
+    layer's MLP bias-dropout-add (the gradient of the branch output); returns (dx, dx_d) where dx_d is masked for the
+    dropout site that produced this layer's input (previous layer's MLP bias-dropout-add, or the embedding)."""
     hd = g.hd
     dev = dout.device
+    if dout_d is None:
+        dout_d = dout
     if "h" in c:
-        linear_wgrad(dout, c.h, pre + "mlp.dense_4h_to_h.weight", pre + "mlp.dense_4h_to_h.bias", G)
-    dpre = linear_dgrad(dout, W[pre + "mlp.dense_4h_to_h.weight"], act=ACT_GELU_TANH, aux_in=c.dact)
+        linear_wgrad(dout_d, c.h, pre + "mlp.dense_4h_to_h.weight", pre + "mlp.dense_4h_to_h.bias", G)
+    dpre = linear_dgrad(dout_d, W[pre + "mlp.dense_4h_to_h.weight"], act=ACT_GELU_TANH, aux_in=c.dact)
     if "ln2" in c:
         linear_wgrad(dpre, c.ln2, pre + "mlp.dense_h_to_4h.weight", pre + "mlp.dense_h_to_4h.bias", G)
     dln2 = linear_dgrad(dpre, W[pre + "mlp.dense_h_to_4h.weight"])
-    dx1 = ops.layernorm_bwd(dln2, c.x1, W[pre + "post_attention_layernorm.weight"], c.m2, c.r2, add=dout,
-                            dgamma=G.get(pre + "post_attention_layernorm.weight"), dbeta=G.get(pre + "post_attention_layernorm.bias"))
-    linear_wgrad(dx1, c.att, pre + "self_attention.dense.weight", pre + "self_attention.dense.bias", G)
-    datt = linear_dgrad(dx1, W[pre + "self_attention.dense.weight"])
+    d_b1 = drop.bda_attn(li) if drop else None
+    r = ops.layernorm_bwd(dln2, c.x1, W[pre + "post_attention_layernorm.weight"], c.m2, c.r2, add=dout,
+                          dgamma=G.get(pre + "post_attention_layernorm.weight"), dbeta=G.get(pre + "post_attention_layernorm.bias"),
+                          drop=d_b1)
+    dx1, dx1_d = r if d_b1 is not None else (r, r)
+    linear_wgrad(dx1_d, c.att, pre + "self_attention.dense.weight", pre + "self_attention.dense.bias", G)
+    datt = linear_dgrad(dx1_d, W[pre + "self_attention.dense.weight"])
     dqkv = torch.empty_like(c.qkv)
     m = ops.dense_map(S)
     q, k, v = (TView(c.qkv, i * hd, 3 * hd, m) for i in range(3))
     dq, dk, dv = (TView(dqkv, i * hd, 3 * hd, m) for i in range(3))
     ops.attn_bwd(q, k, v, TView(c.att, 0, hd, m), c.lse, TView(datt, 0, hd, m), dq, dk, dv, n_seq=B, n_heads=g.heads,
-                 head_dim=hd, s_q=S, s_kv=S, causal=True, scale=g.scale)
+                 head_dim=hd, s_q=S, s_kv=S, causal=True, scale=g.scale, drop=drop.attn(li) if drop else None)
     if "ln1" in c:
         linear_wgrad(dqkv, c.ln1, pre + "self_attention.query_key_value.weight", pre + "self_attention.query_key_value.bias", G)
     dln1 = linear_dgrad(dqkv, W[pre + "self_attention.query_key_value.weight"])
-    return ops.layernorm_bwd(dln1, c.x, W[pre + "input_layernorm.weight"], c.m1, c.r1, add=dx1,
-                             dgamma=G.get(pre + "input_layernorm.weight"), dbeta=G.get(pre + "input_layernorm.bias"))
+    d_in = (drop.bda_mlp(li - 1) if li > 0 else drop.embed()) if drop else None
+    r = ops.layernorm_bwd(dln1, c.x, W[pre + "input_layernorm.weight"], c.m1, c.r1, add=dx1,
+                          dgamma=G.get(pre + "input_layernorm.weight"), dbeta=G.get(pre + "input_layernorm.bias"), drop=d_in)
+    return r if d_in is not None else (r, r)
 
 
-def gpt_fwd(W, x, gcfg, B, S, train_w=False, save=True, out_rows=None):
+def gpt_fwd(W, x, gcfg, B, S, train_w=False, save=True, out_rows=None, drop=None):
     """x [B*S, H] fp32: input embeddings with the learned position embeddings already added
-    (GPT3Embedding.forward, :640-666).  Returns final-LN hidden states [B*S, H], or only the rows
-    listed in out_rows (int32 row indices, compact [len(out_rows), H]) when the caller needs no others."""
+    (GPT3Embedding.forward, :640-666); with `drop` (GptDrop) the embedding dropout (:631) is applied to x IN PLACE
+    first.  Returns final-LN hidden states [B*S, H], or only the rows listed in out_rows (int32 row indices,
+    compact [len(out_rows), H]) when the caller needs no others."""
     g = GptDims(gcfg)
-    c = Ctx(g=g, B=B, S=S, layers=[], out_rows=out_rows)
+    if drop is not None and drop.p_hidden <= 0 and drop.p_attn <= 0:
+        drop = None
+    c = Ctx(g=g, B=B, S=S, layers=[], out_rows=out_rows, drop=drop)
+    if drop is not None and drop.embed() is not None:
+        ops.dropout(x, drop.embed())
     for i in range(g.layers):
-        x, lc = gpt_layer_fwd(W, f"{GPT}encoder.layers.{i}.", x, g, B, S, train_w)
+        x, lc = gpt_layer_fwd(W, f"{GPT}encoder.layers.{i}.", x, g, B, S, train_w, drop, i)
         c.layers.append(lc if save else None)
     hid, c.mf, c.rf = ops.layernorm_fwd(x, W[GPT + "encoder.final_layernorm.weight"], W[GPT + "encoder.final_layernorm.bias"], g.eps,
                                         in_rows=out_rows)
@@ -453,17 +492,20 @@ def gpt_fwd(W, x, gcfg, B, S, train_w=False, save=True, out_rows=None):
 
 
 def gpt_bwd(W, G, c, dhid):
-    g, B, S = c.g, c.B, c.S
-    dx = None
+    """Returns the gradient w.r.t. the decoder input embeddings (before the embedding dropout when active)."""
+    g, B, S, drop = c.g, c.B, c.S, c.drop
+    dx = dx_d = None
     if c.out_rows is not None:  # rows without a consumer get no gradient from the final LayerNorm
         dx = torch.zeros((c.xL.shape[0], c.xL.shape[1]), device=dhid.device, dtype=torch.bfloat16)
-    dx = ops.layernorm_bwd(dhid, c.xL, W[GPT + "encoder.final_layernorm.weight"], c.mf, c.rf,
-                           dgamma=G.get(GPT + "encoder.final_layernorm.weight"), dbeta=G.get(GPT + "encoder.final_layernorm.bias"),
-                           in_rows=c.out_rows, dx=dx)
+    d_last = drop.bda_mlp(g.layers - 1) if drop else None
+    r = ops.layernorm_bwd(dhid, c.xL, W[GPT + "encoder.final_layernorm.weight"], c.mf, c.rf,
+                          dgamma=G.get(GPT + "encoder.final_layernorm.weight"), dbeta=G.get(GPT + "encoder.final_layernorm.bias"),
+                          in_rows=c.out_rows, dx=dx, drop=d_last)
+    dx, dx_d = r if d_last is not None else (r, r)
     for i in reversed(range(g.layers)):
-        dx = gpt_layer_bwd(W, G, f"{GPT}encoder.layers.{i}.", c.layers[i], dx, g, B, S)
+        dx, dx_d = gpt_layer_bwd(W, G, f"{GPT}encoder.layers.{i}.", c.layers[i], dx, g, B, S, drop, i, dx_d)
         c.layers[i] = None
-    return dx
+    return dx_d
 
 
 class KVCache:

@@ -90,6 +90,44 @@ class _GradStore:
                      for k, p in zip(keys, params))
 
 
+# ------------------------------------------------------------------------------------------ dropout RNG
+# One {seed, offset} pair per device, kept in DEVICE memory: every decoder pass takes a private copy (saved for
+# its backward, which regenerates the same masks) and advances the offset with an in-stream add, so a captured
+# CUDA graph draws fresh masks on every replay without host involvement.
+_RNG = {}
+
+
+def set_dropout_seed(seed, device=None):
+    """(Re)seed the decoder's dropout stream (default seed: torch.initial_seed() at first use)."""
+    if device is None:
+        _RNG.clear()
+        _RNG["seed"] = int(seed)
+    else:
+        dev = torch.device(device)
+        _RNG[dev] = dict(state=torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=dev),
+                         inc=torch.tensor([0, 1], dtype=torch.int64, device=dev))
+
+
+def _pass_rng(dev):
+    st = _RNG.get(dev)
+    if st is None:
+        set_dropout_seed(_RNG.get("seed", torch.initial_seed()), dev)
+        st = _RNG[dev]
+    rng = st["state"].clone()
+    st["state"].add_(st["inc"])
+    return rng
+
+
+def gpt_drop(gcfg, dev):
+    """engine.GptDrop for one decoder pass, or None (eval mode / both probabilities zero)."""
+    if not gcfg.get("training", False):
+        return None
+    ph, pa = float(gcfg.get("hidden_dropout", 0.0) or 0.0), float(gcfg.get("attention_dropout", 0.0) or 0.0)
+    if ph <= 0.0 and pa <= 0.0:
+        return None
+    return engine.GptDrop(_pass_rng(dev), ph, pa)
+
+
 _TEXT_ROWS = {}
 
 
@@ -136,7 +174,8 @@ class PretrainFn(torch.autograd.Function):
         # per-token losses are reported as 0.
         text_rows = _text_rows(B, S, Q, video.device)
         targets_t = targets[:, Q:].contiguous()
-        hid, cg = engine.gpt_fwd(W, x_in, gcfg, B, S, train_w=train_gpt, save=need_bwd, out_rows=text_rows)
+        hid, cg = engine.gpt_fwd(W, x_in, gcfg, B, S, train_w=train_gpt, save=need_bwd, out_rows=text_rows,
+                                 drop=gpt_drop(gcfg, video.device))
         logits, losses, lse = engine.lm_head_fwd(W, hid, targets_t)
         losses_bs = torch.zeros((B, S), device=video.device, dtype=torch.float32)
         losses_bs[:, Q:] = losses.view(B, L)
@@ -358,7 +397,8 @@ class GptFn(torch.autograd.Function):
         x_in = (input_embeds.float() + pos[:S][None].float()).reshape(B * S, H).contiguous()  # fp32 stream
         need_bwd = any(ctx.needs_input_grad)
         train_gpt = any(n for k, n in zip(keys, ctx.needs_input_grad[5:]) if k.startswith(engine.GPT + "encoder.layers"))
-        hid, cg = engine.gpt_fwd(W, x_in, gcfg, B, S, train_w=train_gpt, save=need_bwd)
+        hid, cg = engine.gpt_fwd(W, x_in, gcfg, B, S, train_w=train_gpt, save=need_bwd,
+                                 drop=gpt_drop(gcfg, input_embeds.device))
         logits = losses = lse = None
         if labels is not None or want_logits:
             lab = labels if labels is not None else torch.zeros((B, S), dtype=torch.long, device=input_embeds.device)

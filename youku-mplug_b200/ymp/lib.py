@@ -31,6 +31,10 @@ c_i32 = C.c_int32
 c_vp = C.c_void_p
 
 
+class DropoutSpec(C.Structure):
+    _fields_ = [("rng", c_vp), ("site", C.c_uint32), ("p", C.c_float)]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [
         ("A", c_vp), ("B", c_vp), ("D", c_vp),
@@ -42,6 +46,7 @@ class GemmArgs(C.Structure):
         ("out_dtype", c_i32), ("accumulate", c_i32), ("split_k", c_i32),
         ("alpha", C.c_float), ("tile_n", c_i32),
         ("res_row_mod", c_i32), ("d_row_block", c_i32), ("d_row_stride", c_i32), ("residual_dtype", c_i32),
+        ("drop", DropoutSpec),
     ]
 
 
@@ -58,6 +63,7 @@ class LayerNormBwdArgs(C.Structure):
         ("dy", c_vp), ("x", c_vp), ("gamma", c_vp), ("mean", c_vp), ("rstd", c_vp), ("add", c_vp),
         ("dx", c_vp), ("dgamma", c_vp), ("dbeta", c_vp), ("in_rows", c_vp),
         ("rows", c_i32), ("D", c_i32), ("ldx", c_i32), ("lddy", c_i32), ("ldadd", c_i32), ("x_dtype", c_i32),
+        ("dx_drop", c_vp), ("drop", DropoutSpec),
     ]
 
 
@@ -77,6 +83,7 @@ class AttnArgs(C.Structure):
         ("map_q", SeqMap), ("map_kv", SeqMap), ("map_o", SeqMap),
         ("n_seq", c_i32), ("n_heads", c_i32), ("head_dim", c_i32), ("s_q", c_i32), ("s_kv", c_i32),
         ("mask", c_i32), ("mask_block", c_i32), ("total_rows", C.c_int64), ("scale", C.c_float),
+        ("drop", DropoutSpec),
     ]
 
 
@@ -87,6 +94,11 @@ class AttnBwdArgs(C.Structure):
         ("do_head_stride", c_i32), ("dq_head_stride", c_i32), ("dk_head_stride", c_i32), ("dv_head_stride", c_i32),
         ("map_do", SeqMap), ("map_dq", SeqMap), ("map_dkv", SeqMap),
     ]
+
+
+class DropoutArgs(C.Structure):
+    _fields_ = [("x", c_vp), ("y", c_vp), ("rows", c_i32), ("cols", c_i32), ("ldx", c_i32), ("ldy", c_i32),
+                ("dtype", c_i32), ("row0", C.c_int64), ("drop", DropoutSpec)]
 
 
 class Im2colArgs(C.Structure):
@@ -153,6 +165,7 @@ _ce_bwd = _declare("ymp_ce_bwd", CeArgs)
 _colsum = _declare("ymp_colsum", ColsumArgs)
 _group = _declare("ymp_group_reduce", GroupArgs)
 _adamw = _declare("ymp_adamw", AdamwArgs)
+_dropout = _declare("ymp_dropout", DropoutArgs)
 _sumsq = lib.ymp_sumsq
 _sumsq.restype = C.c_int
 _sumsq.argtypes = [c_vp, C.c_int64, c_vp, c_vp]

@@ -12,13 +12,56 @@ from .lib import (ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH, DT_BF16, DT_F32,  # noq
 bf16 = torch.bfloat16
 
 
+class Drop:
+    """One dropout call site: (rng tensor {seed, offset} int64[2] on the device, site id, probability)."""
+    __slots__ = ("rng", "site", "p")
+
+    def __init__(self, rng, site, p):
+        assert rng.dtype == torch.int64 and rng.numel() == 2 and rng.is_cuda
+        self.rng, self.site, self.p = rng, int(site), float(p)
+
+
+def _set_drop(spec, drop):
+    if drop is not None and drop.p > 0.0:
+        spec.rng, spec.site, spec.p = drop.rng.data_ptr(), drop.site, drop.p
+
+
+def site_embed():
+    return 0
+
+
+def site_attn(layer):
+    return 4 * layer + 1
+
+
+def site_bda_attn(layer):
+    return 4 * layer + 2
+
+
+def site_bda_mlp(layer):
+    return 4 * layer + 3
+
+
+def dropout(x, drop, out=None, row0=0):
+    """y = dropout(x) for a 2-D bf16 / fp32 tensor with the decoder's Philox convention (in place by default)."""
+    _chk2d(x, "x")
+    out = x if out is None else out
+    assert out.dtype == x.dtype and out.shape == x.shape and x.dtype in (bf16, torch.float32)
+    a = L.DropoutArgs()
+    a.x, a.y, a.rows, a.cols, a.ldx, a.ldy = x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], x.stride(0), out.stride(0)
+    a.dtype, a.row0 = (DT_F32 if x.dtype == torch.float32 else DT_BF16), row0
+    _set_drop(a.drop, drop)
+    L.call(L._dropout, a, "ymp_dropout")
+    return out
+
+
 def _chk2d(t, name):
     assert t.is_cuda and t.dim() == 2 and t.stride(1) == 1, f"{name}: need 2-D row-major CUDA tensor"
 
 
 def gemm(a, b, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, aux_out=None,
          aux_in=None, out=None, out_dtype=bf16, accumulate=False, split_k=0, alpha=1.0, tile_n=0,
-         res_row_mod=0, d_row_block=0, d_row_stride=0):
+         res_row_mod=0, d_row_block=0, d_row_stride=0, drop=None):
     """D[M,N] = epilogue(alpha * op(A) @ op(B)^T).
 
     a: [M,K] (or [K,M] when a_t)      b: [N,K] like nn.Linear.weight (or [K,N] when b_t)
@@ -60,6 +103,7 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, 
     g.alpha = alpha
     g.tile_n = tile_n
     g.res_row_mod, g.d_row_block, g.d_row_stride = res_row_mod, d_row_block, d_row_stride
+    _set_drop(g.drop, drop)
     L.call(L._gemm, g, "ymp_gemm")
     return out
 
@@ -84,8 +128,10 @@ def layernorm_fwd(x, gamma, beta, eps, out=None, in_rows=None, rows=None, stats=
     return out, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, add=None, dgamma=None, dbeta=None, in_rows=None, dx=None):
-    """dx (+ add) and, when dgamma/dbeta (fp32, accumulated) are given, the affine grads."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, add=None, dgamma=None, dbeta=None, in_rows=None, dx=None, drop=None,
+                  dx_drop=None):
+    """dx (+ add) and, when dgamma/dbeta (fp32, accumulated) are given, the affine grads.  With `drop` the
+    kernel also writes dx_drop = dx * mask / (1 - p) for that dropout site (returned as the second value)."""
     _chk2d(dy, "dy"); _chk2d(x, "x")
     rows, D = dy.shape
     if dx is None:
@@ -98,6 +144,14 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, add=None, dgamma=None, dbeta=None, i
     a.ldadd = add.stride(0) if add is not None else 0
     a.x_dtype = DT_F32 if x.dtype == torch.float32 else DT_BF16
     assert dx.dtype == bf16 and dy.dtype == bf16
+    if drop is not None and drop.p > 0.0:
+        if dx_drop is None:
+            dx_drop = torch.empty_like(dx) if in_rows is None else torch.zeros_like(dx)
+        assert dx_drop.dtype == bf16 and dx_drop.stride(0) == dx.stride(0)
+        a.dx_drop = dx_drop.data_ptr()
+        _set_drop(a.drop, drop)
+        L.call(L._ln_bwd, a, "ymp_layernorm_bwd")
+        return dx, dx_drop
     L.call(L._ln_bwd, a, "ymp_layernorm_bwd")
     return dx
 
@@ -133,7 +187,7 @@ class TView:
         return self.t.stride(0)
 
 
-def _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, mask_block=0, total_rows=0):
+def _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, mask_block=0, total_rows=0, drop=None):
     a = L.AttnArgs()
     a.q, a.k, a.v, a.o, a.lse = q.p, k.p, v.p, o.p, L.ptr(lse)
     a.ldq, a.ldk, a.ldv, a.ldo = q.ld, k.ld, v.ld, o.ld
@@ -142,24 +196,25 @@ def _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, sca
     a.n_seq, a.n_heads, a.head_dim, a.s_q, a.s_kv = n_seq, n_heads, head_dim, s_q, s_kv
     # `causal` may be a bool or one of MASK_NONE / MASK_CAUSAL / MASK_BLOCK
     a.mask, a.mask_block, a.total_rows, a.scale = int(causal), mask_block, total_rows, scale
+    _set_drop(a.drop, drop)
     return a
 
 
 def attn_fwd(q, k, v, o, *, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, lse=None, mask_block=0,
-             total_rows=0):
+             total_rows=0, drop=None):
     """q,k,v,o: TView.  Returns lse [n_seq, n_heads, s_q] fp32."""
     if lse is None:
         lse = torch.empty((n_seq, n_heads, s_q), device=q.t.device, dtype=torch.float32)
-    a = _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, mask_block, total_rows)
+    a = _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, mask_block, total_rows, drop)
     L.call(L._attn_fwd, a, "ymp_attn_fwd")
     return lse
 
 
 def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, *, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale,
-             mask_block=0, total_rows=0):
+             mask_block=0, total_rows=0, drop=None):
     """dout,dq,dk,dv: TView (dk and dv share dk's seqmap)."""
     b = L.AttnBwdArgs()
-    b.fwd = _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, mask_block, total_rows)
+    b.fwd = _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, mask_block, total_rows, drop)
     delta = torch.empty_like(lse)
     b.delta_ws = delta.data_ptr()
     b.dout, b.dq, b.dk, b.dv = dout.p, dq.p, dk.p, dv.p
