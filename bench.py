@@ -29,6 +29,46 @@ for _p in (ROOT, PKG, os.path.join(ROOT, "tests")):
 METRIC = "video-text samples/sec (pretrain 1.3B, 8f x 224^2)"
 GF_PER_SAMPLE = 2563.8  # algorithmic fwd+bwd GFLOP per sample, SURVEY.md section 8(d) config 2
 
+# model dims of the BASELINE configs (configs/models/{clip-b16,config_gpt3_1.3B,config_gpt3_2.7B}.json of the
+# reference; the package's own copies live in youku-mplug_b200/configs/models/)
+VCFG_CLIP_B16 = dict(img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=8, mlp_ratio=4, num_frames=8, clip_model=True)
+GCFG = {"1.3B": dict(vocab_size=51200, hidden_size=2048, ffn_hidden_size=8192, num_hidden_layers=24, num_attention_heads=32,
+                     max_position_embeddings=2048, layernorm_epsilon=1e-5, init_method_std=0.02),
+        "2.7B": dict(vocab_size=51200, hidden_size=2560, ffn_hidden_size=10240, num_hidden_layers=32, num_attention_heads=32,
+                     max_position_embeddings=2048, layernorm_epsilon=1e-5, init_method_std=0.02)}
+# --config: (model class, decoder, frames, text length, batch/GPU, metric)
+CONFIGS = {
+    "pretrain": dict(cls="DistributedGPT3_Pretrain", gpt="1.3B", frames=8, text_len=128, batch=32, metric=METRIC,
+                     workload="mPLUG-Video GPT-3 1.3B pretrain step (BASELINE configs[1])"),
+    "caption27b": dict(cls="DistributedGPT3_Caption", gpt="2.7B", frames=16, text_len=256, batch=32,
+                       metric="video-text samples/sec (caption fine-tuning 2.7B, 16f x 224^2, text 256)",
+                       workload="mPLUG-Video GPT-3 2.7B caption fine-tuning step (BASELINE configs[3])"),
+    "retrieval": dict(cls="DistributedGPT3_Retrieval", gpt="1.3B", frames=8, text_len=80, batch=96,
+                      metric="video-text samples/sec (contrastive retrieval 1.3B, 8f x 224^2, text 80)",
+                      workload="mPLUG-Video GPT-3 1.3B contrastive retrieval step, feature all-gather across ranks (BASELINE configs[2])"),
+}
+
+
+def algorithmic_gflop(kind, vcfg, gcfg, T, L, Q):
+    """fwd+bwd GFLOP per sample as the reference computes the work (SURVEY.md section 8d formulas: multiply-add = 2,
+    full S x S attention, no recompute, frozen decoder = dgrad only, trainable encoder = dgrad + wgrad)."""
+    D, N, depth, V = vcfg["embed_dim"], (vcfg["img_size"] // vcfg["patch_size"]) ** 2, vcfg["depth"], gcfg["vocab_size"]
+    h, layers = gcfg["hidden_size"], gcfg["num_hidden_layers"]
+    TN = T * N
+    block = (2 * TN * D * 3 * D + 4 * N * T * T * D + 2 * (2 * TN * D * D) + 2 * T * (N + 1) * D * 3 * D + 4 * T * (N + 1) ** 2 * D
+             + 2 * T * (N + 1) * D * D + 4 * (TN + 1) * D * 4 * D)
+    vit = depth * block + 2 * TN * 768 * D
+    K = TN + 1
+    abstractor = 4 * Q * D * D + 4 * K * D * D + 4 * Q * (K + 1) * D + 16 * Q * D * D + 2 * Q * D * h
+    if kind == "retrieval":      # CLS-pooled ViT feature + text-only decoder pass (its LM head / CE is computed and unused)
+        S = L
+        fwd = vit + layers * (S * 24 * h * h + 4 * S * S * h) + 2 * S * h * V
+        return (fwd + 2 * vit) / 1e9          # nothing trainable sits below the decoder: no decoder backward
+    S = Q + L
+    gpt = layers * (S * 24 * h * h + 4 * S * S * h)
+    lm = 2 * S * h * V
+    return (vit + abstractor + gpt + lm + 2 * (vit + abstractor) + gpt + lm) / 1e9
+
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -102,11 +142,12 @@ def cpu_baseline(port, torch, T, L, Q, iters=1, warmup=1):
     train = set(port.trainable_keys(sd))
     psd = {k: v.requires_grad_(k in train) for k, v in sd.items()}
     g = torch.Generator().manual_seed(1234)
-    video = torch.randn(1, 3, T, 224, 224, generator=g)
-    ids = torch.randint(0, 51200, (1, L), generator=g)
-    att = torch.ones(1, L, dtype=torch.long)
+    video2 = torch.randn(2, 3, T, 224, 224, generator=g)
+    ids2 = torch.randint(0, 51200, (2, L), generator=g)
+    att2 = torch.ones(2, L, dtype=torch.long)
+    video, ids, att = video2[:1], ids2[:1], att2[:1]
 
-    def one():
+    def one(video=video, ids=ids, att=att):
         t0 = time.time()
         loss = port.pretrain_forward(video, ids, att, psd, vcfg, port.GCFG_1_3B)
         loss.backward()
@@ -121,8 +162,12 @@ def cpu_baseline(port, torch, T, L, Q, iters=1, warmup=1):
     else:
         times = [one() for _ in range(iters)]
     dt = statistics.median(times)
-    return 1.0 / dt, threads, (f"{len(times)} x (fwd+bwd of 1 sample, T={T}, L={L}, Q={Q}, fp32 torch CPU, {threads} threads, "
-                               f"{dt:.1f}s each, {warmup} warm-up){note}")
+    b2 = ""
+    if not note and dt < 20.0:     # batch 2 for the CPU path's own batch scaling, when the host is fast enough
+        t2 = statistics.median([one(video2, ids2, att2) for _ in range(2)])
+        b2 = f"; batch 2: {2.0 / t2:.3f} samples/s ({t2:.1f}s per step)"
+    return 1.0 / dt, threads, (f"median of {len(times)} x (fwd+bwd of 1 sample, T={T}, L={L}, Q={Q}, fp32 torch CPU, {threads} threads, "
+                               f"{dt:.1f}s each, {warmup} warm-up){note}{b2}")
 
 
 def run_reference(args, rank):
@@ -154,18 +199,20 @@ def run_ymp(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from helpers import make_model_dir, pretrain_config
-    from oracle import port
     import models.distributed_gpt3 as D
     import models.modeling_distributed_gpt3 as G
     from ymp import lib, ops, train
 
+    cfg = CONFIGS[args.config]
     B, T, L, Q = args.batch, args.frames, args.text_len, args.queries
-    vcfg = dict(port.VCFG_CLIP_B16, num_frames=T)
-    td = make_model_dir(vcfg, port.GCFG_1_3B)
+    gcfg = GCFG[cfg["gpt"]]
+    vcfg = dict(VCFG_CLIP_B16, num_frames=T)
+    td = make_model_dir(vcfg, gcfg, dropout=(args.dropout, args.dropout))
     torch.manual_seed(0)
     with torch.device(dev):
-        model = D.DistributedGPT3_Pretrain(config=pretrain_config(td, Q), tokenizer=None)
+        model = getattr(D, cfg["cls"])(config=pretrain_config(td, Q, num_frames=T), tokenizer=None)
     model = model.to(torch.bfloat16)
+    model.train()
     n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
     eng = train.TrainEngine(model, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.05, clip_grad=3.0)
 
@@ -174,12 +221,23 @@ def run_ymp(args, rank, local_rank, world):
     ids_h, att_h = make_text(G, B, L, 51200, 4321 + rank)
     ids_h, att_h = ids_h.pin_memory(), att_h.pin_memory()
     video_d = video_h.to(dev).bfloat16()
-    text_d = G.BatchEncoding(dict(input_ids=ids_h.to(dev), attention_mask=att_h.to(dev)))
+    extra_h = {}
+    if args.config == "caption27b":     # [prompt + caption] pairs: prompt tokens carry no loss (distributed_gpt3.py:760-766)
+        extra_h["prompt_lengths"] = torch.full((B,), 4, dtype=torch.long).pin_memory()
+    tail_h = ()
+    if args.config == "retrieval":      # video ids: equal ids are positives of each other (:944-958)
+        tail_h = (torch.arange(rank * B, (rank + 1) * B, dtype=torch.long).pin_memory(),)
+
+    def enc(ids, att, extra):
+        return G.BatchEncoding(dict(input_ids=ids, attention_mask=att, **extra))
+
+    text_d = enc(ids_h.to(dev), att_h.to(dev), {k: v.to(dev) for k, v in extra_h.items()})
+    tail_d = tuple(t.to(dev) for t in tail_h)
 
     use_graph = not args.no_graph
 
     def step_resident():
-        return eng.train_step(video_d, text_d, use_graph=use_graph)
+        return eng.train_step(video_d, text_d, *tail_d, use_graph=use_graph)
 
     from ymp.data import DevicePrefetcher
     pf = DevicePrefetcher(dev)
@@ -187,15 +245,19 @@ def run_ymp(args, rank, local_rank, world):
     def step_e2e():
         # every step copies one batch of pinned fp32 host frames (+ token ids, mask) to the device: the NEXT step's
         # batch is staged on a side stream while this step computes, as a prefetching loader does
+        host = (video_h, ids_h, att_h) + tuple(extra_h.values()) + tail_h
         if not len(pf):
-            pf.submit(video_h, ids_h, att_h)
-        v, ids_d, att_d = pf.take()
-        pf.submit(video_h, ids_h, att_h)
-        loss = eng.train_step(v, G.BatchEncoding(dict(input_ids=ids_d, attention_mask=att_d)), use_graph=use_graph)
+            pf.submit(*host)
+        got = pf.take()
+        pf.submit(*host)
+        v, ids_d, att_d = got[:3]
+        extra_d = dict(zip(extra_h.keys(), got[3:3 + len(extra_h)]))
+        loss = eng.train_step(v, enc(ids_d, att_d, extra_d), *got[3 + len(extra_h):], use_graph=use_graph)
         return loss.item()     # D2H read of the step's result, as the reference loop does (run_pretrain...py:115)
 
     def step_eager():
-        loss, _ = eng(video_d, text_d)
+        out = eng(video_d, text_d, *tail_d)
+        loss = sum(out[1:], out[0]) if isinstance(out, tuple) else out
         eng.backward(loss)
         eng.step()
         return loss
@@ -237,16 +299,20 @@ def run_ymp(args, rank, local_rank, world):
     # informational: the same end-to-end step fed with uint8 clips [B,T,H,W,3]: normalisation, layout
     # change and bf16 cast run on the device (ymp_clip_normalize), the host sends 1 byte per value
     frames_h = torch.randint(0, 256, (B, T, 224, 224, 3), generator=g, dtype=torch.uint8).pin_memory()
+    CLIP_MEAN = [0.48145466, 0.4578275, 0.40821073]   # dataset/__init__.py:69-72
+    CLIP_STD = [0.26862954, 0.26130258, 0.27577711]
 
     pf8 = DevicePrefetcher(dev)
 
     def step_e2e_u8():
+        host = (frames_h, ids_h, att_h) + tuple(extra_h.values()) + tail_h
         if not len(pf8):
-            pf8.submit(frames_h, ids_h, att_h)
-        f, ids_d, att_d = pf8.take()
-        pf8.submit(frames_h, ids_h, att_h)
-        v = ops.clip_normalize(f, port.CLIP_MEAN, port.CLIP_STD)
-        return eng.train_step(v, G.BatchEncoding(dict(input_ids=ids_d, attention_mask=att_d)), use_graph=use_graph).item()
+            pf8.submit(*host)
+        got = pf8.take()
+        pf8.submit(*host)
+        v = ops.clip_normalize(got[0], CLIP_MEAN, CLIP_STD)
+        extra_d = dict(zip(extra_h.keys(), got[3:3 + len(extra_h)]))
+        return eng.train_step(v, enc(got[1], got[2], extra_d), *got[3 + len(extra_h):], use_graph=use_graph).item()
 
     for _ in range(2):
         step_e2e_u8()
@@ -289,10 +355,13 @@ def run_ymp(args, rank, local_rank, world):
     pk = peaks()
     tf = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     ms_step = ms / args.steps
-    step_tf = GF_PER_SAMPLE * (B if (T, L, Q) == (8, 128, 128) else float("nan")) / ms_step  # GFLOP/ms == TFLOP/s
+    gf_sample = algorithmic_gflop(args.config, vcfg, gcfg, T, L, Q)
+    if args.config == "pretrain" and (T, L, Q) == (8, 128, 128):
+        assert abs(gf_sample - GF_PER_SAMPLE) < 0.5, gf_sample
+    step_tf = gf_sample * B / ms_step  # GFLOP/ms == TFLOP/s
     traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if os.path.exists(tpath) and (B, T, L, Q) == (32, 8, 128, 128):
+    if os.path.exists(tpath) and args.config == "pretrain" and (B, T, L, Q) == (32, 8, 128, 128):
         with open(tpath) as fh:
             tj = json.load(fh)
         traffic = tj["bytes_per_launch"]
@@ -308,12 +377,16 @@ def run_ymp(args, rank, local_rank, world):
     h2d = video_h.numel() * 4 + ids_h.numel() * 8 + att_h.numel() * 8
     if rank != 0:
         return
-    line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+    line = dict(metric=cfg["metric"], value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                 data="synthetic", impl="ymp_b200",
-                config=dict(workload="mPLUG-Video GPT-3 1.3B pretrain step (BASELINE configs[1])", batch_per_gpu=B,
+                config=dict(workload=cfg["workload"], model=cfg["cls"], decoder="GPT-3 " + cfg["gpt"], batch_per_gpu=B,
                             global_batch=B * world, frames=T, image=224, text_len=L, queries=Q, parallelism=f"dp{world}",
-                            trainable_params=n_train, step="fwd+bwd+allreduce+clip+AdamW, dropout 0", cuda_graph=use_graph,
+                            trainable_params=n_train,
+                            step=f"fwd+bwd+allreduce+clip+AdamW, decoder dropout {args.dropout:g}"
+                                 + (" (parity mode; the reference default 0.1: --dropout 0.1)" if args.dropout == 0 else
+                                    " (hidden + attention, Philox masks regenerated in the backward)"),
+                            cuda_graph=use_graph,
                             lm_head_rows="B*L text rows: the B*Q visual-prefix rows have loss_mask 0 in the reference "
                                          "(distributed_gpt3.py:142-159) and get no final-LN / LM-head / CE work; loss and all "
                                          "gradients are unchanged, algorithmic FLOPs still count them",
@@ -328,13 +401,18 @@ def run_ymp(args, rank, local_rank, world):
                                      ms_per_step=ms_e2e_u8 / args.steps,
                                      note="uint8 clips normalised on the device (N4); not the headline e2e"),
                 roofline=roofline,
-                step_model=dict(algorithmic_gflop_per_sample=GF_PER_SAMPLE, achieved_tflops=step_tf,
-                                frac_of_sustained_peak=step_tf / pk["tf_sustained"]),
+                step_model=dict(algorithmic_gflop_per_sample=gf_sample, achieved_tflops=step_tf,
+                                frac_of_sustained_peak=step_tf / pk["tf_sustained"],
+                                executed_gflop_per_sample=gf_sample - (2 * 2 * Q * gcfg["hidden_size"] * gcfg["vocab_size"] / 1e9
+                                                                       if args.config == "pretrain" else 0.0),
+                                note="executed = algorithmic minus the LM-head rows of the visual prefix (fwd + dgrad), which "
+                                     "carry loss_mask 0 and are skipped"),
                 final_loss=final_loss)
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.config == "pretrain":
         del eng, model
         torch.cuda.empty_cache()
-        val, cores, sample = cpu_baseline(port, torch, T, L, Q, iters=1, warmup=1)
+        from oracle import port          # the CPU restatement, timed as the baseline only (never on the product path)
+        val, cores, sample = cpu_baseline(port, torch, T, L, Q, iters=3, warmup=1)
         line["cpu_baseline"] = dict(value=val, unit="samples/s", cores=cores, kind="port", sample=sample)
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -347,10 +425,14 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ymp", choices=["ymp", "reference"])
-    ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--frames", type=int, default=8)
-    ap.add_argument("--text-len", type=int, default=128)
+    ap.add_argument("--config", default="pretrain", choices=sorted(CONFIGS),
+                    help="pretrain = BASELINE configs[1] (the headline); caption27b = configs[3]; retrieval = configs[2]")
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--frames", type=int, default=None)
+    ap.add_argument("--text-len", type=int, default=None)
     ap.add_argument("--queries", type=int, default=128)
+    ap.add_argument("--dropout", type=float, default=0.0,
+                    help="hidden + attention dropout of the (frozen, train-mode) decoder; the reference default is 0.1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-report", default=None, help="write per-shape GEMM timings of one step to this json file")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (no CUDA graph replay)")
@@ -358,6 +440,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    c = CONFIGS[args.config]
+    args.batch = args.batch or c["batch"]
+    args.frames = args.frames or c["frames"]
+    args.text_len = args.text_len or c["text_len"]
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -212,47 +212,45 @@ class TrainEngine:
         self.optimizer._global_grad_norm = _LazyNorm(self._sumsq.clone(), scale)
         self.flat_grad.zero_()
 
-    def train_step(self, video, text, use_graph=True, graph_warmup=2):
-        """One full iteration (forward + backward + step); returns loss_caption + loss_contrastive
-        (run_pretrain_distributed_gpt3.py:113) as a detached tensor.
+    def train_step(self, *inputs, use_graph=True, graph_warmup=2):
+        """One full iteration (forward + backward + step) of `self.module(*inputs)`; returns the detached loss -
+        for models that return several losses their sum, e.g. loss_caption + loss_contrastive
+        (run_pretrain_distributed_gpt3.py:113).
 
         Shapes are static in pre-training (`padding='max_length'`, run_pretrain_distributed_gpt3.py:100),
         so after `graph_warmup` eager iterations the ~900 kernel launches of forward+backward are
-        captured ONCE into a CUDA graph per input signature and replayed; the all-reduce, the
+        captured ONCE into a CUDA graph per input signature and replayed; with overlap_comm the bucketed gradient
+        all-reduces are part of the graph (fork/join on NCCL's stream); the remaining all-reduce, the
         grad-norm and the fused AdamW (6 launches) stay outside the graph.  Inputs are copied into the graph's static buffers (the copy
         also casts fp32 frames to bf16), so callers may pass fresh tensors every step."""
-        key = (tuple(video.shape), tuple(text.input_ids.shape))
+        key = tuple(_signature(x) for x in inputs)
         st = self._graphs.setdefault(key, dict(calls=0))
         if self.gas > 1:
             use_graph = False   # boundary / non-boundary micro-steps differ (all-reduce, step): run eagerly
+
+        def total(out):
+            return sum(out[1:], out[0]) if isinstance(out, (tuple, list)) else out
+
         if not use_graph or st["calls"] < graph_warmup:
-            loss_caption, loss_ita = self.module(video, text)
-            loss = loss_caption + loss_ita
+            loss = total(self.module(*inputs))
             self.backward(loss)
             self.step()
             st["calls"] += 1
             return loss.detach()
         if "graph" not in st:
-            from models.modeling_distributed_gpt3 import BatchEncoding
-            st["video"] = torch.empty(video.shape, device=video.device, dtype=torch.bfloat16)
-            st["ids"] = torch.empty_like(text.input_ids)
-            st["att"] = torch.empty_like(text.attention_mask)
-            st["video"].copy_(video)
-            st["ids"].copy_(text.input_ids)
-            st["att"].copy_(text.attention_mask)
-            static_text = BatchEncoding(dict(input_ids=st["ids"], attention_mask=st["att"]))
+            st["static"] = [_static_like(x) for x in inputs]
+            for s_, x in zip(st["static"], inputs):
+                _copy_into(s_, x)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                loss_caption, loss_ita = self.module(st["video"], static_text)
-                loss = loss_caption + loss_ita
+                loss = total(self.module(*st["static"]))
                 self._backward(loss / self.gas if self.gas > 1 else loss)
                 self._join_comm()   # the bucket all-reduces are part of the graph (fork/join on NCCL's stream)
             st["graph"], st["loss"], st["reduced"] = g, loss.detach(), list(self._reduced)
         else:
-            st["video"].copy_(video, non_blocking=True)
-            st["ids"].copy_(text.input_ids, non_blocking=True)
-            st["att"].copy_(text.attention_mask, non_blocking=True)
+            for s_, x in zip(st["static"], inputs):
+                _copy_into(s_, x)
         st["graph"].replay()
         self._reduced = list(st["reduced"])
         self.micro_steps += 1
@@ -286,6 +284,38 @@ class TrainEngine:
         self.exp_avg_sq.copy_(ck["exp_avg_sq"])
         self.global_steps = ck["global_steps"]
         return load_dir, ck.get("client_state", {})
+
+
+def _tensors_of(x):
+    """(container kind, {name: tensor}) of a model input: a tensor, or a BatchEncoding-like object with a dict
+    `data` of tensors (the tokenizer's output, models/modeling_distributed_gpt3.py:139-178)."""
+    if torch.is_tensor(x):
+        return {"": x}
+    if hasattr(x, "data") and isinstance(x.data, dict):
+        return {k: v for k, v in x.data.items() if torch.is_tensor(v)}
+    raise TypeError(f"train_step: unsupported input type {type(x).__name__}")
+
+
+def _signature(x):
+    if x is None:
+        return None
+    return tuple((k, tuple(v.shape), str(v.dtype)) for k, v in sorted(_tensors_of(x).items()))
+
+
+def _static_like(x):
+    if x is None:
+        return None
+    mk = lambda v: torch.empty(v.shape, device=v.device, dtype=torch.bfloat16 if v.is_floating_point() else v.dtype)  # noqa: E731
+    if torch.is_tensor(x):
+        return mk(x)
+    return type(x)({k: (mk(v) if torch.is_tensor(v) else v) for k, v in x.data.items()})
+
+
+def _copy_into(static, x):
+    if x is None:
+        return
+    for k, v in _tensors_of(x).items():
+        (static if k == "" else static.data[k]).copy_(v, non_blocking=True)
 
 
 class _LazyNorm:
