@@ -199,6 +199,71 @@ def run_dropout(name, vcfg, gcfg, Q, B, L, wseed, iseed, p_hidden=0.1, p_attn=0.
     print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
 
 
+def run_hostside(name):
+    """Pins the two host-side restatements that round 1 only checked against themselves:
+    (1) port.clip_to_model_input against the reference's own ClipToTensor + Normalize transform objects
+        (dataset/video_utils/volume_transforms.py:15-37, video_transforms.py:1405-1428 -> functional.normalize) -
+        the two modules are loaded from their files (the `dataset` package __init__ pulls in decord);
+    (2) the product's DistributedGPT3Tokenizer wrapper against the reference's (models/modeling_distributed_gpt3.py:
+        42-137,180-319: padding / truncation / [prompt, text] pairs / decode) on a tiny tokenizer.json, with a
+        whitespace `jieba.cut` stand-in on both sides (jieba is not in this image; the product falls back to the same
+        whitespace segmentation).  The reference's outputs are stored; tests/test_host_cpu.py replays them."""
+    import importlib.util
+    import tempfile
+    import types
+    import numpy as np
+
+    def load(modname, path):
+        spec = importlib.util.spec_from_file_location(modname, path)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+
+    vu = os.path.join(ref_shims.REFERENCE_ROOT, "dataset", "video_utils")
+    vol = load("ymp_ref_volume_transforms", os.path.join(vu, "volume_transforms.py"))
+    fn = load("ymp_ref_functional", os.path.join(vu, "functional.py"))
+    g = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (2, 3, 8, 16, 3), generator=g, dtype=torch.uint8)      # [B,T,H,W,C]
+    to_tensor = vol.ClipToTensor(channel_nb=3)
+    ref_t = torch.stack([fn.normalize(to_tensor(f), port.CLIP_MEAN, port.CLIP_STD) for f in frames])           # torch uint8 input
+    ref_n = torch.stack([fn.normalize(to_tensor(f.numpy()), port.CLIP_MEAN, port.CLIP_STD) for f in frames])   # numpy input (decord off)
+    assert torch.equal(ref_t, ref_n)
+    got = port.clip_to_model_input(frames)
+    assert torch.equal(got.view(torch.int16), ref_t.bfloat16().view(torch.int16)), "port.clip_to_model_input != reference transforms"
+    # ---- tokenizer wrapper
+    from tokenizers import Tokenizer, models as tk_models, pre_tokenizers
+    td = tempfile.mkdtemp(prefix="ymp_tok_")
+    vocab = {"<|endoftext|>": 0, "<sep>": 1, "[UNK]": 2, "\n": 3}
+    for i, w in enumerate("a b c d e f g hello world video cat dog".split()):
+        vocab[w] = 4 + i
+    tok = Tokenizer(tk_models.WordLevel(vocab, unk_token="[UNK]"))
+    tok.pre_tokenizer = pre_tokenizers.Whitespace()
+    tok.save(os.path.join(td, "tokenizer.json"))
+    jb = types.ModuleType("jieba")
+    jb.cut = lambda s: s.split()
+    jb.setLogLevel = lambda *_: None
+    sys.modules.setdefault("jieba", jb)
+    V, G, D = ref_shims.import_reference()
+    rt = G.DistributedGPT3Tokenizer(td)
+    cases = [dict(data=["hello world", "a b c d e f g"], padding="max_length", truncation=True, max_length=6),
+             dict(data=["hello world", "a b c"], padding="longest", truncation=True, max_length=64),
+             dict(data=[["video cat", "dog"], ["a b c d e f g", "hello world"]], padding="max_length", max_length=8),
+             dict(data=["cat dog video", "hello", "world world world world"], padding="max_length", truncation=True, max_length=4),
+             dict(data=[["hello", "a b c d e f g a b c"], ["a b", "c"]], padding="longest", truncation=True, max_length=7)]
+    outs = []
+    for c in cases:
+        kw = {k: v for k, v in c.items() if k != "data"}
+        o = rt(c["data"], return_tensors="pt", add_special_tokens=True, **kw)
+        outs.append({k: v.clone() for k, v in o.data.items() if torch.is_tensor(v)})
+    dec = rt.decode(torch.tensor([11, 12]))
+    fix = dict(name=name, clip_frames=frames, clip_out=ref_t, vocab=vocab, cases=cases, outputs=outs, decode_11_12=dec,
+               eos=rt.tokenizer.eos, torch_version=torch.__version__)
+    path = os.path.join(GOLD, name + ".pt")
+    torch.save(fix, path)
+    print(f"[{name}] reference clip transform == port (bit-exact); {len(cases)} tokenizer cases stored; wrote {path} "
+          f"({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
+
+
 def run_generate(name, vcfg, gcfg, Q, B, L, wseed, iseed, beam_size=3, n_new=6, pos_gain=30.0, ln_gain=16.0, stop_after=3):
     """Golden vectors for the generation path: the UNMODIFIED reference's per-sample beam
     search and batched greedy sampling over its KV cache, with the visual prefix, next to the oracle's
@@ -466,6 +531,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also the real 1.3B / T=8 / B=1 config (~6 GB RAM, minutes)")
     ap.add_argument("--caption27b", action="store_true", help="only the 2.7B caption config at its real dims (~35 GB RAM, minutes)")
+    ap.add_argument("--only-hostside", action="store_true", help="only the clip-transform / tokenizer fixture")
     ap.add_argument("--only-dropout", action="store_true", help="only (re)write the decoder-dropout fixture")
     ap.add_argument("--only-generate", action="store_true", help="only (re)write the generation fixture")
     ap.add_argument("--only-downstream", action="store_true", help="only (re)write the downstream-model fixture")
@@ -475,12 +541,16 @@ if __name__ == "__main__":
         run_caption_full("full_2p7b_caption_T16_B1", dict(port.VCFG_CLIP_B16, num_frames=16), port.GCFG_2_7B, Q=128, B=1, L=256,
                          wseed=0, iseed=4321)
         sys.exit(0)
+    if a.only_hostside:
+        run_hostside("tiny_hostside")
+        sys.exit(0)
     if a.only_dropout:
         run_dropout("tiny_pretrain_dropout", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=2, L=8, wseed=61, iseed=62)
         sys.exit(0)
     if a.only_downstream:
         run_downstream("tiny_downstream", port.VCFG_TINY, port.GCFG_TINY, Q=8, wseed=21)
         sys.exit(0)
+    run_hostside("tiny_hostside")
     run_generate("tiny_generate", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=2, L=8, wseed=51, iseed=52)
     if a.only_generate:
         sys.exit(0)

@@ -155,3 +155,26 @@ def test_clip_lut_equals_reference_ops():
     lut = ops.clip_lut(port.CLIP_MEAN, port.CLIP_STD, "cpu").view(3, 256)
     got = torch.stack([lut[c][frames[..., c].long()] for c in range(3)], dim=1)  # [B,C,T,H,W]
     assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+
+
+def test_hostside_fixture_from_the_reference():
+    """tests/golden/tiny_hostside.pt (oracle/make_golden.py run_hostside): the reference's own ClipToTensor + Normalize
+    output and the reference's own DistributedGPT3Tokenizer outputs; the oracle's clip restatement and the product's
+    tokenizer wrapper must reproduce them exactly (token ids, masks, prompt lengths are integer work)."""
+    import models.modeling_distributed_gpt3 as G
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "tiny_hostside.pt"), weights_only=False)
+    got = port.clip_to_model_input(fx["clip_frames"])
+    assert torch.equal(got.view(torch.int16), fx["clip_out"].bfloat16().view(torch.int16))
+    td = make_model_dir(port.VCFG_TINY, port.GCFG_TINY)
+    tok = Tokenizer(models.WordLevel(fx["vocab"], unk_token="[UNK]"))
+    tok.pre_tokenizer = pre_tokenizers.Whitespace()
+    tok.save(os.path.join(td, "tokenizer.json"))
+    tk = G.DistributedGPT3Tokenizer(td)
+    for case, want in zip(fx["cases"], fx["outputs"]):
+        kw = {k: v for k, v in case.items() if k != "data"}
+        out = tk(case["data"], return_tensors="pt", add_special_tokens=True, **kw)
+        for k, v in want.items():
+            assert torch.equal(getattr(out, k), v), (case, k, getattr(out, k), v)
+    assert tk.decode(torch.tensor([11, 12])) == fx["decode_11_12"]
+    assert tk.tokenizer.eos == fx["eos"]

@@ -445,3 +445,32 @@ def test_device_prefetcher_orders_copies(cuda):
     assert len(pf) == 0
     for t, v in ((a, 0.0), (b, 1.0), (c, 2.0), (d, 3.0)):
         assert t.is_cuda and float(t.sum()) == v * (1 << 20)
+
+
+@pytest.mark.parametrize("B,T,H,W,D,tile_n", [(3, 8, 64, 48, 128, 0), (2, 16, 32, 64, 256, 0), (5, 8, 224, 224, 768, 512), (2, 8, 48, 32, 768, 128)])
+def test_patch_embed_fused_im2col(cuda, B, T, H, W, D, tile_n):
+    """The patch embedding as ONE GEMM whose operand tiles are gathered from the video by 5-D TMA boxes (forward: A
+    operand; weight gradient: MN-major B operand) against the explicit im2col matrix (models/vision_transformer.py:392-398)."""
+    from ymp import ops
+    torch.manual_seed(31)
+    P, C = 16, 3
+    video = torch.randn(B, C, T, H, W, device=cuda).to(bf16)
+    w = (torch.randn(D, C * P * P, device=cuda) * 0.05).to(bf16)
+    bias = torch.randn(D, device=cuda).to(bf16)
+    N = (H // P) * (W // P)
+    table = torch.randn(N * T, D, device=cuda).to(bf16)
+    patches = ops.im2col(video, P)
+    want = ops.gemm(patches, w, bias=bias, residual=table, res_row_mod=N * T, out_dtype=torch.float32, tile_n=tile_n)
+    got = ops.patch_embed_gemm(video, w, P, bias=bias, residual=table, res_row_mod=N * T, out_dtype=torch.float32, tile_n=tile_n)
+    assert torch.equal(got, want)                       # same tiles, same accumulation order: bit-identical
+    ref = patches.float() @ w.float().t() + bias.float() + table.float().repeat(B, 1)
+    assert _rel(got, ref) < 1e-2
+    dy = torch.randn(B * N * T, D, device=cuda).to(bf16)
+    dw_want = torch.zeros(D, C * P * P, device=cuda)
+    ops.gemm(dy, patches, a_t=True, b_t=True, out=dw_want, accumulate=True, split_k=1, tile_n=tile_n)
+    dw = torch.zeros(D, C * P * P, device=cuda)
+    ops.gemm(dy, video.view(-1, W), a_t=True, b_t=True, out=dw, accumulate=True, split_k=1, tile_n=tile_n, _im2col=(P, B, C, T, H, W, 1))
+    assert torch.equal(dw, dw_want)
+    dw2 = torch.zeros(D, C * P * P, device=cuda)
+    ops.patch_embed_wgrad(dy, video, P, dw2)            # library-chosen tiles / split-K
+    assert _rel(dw2, dy.float().t() @ patches.float()) < 1e-2

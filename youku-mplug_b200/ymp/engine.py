@@ -201,12 +201,21 @@ def vit_fwd(W, video, vcfg, save=True):
     assert video.shape[2] == d.T, f"video has {video.shape[2]} frames, model expects {d.T}"
     dev = video.device
     c = Ctx(d=d, blocks=[])
-    patches = ops.im2col(video.contiguous(), d.P)
+    video = video.contiguous()
     pos, temb = W[VE + "pos_embed"], W[VE + "temporal_embed"]
     table = (pos[0, 1:, None, :] + temb[0, None, :, :]).reshape(d.N * d.T, d.D).contiguous()
     x0 = torch.empty((d.RB, d.D), device=dev, dtype=torch.float32)
     wp = W[VE + "patch_embed.proj.weight"].reshape(d.D, -1)
-    ops.gemm(patches, wp, bias=W.get(VE + "patch_embed.proj.bias"), residual=table, res_row_mod=d.N * d.T, out=x0[:d.R])
+    # PatchEmbed (:392-398) + position / temporal embedding add (:552-566) in ONE GEMM: the TMA producer gathers the
+    # 16x16 patches straight from the video (fused im2col), the epilogue adds bias and the (pos + temporal) table
+    fused = ops.fused_im2col_ok(d.T, d.P) and video.shape[1] * d.P * d.P % 64 == 0
+    patches = None
+    if fused:
+        ops.patch_embed_gemm(video, wp, d.P, bias=W.get(VE + "patch_embed.proj.bias"), residual=table, res_row_mod=d.N * d.T,
+                             out=x0[:d.R])
+    else:   # frame counts below 8 (tiny test configs): explicit patch matrix
+        patches = ops.im2col(video, d.P)
+        ops.gemm(patches, wp, bias=W.get(VE + "patch_embed.proj.bias"), residual=table, res_row_mod=d.N * d.T, out=x0[:d.R])
     x0[d.R:] = (W[VE + "cls_token"][0, 0].float() + pos[0, 0].float())
     if VE + "norm_pre.weight" in W:
         x, c.m0, c.r0 = ops.layernorm_fwd(x0, W[VE + "norm_pre.weight"], W[VE + "norm_pre.bias"], d.eps,
@@ -219,7 +228,7 @@ def vit_fwd(W, video, vcfg, save=True):
     rows = _final_gather_rows(d, dev)
     out, c.mf, c.rf = ops.layernorm_fwd(x, W[VE + "norm.weight"], W[VE + "norm.bias"], d.eps, in_rows=rows)
     if save:
-        c.update(patches=patches, x0=x0, xL=x, rows=rows)
+        c.update(patches=patches, video=video if fused else None, x0=x0, xL=x, rows=rows)
     return out, c
 
 
@@ -256,7 +265,13 @@ def vit_bwd(W, G, c, d_out):
             G[VE + "pos_embed"].view(d.N + 1, d.D)[1:].add_(dtab.sum(1))
         if VE + "temporal_embed" in G:
             G[VE + "temporal_embed"].view(d.T, d.D).add_(dtab.sum(0))
-    linear_wgrad(dx0[:d.R], c.patches, VE + "patch_embed.proj.weight", VE + "patch_embed.proj.bias", G)
+    if c.patches is not None:
+        linear_wgrad(dx0[:d.R], c.patches, VE + "patch_embed.proj.weight", VE + "patch_embed.proj.bias", G)
+    else:   # fused im2col on the B operand of the weight-gradient GEMM
+        if VE + "patch_embed.proj.weight" in G:
+            ops.patch_embed_wgrad(dx0[:d.R], c.video, d.P, G[VE + "patch_embed.proj.weight"].view(d.D, -1))
+        if VE + "patch_embed.proj.bias" in G:
+            ops.colsum(dx0[:d.R], G[VE + "patch_embed.proj.bias"])
 
 
 # ------------------------------------------------------------------------------------------
