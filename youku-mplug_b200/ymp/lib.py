@@ -136,7 +136,7 @@ class AdamwArgs(C.Structure):
     _fields_ = [("master", c_vp), ("param", c_vp), ("grad", c_vp), ("m", c_vp), ("v", c_vp), ("sumsq", c_vp),
                 ("n", C.c_int64), ("step", c_i32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("eps", C.c_float), ("weight_decay", C.c_float), ("grad_scale", C.c_float),
-                ("max_grad_norm", C.c_float), ("hyper", c_vp)]
+                ("max_grad_norm", C.c_float), ("hyper", c_vp), ("zero_grad", c_i32)]
 
 
 lib.ymp_last_error.restype = C.c_char_p

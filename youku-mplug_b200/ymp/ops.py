@@ -400,7 +400,7 @@ def sumsq(g, out):
 
 
 def adamw(master, param, grad, m, v, *, step, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0,
-          max_grad_norm=0.0, sumsq_t=None, hyper=None):
+          max_grad_norm=0.0, sumsq_t=None, hyper=None, zero_grad=False):
     a = L.AdamwArgs()
     a.hyper = L.ptr(hyper)
     a.master, a.param, a.grad, a.m, a.v = master.data_ptr(), param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr()
@@ -408,4 +408,5 @@ def adamw(master, param, grad, m, v, *, step, lr, beta1, beta2, eps, weight_deca
     a.n, a.step = master.numel(), step
     a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = lr, beta1, beta2, eps, weight_decay
     a.grad_scale, a.max_grad_norm = grad_scale, max_grad_norm
+    a.zero_grad = int(zero_grad)
     L.call(L._adamw, a, "ymp_adamw")

@@ -208,9 +208,9 @@ class TrainEngine:
             ops.adamw(self.master[a:b], self.flat_param[a:b], self.flat_grad[a:b], self.exp_avg[a:b],
                       self.exp_avg_sq[a:b], step=self.global_steps, lr=g["lr"], beta1=g["betas"][0], beta2=g["betas"][1],
                       eps=g["eps"], weight_decay=g["weight_decay"], grad_scale=scale,
-                      max_grad_norm=self.clip_grad or 0.0, sumsq_t=self._sumsq if self.clip_grad else None)
+                      max_grad_norm=self.clip_grad or 0.0, sumsq_t=self._sumsq if self.clip_grad else None, zero_grad=True)
         self.optimizer._global_grad_norm = _LazyNorm(self._sumsq.clone(), scale)
-        self.flat_grad.zero_()
+        # every group range was reset by its AdamW pass (the ranges tile the flat buffer)
 
     def train_step(self, *inputs, use_graph=True, graph_warmup=2):
         """One full iteration (forward + backward + step) of `self.module(*inputs)`; returns the detached loss -
