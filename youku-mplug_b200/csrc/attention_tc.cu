@@ -422,6 +422,291 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) 
 }
 
 // ======================================================================================================
+// Pair-tile forward for s_q, s_kv <= 256 (ViT spatial 197, GPT causal 256): one PERSISTENT CTA per SM walks over
+// (sequence, head) items.  Per item K / V are fetched ONCE for both 128-row query tiles (the single-tile kernel
+// above fetches them per tile: +33 % HBM traffic at 197 rows) into one of two shared-memory stages - the next
+// item's K / V / Q arrive behind the current item's MMAs and softmax (cp.async issued a whole item ahead), so no
+// load latency is exposed.  Warpgroup w owns query tile w: its own Q tile, its own 256 TMEM columns, its own
+// mbarriers, one thread per query row over all key columns (S in [0,nkv), packed P over the consumed front half
+// [0,nkv/2), O in [128,128+HD)); the two warpgroups drift apart, so one tile's softmax overlaps the other's MMAs.
+// Output rows are staged in the item's (by then idle) K / V stage and written with coalesced 16-byte accesses.
+// ======================================================================================================
+template <int HD>
+__device__ __forceinline__ void tc_load128(uint8_t* blk0, uint8_t* blk1, const TcMat& m, int r0, int rows, int n_valid, int hd, int t) {
+  constexpr int CPT = HD / 32;
+  const int rl = t >> 2, c0 = t & 3;
+  for (int rb = 0; rb < rows; rb += 32) {
+    const int r = rb + rl;
+    if (r >= rows) break;
+    const bool rv = r0 + r < n_valid;
+    const __nv_bfloat16* g = rv ? tc_row(m, r0 + r) : nullptr;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const int c = c0 + 4 * j;
+      uint8_t* dst = (c < 8) ? blk0 + sw128_off(r, c) : blk1 + sw64_off(r, c - 8);
+      if (rv && c * 8 < hd) cp16(dst, g + c * 8);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+__device__ __forceinline__ void wg_sync(int w) { asm volatile("bar.sync %0, 128;" ::"r"(1 + w) : "memory"); }
+
+template <int HD>
+__global__ void __launch_bounds__(256, 1) attn_tc_fwd_pair_kernel(const AttnTcParams p) {
+  static_assert(HD == 64 || HD == 96, "head_dim 64 or 96 (80 / 88 are padded to 96)");
+  constexpr bool TWO = (HD == 96);
+  constexpr int PITCH = HD * 2 + 16;                    // staging row pitch (the pad spreads the banks)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  const int kvr = p.kv_rows;
+  const int QT0 = 128 * 128, QT1 = TWO ? 128 * 64 : 0;                 // bytes of one Q tile (128 B + 64 B column blocks)
+  const int KB0 = kvr * 128, KB1 = TWO ? kvr * 64 : 0;                  // bytes of one K (or V) block pair
+  const int STG = 2 * (KB0 + KB1);                                      // one stage: K0 K1 V0 V1
+  uint8_t* qs = smem;                                                   // [2 tiles][QT0 + QT1]
+  uint8_t* kvs = qs + 2 * (QT0 + QT1);                                  // [2 stages][STG]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(kvs + 2 * STG);          // bar_s[2], bar_o[2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int w = warp >> 2, wq = warp & 3, t = tid & 127;   // warpgroup = query tile, TMEM lane quarter, thread in group
+  const int n_items = p.n_seq * p.n_heads;
+
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  if (tid == 32) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], (i >= 2 && TWO) ? 2 : 1);
+    fence_mbar_init();
+  }
+  DropState ds = {};
+  if (p.has_drop) ds = drop_state(p.drop);
+
+  // loads of one item: K, V by all 256 threads, the Q tile of warpgroup w by its 128 threads
+  auto item_len = [&](int it, int& sq, int& skv) {
+    sq = p.s_q; skv = p.s_kv;
+    if (p.total_rows > 0) {
+      const long left = p.total_rows - (long)(it / p.n_heads) * p.s_q;
+      if (left < sq) sq = (int)max(left, 0l);
+      if (left < skv) skv = (int)max(left, 0l);
+    }
+  };
+  auto load_kv = [&](int it, int stage) {
+    int sq, skv;
+    item_len(it, sq, skv);
+    const int s = it / p.n_heads, h = it - s * p.n_heads;
+    const TcMat Mk = tc_mat(p.k, p.mkv, s, p.ldk, h * p.hsk), Mv = tc_mat(p.v, p.mkv, s, p.ldv, h * p.hsv);
+    uint8_t* st = kvs + stage * STG;
+    const int nk = (skv + 31) & ~31;
+    tc_load256<HD>(st, st + KB0, Mk, 0, nk, skv, p.hd);
+    tc_load256<HD>(st + KB0 + KB1, st + 2 * KB0 + KB1, Mv, 0, nk, skv, p.hd);
+  };
+  auto load_q = [&](int it) {
+    int sq, skv;
+    item_len(it, sq, skv);
+    if (w * 128 >= sq) return;
+    const int s = it / p.n_heads, h = it - s * p.n_heads;
+    const TcMat Mq = tc_mat(p.q, p.mq, s, p.ldq, h * p.hsq);
+    uint8_t* q0 = qs + w * (QT0 + QT1);
+    tc_load128<HD>(q0, q0 + QT0, Mq, w * 128, 128, sq, p.hd, t);
+  };
+
+  int item = blockIdx.x;
+  if (item < n_items) { load_kv(item, 0); load_q(item); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr + (uint32_t)(w * 256);                // this warpgroup's 256 columns
+  const uint32_t tl = tmem + ((uint32_t)(wq * 32) << 16);
+  const bool stage_ok = kvr * (HD * 2) >= 128 * PITCH;                  // the K (V) stage can hold a staged output tile
+
+  uint32_t n0 = 0, n1 = 0;   // how many items so far had a tile 0 / a tile 1: the phases of bar_s / bar_o of each tile
+  for (int k = 0; item < n_items; item += gridDim.x, ++k) {
+    const int stage = k & 1;
+    int sq, skv;
+    item_len(item, sq, skv);
+    const uint32_t par0 = n0 & 1, par1 = n1 & 1, par = w ? par1 : par0;
+    n0 += sq > 0 ? 1 : 0;
+    n1 += sq > 128 ? 1 : 0;
+    const int s = item / p.n_heads, h = item - s * p.n_heads;
+    uint8_t* st = kvs + stage * STG;
+    uint8_t *k0s = st, *k1s = st + KB0, *v0s = st + KB0 + KB1, *v1s = st + 2 * KB0 + KB1;
+    uint8_t *q0s = qs + w * (QT0 + QT1), *q1s = q0s + QT0;
+    const bool have = w * 128 < sq;                                     // this warpgroup's tile exists
+    const int q0 = w * 128;
+    int kv_end = skv;
+    if (p.mask == TC_MASK_CAUSAL) kv_end = min(skv, q0 + 128 + (p.s_kv - p.s_q));
+    const int nkv = (kv_end + 31) & ~31;
+
+    // ---- (A) this item's K / V / Q have landed; everybody has left the previous item
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // ---- (B) S = Q K^T of this tile, issued by the warpgroup's first thread
+    if (have && t == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, nkv, 0, 0);
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) {
+        uint64_t ad, bd;
+        if (ks < 4) {
+          ad = desc_sw(smem_u32(q0s) + ks * 32, 1024, LAYOUT_SW128);
+          bd = desc_sw(smem_u32(k0s) + ks * 32, 1024, LAYOUT_SW128);
+        } else {
+          ad = desc_sw(smem_u32(q1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
+          bd = desc_sw(smem_u32(k1s) + (ks - 4) * 32, 512, LAYOUT_SW64);
+        }
+        umma_bf16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      }
+      umma_commit(&bar[w]);
+    }
+    // the next item's K / V stream into the other stage behind everything that follows
+    const int nxt = item + gridDim.x;
+    if (nxt < n_items) load_kv(nxt, stage ^ 1);
+    if (!have) {           // (warpgroup-uniform; the CTA-wide barrier of the next iteration still sees these threads)
+      if (nxt < n_items) load_q(nxt);
+      continue;
+    }
+
+    mbar_wait(&bar[w], par);
+    tc_fence_after();
+    if (nxt < n_items) load_q(nxt);                                     // Q tile consumed: fetch the next item's
+
+    // ---- (C) softmax, one thread per query row
+    const int rl = wq * 32 + lane, row = q0 + rl;
+    int lo = 0, hi = kv_end;
+    if (p.mask == TC_MASK_CAUSAL) hi = min(hi, row + 1 + (p.s_kv - p.s_q));
+    const int nch = nkv / 32;
+    const uint32_t drow = ((uint32_t)s * p.n_heads + h) * p.s_q + row;
+    float mx = -CUDART_INF_F;
+    for (int c = 0; c < nch; ++c) {
+      if (__all_sync(0xffffffffu, c * 32 >= hi || c * 32 + 32 <= lo)) continue;
+      uint32_t r[32];
+      tmem_ld32(tl + c * 32, r);
+      tmem_ld_wait();
+      if (c * 32 >= lo && c * 32 + 32 <= hi) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = c * 32 + i;
+          if (col >= lo && col < hi) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+      }
+    }
+    const float ms = (mx == -CUDART_INF_F) ? 0.f : mx * p.scale_log2;
+    float lsum = 0.f;
+    for (int c = 0; c < nch; ++c) {
+      uint32_t pk[16];
+      if (__all_sync(0xffffffffu, c * 32 >= hi || c * 32 + 32 <= lo)) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+      } else {
+        uint32_t r[32];
+        tmem_ld32(tl + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+        if (c * 32 >= lo && c * 32 + 32 <= hi) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pv[i] = exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -ms));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = c * 32 + i;
+            pv[i] = (col >= lo && col < hi) ? exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -ms)) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) lsum += pv[i];
+        if (p.has_drop) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) drop4(ds, drow, (uint32_t)(c * 32 + 4 * j), pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+      }
+      tmem_st16(tl + c * 16, pk);   // packed P over the front half of S: chunk c lands inside chunk c/2, already consumed
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    wg_sync(w);
+    tc_fence_after();
+
+    // ---- O = P V (A = P from TMEM, B = V MN-major): 64-column part by thread 0, the 32-column rest by thread 32
+    if (t == 0 || (TWO && t == 32)) {
+      const bool second = t == 32;
+      const uint32_t idesc = second ? make_idesc_bf16(128, 32, 0, 1) : make_idesc_bf16(128, 64, 0, 1);
+      const uint32_t ocol = tmem + (second ? 192 : 128);
+      const uint32_t vb = smem_u32(second ? v1s : v0s);
+      for (int ks = 0; ks < nkv / 16; ++ks)
+        umma_ts(ocol, tmem + ks * 8, second ? desc_sw(vb + ks * 1024, 512, LAYOUT_SW64) : desc_sw(vb + ks * 2048, 1024, LAYOUT_SW128), idesc,
+                ks > 0 ? 1u : 0u);
+      umma_commit(&bar[2 + w]);
+    }
+    mbar_wait(&bar[2 + w], par);
+    tc_fence_after();
+
+    // ---- epilogue: rows staged in this item's idle K (tile 0) / V (tile 1) stage, then coalesced stores
+    const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+    const TcMat Mo = tc_mat(p.o, p.mo, s, p.ldo, h * p.hso);
+    if (row < sq && p.lse) p.lse[((size_t)s * p.n_heads + h) * p.s_q + row] = mx * p.scale + logf(lsum);
+    uint8_t* stg = w ? v0s : k0s;
+    if (stage_ok && w == 0 && sq > 128) mbar_wait(&bar[1], par1);      // tile 1's S MMA reads K until its barrier flips
+    if (stage_ok && w == 1) mbar_wait(&bar[2], par0);                   // tile 0's P V MMA reads V until its barrier flips
+#pragma unroll
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tl + (c < 2 ? 128 + c * 32 : 192), r);
+      tmem_ld_wait();
+      if (stage_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(stg + rl * PITCH + c * 64 + g * 16) =
+              make_uint4(pack_bf16(__uint_as_float(r[8 * g]) * inv, __uint_as_float(r[8 * g + 1]) * inv),
+                         pack_bf16(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv),
+                         pack_bf16(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv),
+                         pack_bf16(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv));
+      } else if (row < sq) {
+        __nv_bfloat16* orow = const_cast<__nv_bfloat16*>(tc_row(Mo, row));
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (c * 32 + g * 8 >= p.hd) break;
+          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) =
+              make_uint4(pack_bf16(__uint_as_float(r[8 * g]) * inv, __uint_as_float(r[8 * g + 1]) * inv),
+                         pack_bf16(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv),
+                         pack_bf16(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv),
+                         pack_bf16(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv));
+        }
+      }
+    }
+    tc_fence_before();   // the next item's S MMA overwrites these TMEM columns: ordered by the CTA barrier at (A)
+    if (stage_ok) {
+      wg_sync(w);
+      constexpr int CPT = HD / 32;
+      const int srl = t >> 2, c0 = t & 3;
+#pragma unroll
+      for (int rb = 0; rb < 128; rb += 32) {
+        const int r = rb + srl;
+        if (q0 + r < sq) {
+          __nv_bfloat16* g = const_cast<__nv_bfloat16*>(tc_row(Mo, q0 + r));
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) {
+            const int c = c0 + 4 * j;
+            if (c * 8 < p.hd) *reinterpret_cast<uint4*>(g + c * 8) = *reinterpret_cast<const uint4*>(stg + r * PITCH + c * 16);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(*tmem_ptr);
+  }
+}
+
+// ======================================================================================================
 // tcgen05 attention backward, any s_kv, s_q <= 2048 (per-query statistics live in shared memory).
 // One CTA (256 threads) = one (sequence, head).
 // Everything is computed in the TRANSPOSED frame (TMEM lane = key row, TMEM column = query row) so that
@@ -848,6 +1133,19 @@ static int launch_tc(const AttnTcParams& p, cudaStream_t st) {
   return YMP_OK;
 }
 
+template <int HD>
+static int launch_tc_pair(const AttnTcParams& p, int smem, cudaStream_t st) {
+  static int cur = 0;
+  if (smem > cur) {
+    YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_pair_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cur = smem;
+  }
+  const int items = p.n_seq * p.n_heads;
+  attn_tc_fwd_pair_kernel<HD><<<min(items, num_sms()), 256, smem, st>>>(p);
+  YMP_LAUNCH_CHECK();
+  return YMP_OK;
+}
+
 static bool tc_head_dim(int hd) { return hd == 64 || hd == 80 || hd == 88 || hd == 96; }
 
 // Returns YMP_ENOSUP (without setting an error) when the configuration is outside this kernel's domain.
@@ -874,6 +1172,13 @@ int attn_tc_fwd_try(const ymp_attn_args* a, cudaStream_t st) {
   p.drop.rng = a->drop.rng; p.drop.site = a->drop.site; p.drop.p = a->drop.p;
   const bool lng = a->s_kv > 256;
   p.kv_rows = lng ? 256 : ((a->s_kv + 31) & ~31);
+  // pair-tile persistent kernel: both query tiles of a (sequence, head) share one K / V fetch, two stages in flight
+  static const bool no_pair = [] { const char* e = getenv("YMP_ATTN_NO_PAIR"); return e && e[0] == '1'; }();
+  if (!lng && !no_pair && a->s_q > 128 && a->s_q <= 256 && (a->mask == YMP_MASK_NONE || a->mask == YMP_MASK_CAUSAL)) {
+    const int HDp = a->head_dim == 64 ? 64 : 96;
+    const int smem = 2 * 128 * HDp * 2 + 2 * 2 * p.kv_rows * HDp * 2 + 64 + 1024;
+    if (smem <= 227 * 1024) return HDp == 64 ? launch_tc_pair<64>(p, smem, st) : launch_tc_pair<96>(p, smem, st);
+  }
   if (a->head_dim == 64) return lng ? launch_tc<64, true>(p, st) : launch_tc<64, false>(p, st);
   return lng ? launch_tc<96, true>(p, st) : launch_tc<96, false>(p, st);
 }

@@ -115,6 +115,14 @@ class _PrefixModelBase(nn.Module):
         return {'visual_encoder.pos_embed', 'visual_encoder.cls_token', 'visual_encoder.temporal_embed'}
 
 
+def mask_prompt(text_loss_atts, prompt_lengths):
+    """text_loss_atts[i, :prompt_lengths[i]] = 0 for every sample (the reference loops over `.cpu().tolist()`,
+    models/distributed_gpt3.py:760-766) as one device-side comparison: same integers, no host synchronisation, so
+    the step stays CUDA-graph capturable."""
+    pos = torch.arange(text_loss_atts.shape[1], device=text_loss_atts.device)[None, :]
+    return text_loss_atts * (pos >= prompt_lengths.to(text_loss_atts.device).view(-1, 1)).to(text_loss_atts.dtype)
+
+
 def build_targets(input_ids, text_loss_atts, num_query):
     """targets = [100]*Q ++ ids[:,1:] ++ ids[:,1] ; loss_mask = [0]*Q ++ mask[:,1:]  (:142-159)."""
     B = input_ids.shape[0]
@@ -172,7 +180,7 @@ class DistributedGPT3_Pretrain(_PrefixModelBase):
                                          labels=targets_dep)
         vision_feats = F.normalize(self.vision_proj(image_query).float(), dim=-1)
         pooled = outputs_text.last_hidden_state
-        pooled = pooled[torch.arange(pooled.shape[0]), text.attention_mask.sum(dim=-1) - 1]
+        pooled = pooled[torch.arange(pooled.shape[0], device=pooled.device), text.attention_mask.sum(dim=-1) - 1]
         text_feat = F.normalize(self.text_proj(pooled).float(), dim=-1)
         dist_on = torch.distributed.is_initialized()
         vision_feats_all = all_gather_cat(vision_feats) if dist_on else vision_feats   # [B*W, Q, E]
@@ -206,8 +214,7 @@ class DistributedGPT3_Caption(_PrefixModelBase):
         text_loss_atts = text.attention_mask[:, 1:].clone()
         prompt_lengths = getattr(text, "prompt_lengths", None)
         if prompt_lengths is not None:
-            for i, ln in enumerate(prompt_lengths.cpu().tolist()):
-                text_loss_atts[i, :ln] = 0
+            text_loss_atts = mask_prompt(text_loss_atts, prompt_lengths)
         targets, loss_mask = build_targets(text.input_ids, text_loss_atts, Q)
         input_embeds = torch.cat([query_features, self._word_embedding()(text.input_ids).to(query_features.dtype)], dim=1)
         return self.text_decoder(input_embeds=input_embeds, loss_mask=loss_mask, labels=targets).loss
@@ -235,9 +242,7 @@ class _PromptClsBase(_PrefixModelBase):
     def _gen_pass(self, query_features, text):
         """Decoder pass over [visual prefix | text]; returns (outputs, loss_mask [B, S-1])."""
         Q = query_features.shape[1]
-        text_loss_atts = text.attention_mask[:, 1:].clone()
-        for i, ln in enumerate(text.prompt_lengths.cpu().tolist()):
-            text_loss_atts[i, :ln] = 0
+        text_loss_atts = mask_prompt(text.attention_mask[:, 1:].clone(), text.prompt_lengths)
         targets, loss_mask = build_targets(text.input_ids, text_loss_atts, Q)
         emb = self._word_embedding()(text.input_ids).to(query_features.dtype)
         out = self.text_decoder(input_embeds=torch.cat([query_features, emb], dim=1), loss_mask=loss_mask, labels=targets)
@@ -342,7 +347,7 @@ class DistributedGPT3_Retrieval(_PrefixModelBase):
         targets = torch.cat([text.input_ids[:, 1:], text.input_ids[:, 1:2]], dim=1)
         out = self.text_decoder(tokens=text.input_ids, loss_mask=text.attention_mask[:, 1:].clone(), labels=targets)
         hid = out.last_hidden_state
-        pooled = hid[torch.arange(hid.shape[0]), text.attention_mask.sum(dim=-1) - 1]
+        pooled = hid[torch.arange(hid.shape[0], device=hid.device), text.attention_mask.sum(dim=-1) - 1]
         return F.normalize(self.text_proj(pooled).float(), dim=-1)
 
     def forward(self, image, text, idx):
