@@ -199,6 +199,78 @@ def run_dropout(name, vcfg, gcfg, Q, B, L, wseed, iseed, p_hidden=0.1, p_attn=0.
     print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
 
 
+def run_image(name, ecfg, gcfg, Q, B, L, wseed, iseed):
+    """the UNMODIFIED reference's DistributedGPT3_Pretrain_Image with the EVA encoder class
+    (models/eva_vit.py VisionTransformer - the class create_eva_vit_g instantiates at 1408 x 40) at tiny dims
+    (head_dim 88 kept).  create_eva_vit_g hard-codes the EVA-g dims (:413-424), so the module-level name the model
+    constructor looks up is pointed at a small instance of the same class - no reference code is changed."""
+    import tempfile, json
+    V, G, D = ref_shims.import_reference()
+    import models.eva_vit as E
+    from functools import partial
+    sd = port.eva_state_dict(ecfg, gcfg, Q, seed=wseed)
+    td = tempfile.mkdtemp(prefix="ymp_ref_img_")
+    json.dump(dict(gcfg, hidden_dropout=0.0, attention_dropout=0.0), open(os.path.join(td, "config.json"), "w"))
+    json.dump(dict(img_size=ecfg["img_size"], embed_dim=ecfg["embed_dim"], num_heads=ecfg["num_heads"], mlp_ratio=ecfg["mlp_ratio"],
+                   pretrained_ckpt=None, drop_path=0), open(os.path.join(td, "vis.json"), "w"))
+    orig = D.create_eva_vit_g
+    D.create_eva_vit_g = lambda img_size, norm_layer, drop_path_rate, use_checkpoint: E.VisionTransformer(
+        img_size=img_size, patch_size=ecfg["patch_size"], use_mean_pooling=False, embed_dim=ecfg["embed_dim"], depth=ecfg["depth"],
+        num_heads=ecfg["num_heads"], mlp_ratio=ecfg["mlp_ratio"], qkv_bias=True, drop_path_rate=drop_path_rate or 0.0,
+        norm_layer=norm_layer, use_checkpoint=False)
+    try:
+        config = dict(visual_cfg=os.path.join(td, "vis.json"), text_cfg=os.path.join(td, "config.json"), text_decoder=td,
+                      megatron_cfg={}, num_learnable_token=Q, use_contrastive=False, freeze_text_decoder=True, use_eva_g=True)
+        torch.manual_seed(0)
+        model = D.DistributedGPT3_Pretrain_Image(config=config, tokenizer=None).eval()
+    finally:
+        D.create_eva_vit_g = orig
+    ref_keys = sorted(k for k in model.state_dict() if not k.endswith("relative_position_index"))
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    g = torch.Generator().manual_seed(iseed)
+    image = torch.randn(B, 3, ecfg["img_size"], ecfg["img_size"], generator=g)
+    ids = torch.randint(0, gcfg["vocab_size"], (B, L), generator=g)
+    lens = torch.randint(max(2, L // 4), L + 1, (B,), generator=g)
+    att = (torch.arange(L)[None, :] < lens[:, None]).long()
+    inter = {}
+    h1 = model.visual_encoder.register_forward_hook(lambda m, i, o: inter.__setitem__("image_embeds", o[1].detach()))
+    h3 = model.text_decoder.register_forward_hook(lambda m, i, o: inter.__setitem__("gpt", o))
+    loss_ref, _ = model(image, G.BatchEncoding(dict(input_ids=ids, attention_mask=att)))
+    loss_ref.backward()
+    h1.remove(); h3.remove()
+    out = inter["gpt"]
+    ref_grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    del model
+    train = [k for k in sd if not k.startswith("text_decoder.")]
+    psd = {k: v.clone().requires_grad_(k in train) for k, v in sd.items()}
+    res = port.pretrain_image_forward(image, ids, att, psd, ecfg, gcfg, return_all=True)
+    res["loss"].backward()
+
+    def chk(a, b, what, tol=2e-4):
+        err = (a.float() - b.float()).abs().max().item()
+        scale = b.float().abs().max().item() + 1e-12
+        assert err <= tol * scale + 1e-6, f"{name}: port != reference for {what}: {err} (scale {scale})"
+        return err / scale
+
+    worst = max(chk(res["loss"], loss_ref, "loss", 1e-5), chk(res["image_embeds"], inter["image_embeds"], "image_embeds"),
+                chk(res["logits"], out.logits, "logits"), chk(res["losses"][:, :-1], out.losses, "losses"))
+    assert set(ref_grads) == {k for k in psd if psd[k].grad is not None}
+    for k, gref in ref_grads.items():
+        worst = max(worst, chk(psd[k].grad, gref, "grad " + k, 5e-4))
+    print(f"[{name}] reference loss {loss_ref.item():.6f}; port == reference (worst rel err {worst:.2e}); {len(ref_grads)} grads", flush=True)
+    fix = dict(name=name, ecfg=ecfg, gcfg=gcfg, Q=Q, B=B, L=L, wseed=wseed, iseed=iseed, keys=ref_keys, image=image, ids=ids, att=att,
+               loss=loss_ref.detach(), losses=out.losses.detach(), logits=out.logits.detach(), image_embeds=inter["image_embeds"],
+               grad_norms={k: v.norm() for k, v in ref_grads.items()},
+               grads={k: sample_grad(v) for k, v in ref_grads.items() if k.startswith(("visual_encoder.blocks.0.", "visual_encoder.patch_embed",
+                                                                                        "visual_encoder.cls_token", "visual_encoder.pos_embed",
+                                                                                        "visual_encoder.norm.", "visual_fc", "learnable_queries"))},
+               port_vs_ref_worst_rel=worst, torch_version=torch.__version__)
+    path = os.path.join(GOLD, name + ".pt")
+    torch.save(fix, path)
+    print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
+
+
 def run_hostside(name):
     """Pins the two host-side restatements that round 1 only checked against themselves:
     (1) port.clip_to_model_input against the reference's own ClipToTensor + Normalize transform objects
@@ -531,6 +603,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also the real 1.3B / T=8 / B=1 config (~6 GB RAM, minutes)")
     ap.add_argument("--caption27b", action="store_true", help="only the 2.7B caption config at its real dims (~35 GB RAM, minutes)")
+    ap.add_argument("--only-image", action="store_true", help="only the EVA / Pretrain_Image fixture (N3)")
     ap.add_argument("--only-hostside", action="store_true", help="only the clip-transform / tokenizer fixture")
     ap.add_argument("--only-dropout", action="store_true", help="only (re)write the decoder-dropout fixture")
     ap.add_argument("--only-generate", action="store_true", help="only (re)write the generation fixture")
@@ -540,6 +613,9 @@ if __name__ == "__main__":
     if a.caption27b:
         run_caption_full("full_2p7b_caption_T16_B1", dict(port.VCFG_CLIP_B16, num_frames=16), port.GCFG_2_7B, Q=128, B=1, L=256,
                          wseed=0, iseed=4321)
+        sys.exit(0)
+    if a.only_image:
+        run_image("tiny_pretrain_image", port.ECFG_TINY, port.GCFG_TINY, Q=8, B=2, L=8, wseed=71, iseed=72)
         sys.exit(0)
     if a.only_hostside:
         run_hostside("tiny_hostside")
@@ -551,6 +627,7 @@ if __name__ == "__main__":
         run_downstream("tiny_downstream", port.VCFG_TINY, port.GCFG_TINY, Q=8, wseed=21)
         sys.exit(0)
     run_hostside("tiny_hostside")
+    run_image("tiny_pretrain_image", port.ECFG_TINY, port.GCFG_TINY, Q=8, B=2, L=8, wseed=71, iseed=72)
     run_generate("tiny_generate", port.VCFG_TINY, port.GCFG_TINY, Q=8, B=2, L=8, wseed=51, iseed=52)
     if a.only_generate:
         sys.exit(0)

@@ -94,6 +94,72 @@ def timesformer(video, sd, cfg, pre="visual_encoder."):
     return layer_norm(x, sd[pre + "norm.weight"], sd[pre + "norm.bias"], eps)
 
 
+def eva_vit(image, sd, cfg, pre="visual_encoder.", eps=1e-6):
+    """EVA VisionTransformer.forward_features - models/eva_vit.py:334-350 with Block.forward :174-181 (no layer
+    scale, drop_path 0), Attention.forward :117-145 (bias = cat(q_bias, 0, v_bias), q scaled, softmax), PatchEmbed
+    :200-207 (Conv2d with bias), final `norm` (use_mean_pooling=False: create_eva_vit_g :413-436).
+    image [B,3,H,W] -> tokens [B, 1+N, D] (cls first)."""
+    B = image.shape[0]
+    P, heads = cfg["patch_size"], cfg["num_heads"]
+    x = F.conv2d(image, sd[pre + "patch_embed.proj.weight"], sd[pre + "patch_embed.proj.bias"], stride=P).flatten(2).transpose(1, 2)
+    x = torch.cat([sd[pre + "cls_token"].expand(B, -1, -1), x], dim=1) + sd[pre + "pos_embed"]
+    for i in range(cfg["depth"]):
+        b = f"{pre}blocks.{i}."
+        x = x + vit_attention(layer_norm(x, sd[b + "norm1.weight"], sd[b + "norm1.bias"], eps), sd, b + "attn.", heads)
+        x = x + mlp(layer_norm(x, sd[b + "norm2.weight"], sd[b + "norm2.bias"], eps), sd, b + "mlp.")
+    return layer_norm(x, sd[pre + "norm.weight"], sd[pre + "norm.bias"], eps)
+
+
+def eva_state_dict(cfg, gcfg, num_query, seed=0):
+    """Random state dict with the keys / shapes of DistributedGPT3_Pretrain_Image(use_eva_g) - EVA encoder
+    (models/eva_vit.py:245-300), abstractor, visual_fc, decoder - every tensor non-trivial."""
+    g = torch.Generator().manual_seed(seed)
+    D, depth, P = cfg["embed_dim"], cfg["depth"], cfg["patch_size"]
+    N = (cfg["img_size"] // P) ** 2
+    hid = int(D * cfg["mlp_ratio"])
+    rn = lambda *s, std=0.02: torch.randn(*s, generator=g) * std  # noqa: E731
+    ln = lambda n: (1.0 + 0.1 * torch.randn(n, generator=g), 0.02 * torch.randn(n, generator=g))  # noqa: E731
+    ve = "visual_encoder."
+    sd = {ve + "cls_token": rn(1, 1, D), ve + "pos_embed": rn(1, N + 1, D), ve + "patch_embed.proj.weight": rn(D, 3, P, P),
+          ve + "patch_embed.proj.bias": rn(D)}
+    for i in range(depth):
+        b = f"{ve}blocks.{i}."
+        for nm in ("norm1", "norm2"):
+            sd[b + nm + ".weight"], sd[b + nm + ".bias"] = ln(D)
+        sd[b + "attn.q_bias"], sd[b + "attn.v_bias"] = rn(D), rn(D)
+        sd[b + "attn.qkv.weight"], sd[b + "attn.proj.weight"], sd[b + "attn.proj.bias"] = rn(3 * D, D), rn(D, D), rn(D)
+        sd[b + "mlp.fc1.weight"], sd[b + "mlp.fc1.bias"] = rn(hid, D), rn(hid)
+        sd[b + "mlp.fc2.weight"], sd[b + "mlp.fc2.bias"] = rn(D, hid), rn(D)
+    sd[ve + "norm.weight"], sd[ve + "norm.bias"] = ln(D)
+    base = init_state_dict(dict(VCFG_TINY, embed_dim=D, mlp_ratio=cfg["mlp_ratio"], num_heads=cfg["num_heads"]), gcfg, num_query,
+                           seed=seed + 1, randomize=True)
+    for k, v in base.items():
+        if not k.startswith(ve):
+            sd[k] = v
+    return sd
+
+
+def pretrain_image_forward(image, input_ids, attention_mask, sd, cfg, gcfg, return_all=False):
+    """DistributedGPT3_Pretrain_Image.forward (use_eva_g, no contrastive) - models/distributed_gpt3.py:347-385."""
+    image_embeds = eva_vit(image, sd, cfg)
+    B = image.shape[0]
+    image_query = attention_pool(sd["learnable_queries"].expand(B, -1, -1), image_embeds, sd, cfg["num_heads"])
+    query_features = F.linear(image_query, sd["visual_fc.weight"], sd["visual_fc.bias"])
+    Q = query_features.shape[1]
+    targets, loss_mask = build_targets(input_ids, attention_mask, Q)
+    emb_w = sd[GPT_PRE + "embedding.word_embeddings.weight"]
+    hidden = gpt3_decoder(torch.cat([query_features, emb_w[input_ids]], dim=1), sd, gcfg)
+    logits, losses = lm_head_losses(hidden, emb_w, targets)
+    loss = masked_mean_loss(losses, loss_mask)
+    if return_all:
+        return dict(loss=loss, logits=logits, losses=losses, image_embeds=image_embeds, query_features=query_features)
+    return loss
+
+
+ECFG_TINY = dict(img_size=28, patch_size=14, embed_dim=176, depth=2, num_heads=2, mlp_ratio=4.3637)   # head_dim 88 as in EVA-g
+ECFG_EVA_G = dict(img_size=224, patch_size=14, embed_dim=1408, depth=40, num_heads=16, mlp_ratio=4.3637)
+
+
 def attention_pool(q, k, sd, heads, pre="attn_pool.", eps=1e-6):
     """AttentionPool.forward - models/vision_transformer.py:368-374 with nn.MultiheadAttention
     (bias=True, add_bias_kv=True): one learned key/value row is appended; the residual is taken

@@ -226,3 +226,29 @@ def test_full_2p7b_caption_matches_reference_fixture(cuda):
         if n.item() > 1e-9 and abs(gn - n.item()) > 0.1 * n.item():
             bad.append((k, gn, n.item()))
     assert not bad, bad[:5]
+
+
+def test_pretrain_image_eva_matches_reference_fixture(cuda):
+    """DistributedGPT3_Pretrain_Image with the EVA encoder (head_dim 88, 14 x 14 patches, conv bias)
+    forward + backward against the unmodified reference's fp32 outputs (tests/golden/tiny_pretrain_image.pt)."""
+    from helpers import build_pretrain_image
+    fx = torch.load(os.path.join(GOLD, "tiny_pretrain_image.pt"), weights_only=False)
+    sd = port.eva_state_dict(fx["ecfg"], fx["gcfg"], fx["Q"], seed=fx["wseed"])
+    m = build_pretrain_image(fx["ecfg"], fx["gcfg"], fx["Q"], sd=sd, device=cuda, dtype=torch.bfloat16)
+    img = fx["image"].to(cuda).bfloat16()
+    with torch.no_grad():
+        _, emb = m.visual_encoder(img)
+    assert _rel(emb, fx["image_embeds"]) < 2e-2
+    loss, zero = m(img, _enc(cuda, input_ids=fx["ids"], attention_mask=fx["att"]))
+    assert float(zero) == 0.0
+    assert abs(loss.item() - fx["loss"].item()) < 1e-2 * abs(fx["loss"].item())
+    loss.backward()
+    params = dict(m.named_parameters())
+    for k, (stride, vals) in fx["grads"].items():
+        g = params[k].grad.float().cpu().flatten()[::stride]
+        if vals.abs().max() > 1e-7:
+            assert _rel(g, vals) < 8e-2, k
+    bad = [(k, params[k].grad.float().norm().item(), n.item()) for k, n in fx["grad_norms"].items()
+           if n.item() > 1e-7 and abs(params[k].grad.float().norm().item() - n.item()) > 0.1 * n.item()]
+    assert not bad, bad[:5]
+    assert all(p.grad is None for k, p in params.items() if k.startswith("text_decoder."))

@@ -178,3 +178,25 @@ def test_hostside_fixture_from_the_reference():
             assert torch.equal(getattr(out, k), v), (case, k, getattr(out, k), v)
     assert tk.decode(torch.tensor([11, 12])) == fx["decode_11_12"]
     assert tk.tokenizer.eos == fx["eos"]
+
+
+def test_pretrain_image_state_dict_surface_and_oracle():
+    """DistributedGPT3_Pretrain_Image (EVA encoder) exposes the reference's state-dict keys (from the
+    unmodified reference, tests/golden/tiny_pretrain_image.pt) and the oracle's eva restatement reproduces the
+    reference's loss / logits / encoder output on the fixture's inputs."""
+    from helpers import build_pretrain_image
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "tiny_pretrain_image.pt"), weights_only=False)
+    m = build_pretrain_image(fx["ecfg"], fx["gcfg"], fx["Q"])
+    assert sorted(m.state_dict().keys()) == fx["keys"]
+    frozen = {k for k, p in m.named_parameters() if not p.requires_grad}
+    assert frozen and all(k.startswith("text_decoder.") for k in frozen)
+    sd = port.eva_state_dict(fx["ecfg"], fx["gcfg"], fx["Q"], seed=fx["wseed"])
+    with torch.no_grad():
+        res = port.pretrain_image_forward(fx["image"], fx["ids"], fx["att"], sd, fx["ecfg"], fx["gcfg"], return_all=True)
+    assert abs(res["loss"].item() - fx["loss"].item()) < 1e-5 * abs(fx["loss"].item())
+    assert (res["image_embeds"] - fx["image_embeds"]).abs().max() < 2e-4 * fx["image_embeds"].abs().max()
+    assert (res["logits"] - fx["logits"]).abs().max() < 2e-4 * fx["logits"].abs().max()
+    import models.eva_vit as E
+    g = E.create_eva_vit_g(img_size=224, drop_path_rate=0, norm_layer=None)
+    assert g.ecfg["embed_dim"] == 1408 and g.ecfg["depth"] == 40 and g.ecfg["num_heads"] == 16 and g.pos_embed.shape == (1, 257, 1408)
+    assert g.get_parameter("blocks.39.mlp.fc1.weight").shape == (6144, 1408)

@@ -35,6 +35,27 @@ __global__ void __launch_bounds__(256) im2col_kernel(const __nv_bfloat16* __rest
   }
 }
 
+// Any patch size (EVA-g: 14 x 14 patches, row length 588 is not a multiple of 8): one element per thread, columns
+// [C*P*P, ldo) of every row are zero-filled so that the GEMM can use a 16-byte aligned, padded K extent.
+__global__ void __launch_bounds__(256) im2col_generic_kernel(const __nv_bfloat16* __restrict__ video,
+                                                             __nv_bfloat16* __restrict__ out, int B, int C, int T,
+                                                             int H, int W, int P, int ldo) {
+  const int Hp = H / P, Wp = W / P, N = Hp * Wp, K = C * P * P;
+  const long total = (long)B * N * T * ldo;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % ldo);
+    const long row = idx / ldo;
+    __nv_bfloat16 val = __float2bfloat16(0.f);
+    if (col < K) {
+      const int t = (int)(row % T), n = (int)((row / T) % N), b = (int)(row / ((long)T * N));
+      const int ix = col % P, iy = (col / P) % P, c = col / (P * P);
+      const int py = n / Wp, px = n % Wp;
+      val = video[((((size_t)b * C + c) * T + t) * H + (py * P + iy)) * W + px * P + ix];
+    }
+    out[idx] = val;
+  }
+}
+
 // ------------------------------------------------------------------------------ embedding gather
 // out[(b*S + off + l), :] = table[ids[b,l], :] + pos[off + l, :]     (one warp per row)
 __global__ void __launch_bounds__(256) embed_gather_kernel(const int64_t* __restrict__ ids,
@@ -346,8 +367,16 @@ extern "C" int ymp_dropout(const ymp_dropout_args* a, void* stream) {
 
 extern "C" int ymp_im2col(const ymp_im2col_args* a, void* stream) {
   YMP_CHECK_ARG(a && a->video && a->out, "ymp_im2col: null pointer");
-  YMP_CHECK_ARG(a->P > 0 && a->P % 8 == 0 && a->H % a->P == 0 && a->W % a->P == 0 && a->W % 8 == 0,
-                "ymp_im2col: need P%%8==0, H%%P==0, W%%P==0 (P=%d H=%d W=%d)", a->P, a->H, a->W);
+  YMP_CHECK_ARG(a->P > 0 && a->H % a->P == 0 && a->W % a->P == 0, "ymp_im2col: need H%%P==0, W%%P==0 (P=%d H=%d W=%d)", a->P, a->H, a->W);
+  if (a->P % 8 != 0 || a->W % 8 != 0) {
+    YMP_CHECK_ARG(a->ldo >= a->C * a->P * a->P && a->ldo % 8 == 0 && aligned16(a->out), "ymp_im2col: bad ldo / alignment");
+    const long tot = (long)a->B * (a->H / a->P) * (a->W / a->P) * a->T * a->ldo;
+    const int blk = (int)min((tot + 255) / 256, (long)num_sms() * 16);
+    im2col_generic_kernel<<<blk, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a->video, (__nv_bfloat16*)a->out, a->B, a->C,
+                                                                 a->T, a->H, a->W, a->P, a->ldo);
+    YMP_LAUNCH_CHECK();
+    return YMP_OK;
+  }
   YMP_CHECK_ARG(a->ldo >= a->C * a->P * a->P && a->ldo % 8 == 0, "ymp_im2col: bad ldo");
   YMP_CHECK_ARG(aligned16(a->video) && aligned16(a->out), "ymp_im2col: alignment");
   const long total = (long)a->B * (a->H / a->P) * (a->W / a->P) * a->T * a->C * a->P * (a->P / 8);

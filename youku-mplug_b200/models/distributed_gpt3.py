@@ -199,6 +199,75 @@ class DistributedGPT3_Pretrain(_PrefixModelBase):
         return loss_caption, loss_contrastive
 
 
+class DistributedGPT3_Pretrain_Image(_PrefixModelBase):
+    """Image pre-training variant (reference :230-427) with the EVA-g encoder (`use_eva_g: true`): image
+    [B,3,H,W] -> EVA tokens [B,257,1408] -> abstractor -> visual_fc -> frozen decoder -> masked token CE.  The
+    reference's other branch (a plain image ViT from models/vision_transformer.py) is not part of this package."""
+
+    def __init__(self, config=None, tokenizer=None):
+        super().__init__()
+        from . import eva_vit
+        if not config.get('use_eva_g', False):
+            raise NotImplementedError("DistributedGPT3_Pretrain_Image on the B200 path implements the EVA-g encoder (use_eva_g: true)")
+        self.tokenizer = tokenizer
+        with open(config['visual_cfg'], 'r') as f:
+            visual_cfg = json.load(f)
+        text_cfg = GPT3Config.from_json_file(config['text_cfg'])
+        self.visual_cfg = visual_cfg
+        self.visual_encoder = eva_vit.create_eva_vit_g(img_size=visual_cfg['img_size'], norm_layer=partial(LayerNormWithForceFP32, eps=1e-6),
+                                                       drop_path_rate=visual_cfg.get('drop_path', False), use_checkpoint=True)
+        ckpt = visual_cfg.get("pretrained_ckpt", None)
+        if ckpt is not None:
+            if not ckpt.startswith("eva"):
+                raise NotImplementedError(f"pretrained_ckpt={ckpt!r}: only eva/<path> checkpoints load into the EVA-g encoder")
+            weights = torch.load("/".join(ckpt.split("/")[1:]), map_location='cpu')
+            eva_vit.interpolate_pos_embed(self.visual_encoder, weights)
+            print(self.visual_encoder.load_state_dict(weights, strict=False))
+        rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        self.text_decoder = DistributedGPT3(model_dir=config['text_decoder'], rank=rank, path_load_tag='model',
+                                            megatron_cfg=config['megatron_cfg'],
+                                            checkpoint_model_parallel_size=1 if text_cfg.num_hidden_layers < 40 else 8)
+        if config.get('freeze_vit', False):
+            for param in self.visual_encoder.parameters():
+                param.requires_grad = False
+        if config.get('freeze_text_decoder', True):
+            for param in self.text_decoder.parameters():
+                param.requires_grad = False
+        self.vision_width = visual_cfg['embed_dim']
+        self.text_width = self.text_decoder.config.hidden_size
+        self.learnable_token = True
+        self.num_learnable_token = config.get('num_learnable_token', 256)
+        self.learnable_queries = nn.Parameter(trunc_normal((1, self.num_learnable_token, self.vision_width), 0.015))
+        self.attn_pool = AttentionPool(self.vision_width, num_heads=visual_cfg['num_heads'], mlp_ratio=visual_cfg['mlp_ratio'],
+                                       norm_layer=partial(LayerNormWithForceFP32, eps=1e-6))
+        self.visual_fc = _Linear(self.vision_width, self.text_width)
+        with torch.no_grad():
+            self.visual_fc.weight.copy_(trunc_normal((self.text_width, self.vision_width), 0.015))
+        self.connect_ln = bool(visual_cfg.get('connect_ln', False))
+        self.visual_norm = _VisualNorm(self.text_width, eps=1e-6) if self.connect_ln else nn.Identity()
+        self.prompt = config.get('prompt', "")
+        self.use_contrastive = config.get('use_contrastive', False)
+        if self.use_contrastive:
+            raise NotImplementedError("DistributedGPT3_Pretrain_Image: the contrastive branch is implemented for the video model "
+                                      "(DistributedGPT3_Pretrain) only")
+
+    def forward(self, image, text):
+        _, _, _, query_features = self.visual_prefix(image)
+        Q = query_features.shape[1]
+        text_loss_atts = text.attention_mask[:, 1:].clone()
+        prompt_lengths = getattr(text, "prompt_lengths", None)
+        if prompt_lengths is not None:
+            text_loss_atts = mask_prompt(text_loss_atts, prompt_lengths)
+        targets, loss_mask = build_targets(text.input_ids, text_loss_atts, Q)
+        input_embeds = torch.cat([query_features, self._word_embedding()(text.input_ids).to(query_features.dtype)], dim=1)
+        loss_caption = self.text_decoder(input_embeds=input_embeds, loss_mask=loss_mask, labels=targets).loss
+        return loss_caption, loss_caption.new_zeros(())
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'visual_encoder.pos_embed', 'visual_encoder.cls_token'}
+
+
 class DistributedGPT3_Caption(_PrefixModelBase):
     """Caption fine-tuning forward (:751-788) and generate() (:790-809, beam search over the KV cache)."""
 

@@ -275,6 +275,112 @@ def vit_bwd(W, G, c, d_out):
 
 
 # ------------------------------------------------------------------------------------------
+# EVA image encoder: plain pre-LN ViT over [cls | 16 x 16 patches of 14 x 14 pixels]
+# ------------------------------------------------------------------------------------------
+class EvaDims:
+    def __init__(self, ecfg, B):
+        self.P, self.D, self.depth, self.heads = ecfg["patch_size"], ecfg["embed_dim"], ecfg["depth"], ecfg["num_heads"]
+        self.hd = self.D // self.heads
+        self.N = (ecfg["img_size"] // self.P) ** 2
+        self.S = self.N + 1
+        self.hid = int(self.D * ecfg["mlp_ratio"])
+        self.B, self.R = B, B * (self.N + 1)
+        self.eps = ecfg.get("eps", 1e-6)
+        self.scale = self.hd ** -0.5
+
+
+def eva_fwd(W, image, ecfg, save=True):
+    """EVA VisionTransformer.forward_features - models/eva_vit.py:334-350 (Block :174-181, Attention :117-145, PatchEmbed
+    :200-207 with bias, final norm).  image [B,3,H,W] bf16 -> tokens [B*(1+N), D], row b*(N+1) + i, cls first."""
+    B = image.shape[0]
+    d = EvaDims(ecfg, B)
+    dev = image.device
+    c = Ctx(d=d, blocks=[])
+    patches = ops.im2col(image.contiguous().unsqueeze(2), d.P)               # [B*N, Kp] (588 -> 592 zero-padded)
+    Kp = patches.shape[1]
+    wp = W[VE + "patch_embed.proj.weight"].reshape(d.D, -1)
+    if wp.shape[1] != Kp:
+        wpad = torch.zeros((d.D, Kp), device=dev, dtype=bf16)
+        wpad[:, :wp.shape[1]] = wp
+        wp = wpad
+    pos = W[VE + "pos_embed"][0]
+    x = torch.empty((d.R, d.D), device=dev, dtype=torch.float32)
+    # patch rows land at b*(N+1) + 1 + n (row re-blocking), position embeddings added by the epilogue
+    ops.gemm(patches, wp, bias=W[VE + "patch_embed.proj.bias"], residual=pos[1:], res_row_mod=d.N, out=x[1:], d_row_block=d.N,
+             d_row_stride=d.S)
+    x.view(B, d.S, d.D)[:, 0] = W[VE + "cls_token"][0, 0].float() + pos[0].float()
+    m = ops.dense_map(d.S)
+    for i in range(d.depth):
+        pre = f"{VE}blocks.{i}."
+        bc = Ctx()
+        ln1, bc.m1, bc.r1 = ops.layernorm_fwd(x, W[pre + "norm1.weight"], W[pre + "norm1.bias"], d.eps)
+        qkv = ops.gemm(ln1, W[pre + "attn.qkv.weight"], bias=_qkv_bias(W, pre + "attn."))
+        att = torch.empty((d.R, d.D), device=dev, dtype=bf16)
+        q, k, v = (TView(qkv, j * d.D, d.hd, m) for j in range(3))
+        bc.lse = ops.attn_fwd(q, k, v, TView(att, 0, d.hd, m), n_seq=B, n_heads=d.heads, head_dim=d.hd, s_q=d.S, s_kv=d.S,
+                              causal=False, scale=d.scale)
+        x1 = ops.gemm(att, W[pre + "attn.proj.weight"], bias=W[pre + "attn.proj.bias"], residual=x, out_dtype=torch.float32)
+        ln2, bc.m2, bc.r2 = ops.layernorm_fwd(x1, W[pre + "norm2.weight"], W[pre + "norm2.bias"], d.eps)
+        dact = torch.empty((d.R, d.hid), device=dev, dtype=bf16)
+        h = ops.gemm(ln2, W[pre + "mlp.fc1.weight"], bias=W[pre + "mlp.fc1.bias"], act=ACT_GELU_ERF, aux_out=dact)
+        xn = ops.gemm(h, W[pre + "mlp.fc2.weight"], bias=W[pre + "mlp.fc2.bias"], residual=x1, out_dtype=torch.float32)
+        if save:
+            bc.update(x=x, ln1=ln1, qkv=qkv, att=att, x1=x1, ln2=ln2, dact=dact, h=h)
+        c.blocks.append(bc)
+        x = xn
+    out, c.mf, c.rf = ops.layernorm_fwd(x, W[VE + "norm.weight"], W[VE + "norm.bias"], d.eps)
+    if save:
+        c.update(patches=patches, xL=x, Kp=Kp)
+    return out, c
+
+
+def eva_bwd(W, G, c, d_out):
+    """d_out [B*(1+N), D] -> accumulates every encoder weight gradient."""
+    d = c.d
+    dev = d_out.device
+    B = d.B
+    m = ops.dense_map(d.S)
+    dx = ops.layernorm_bwd(d_out, c.xL, W[VE + "norm.weight"], c.mf, c.rf, dgamma=G.get(VE + "norm.weight"), dbeta=G.get(VE + "norm.bias"))
+    for i in reversed(range(d.depth)):
+        pre, bc = f"{VE}blocks.{i}.", c.blocks[i]
+        linear_wgrad(dx, bc.h, pre + "mlp.fc2.weight", pre + "mlp.fc2.bias", G)
+        dpre = linear_dgrad(dx, W[pre + "mlp.fc2.weight"], act=ACT_GELU_ERF, aux_in=bc.dact)
+        linear_wgrad(dpre, bc.ln2, pre + "mlp.fc1.weight", pre + "mlp.fc1.bias", G)
+        dln2 = linear_dgrad(dpre, W[pre + "mlp.fc1.weight"])
+        dx1 = ops.layernorm_bwd(dln2, bc.x1, W[pre + "norm2.weight"], bc.m2, bc.r2, add=dx,
+                                dgamma=G.get(pre + "norm2.weight"), dbeta=G.get(pre + "norm2.bias"))
+        linear_wgrad(dx1, bc.att, pre + "attn.proj.weight", pre + "attn.proj.bias", G)
+        datt = linear_dgrad(dx1, W[pre + "attn.proj.weight"])
+        dqkv = torch.empty_like(bc.qkv)
+        q, k, v = (TView(bc.qkv, j * d.D, d.hd, m) for j in range(3))
+        dq, dk, dv = (TView(dqkv, j * d.D, d.hd, m) for j in range(3))
+        ops.attn_bwd(q, k, v, TView(bc.att, 0, d.hd, m), bc.lse, TView(datt, 0, d.hd, m), dq, dk, dv, n_seq=B, n_heads=d.heads,
+                     head_dim=d.hd, s_q=d.S, s_kv=d.S, causal=False, scale=d.scale)
+        _qkv_wgrad(G, pre + "attn.", dqkv, bc.ln1, d.D, dev)
+        dln1 = linear_dgrad(dqkv, W[pre + "attn.qkv.weight"])
+        dx = ops.layernorm_bwd(dln1, bc.x, W[pre + "norm1.weight"], bc.m1, bc.r1, add=dx1,
+                               dgamma=G.get(pre + "norm1.weight"), dbeta=G.get(pre + "norm1.bias"))
+        c.blocks[i] = None
+    dx3 = dx.view(B, d.S, d.D)
+    if VE + "cls_token" in G:
+        G[VE + "cls_token"].view(-1).add_(dx3[:, 0].float().sum(0))
+    if VE + "pos_embed" in G:
+        G[VE + "pos_embed"].view(d.S, d.D).add_(dx3.float().sum(0))
+    dpatch = dx3[:, 1:].reshape(B * d.N, d.D).contiguous()
+    pk = VE + "patch_embed.proj.weight"
+    if pk in G:
+        K = G[pk].numel() // d.D
+        if c.Kp == K:
+            ops.gemm(dpatch, c.patches, a_t=True, b_t=True, out=G[pk].view(d.D, K), accumulate=True)
+        else:   # padded patch rows: accumulate into a padded buffer, fold the real columns back
+            tmp = torch.zeros((d.D, c.Kp), device=dev, dtype=torch.float32)
+            ops.gemm(dpatch, c.patches, a_t=True, b_t=True, out=tmp, accumulate=True)
+            G[pk].view(d.D, K).add_(tmp[:, :K])
+    if VE + "patch_embed.proj.bias" in G:
+        ops.colsum(dpatch, G[VE + "patch_embed.proj.bias"])
+
+
+# ------------------------------------------------------------------------------------------
 # visual abstractor (AttentionPool) + visual_fc
 # ------------------------------------------------------------------------------------------
 _pad_cache = {}

@@ -234,6 +234,27 @@ class VitFn(torch.autograd.Function):
         return (None, None, None) + store.grads(ctx.keys, ctx.params)
 
 
+class EvaFn(torch.autograd.Function):
+    """EVA image encoder (models/eva_vit.py VisionTransformer.forward_features): image [B,3,H,W] -> tokens [B, 1+N, D]."""
+
+    @staticmethod
+    def forward(ctx, image, ecfg, keys, *params):
+        _require_cuda(image, "EvaFn")
+        W = {k: as_bf16(p) for k, p in zip(keys, params)}
+        need_bwd = any(ctx.needs_input_grad[3:])
+        out, c = engine.eva_fwd(W, image.to(bf16), ecfg, save=need_bwd)
+        if need_bwd:
+            ctx.W, ctx.keys, ctx.c, ctx.params = W, keys, c, params
+        return out.view(image.shape[0], -1, out.shape[1])
+
+    @staticmethod
+    def backward(ctx, dout):
+        store = _GradStore(ctx.keys, ctx.params, ctx.needs_input_grad[3:], dout.device)
+        engine.eva_bwd(ctx.W, store.G, ctx.c, dout.reshape(-1, dout.shape[-1]).to(bf16).contiguous())
+        ctx.c = None
+        return (None, None, None) + store.grads(ctx.keys, ctx.params)
+
+
 class AttnPoolFn(torch.autograd.Function):
     """AttentionPool on learnable_queries.repeat(B): image_embeds [B,K1,D] -> [B,Q,D]."""
 

@@ -287,12 +287,13 @@ def fused_im2col_ok(T, P):
 
 
 def im2col(video, P, out=None):
-    """video [B,C,T,H,W] bf16 contiguous -> [(b n t), C*P*P]."""
+    """video [B,C,T,H,W] bf16 contiguous -> [(b n t), C*P*P] (row length rounded up to 8 and zero-padded when
+    C*P*P is not a multiple of 8, e.g. the 14 x 14 patches of EVA-g: returns the padded [rows, ld] tensor)."""
     assert video.is_contiguous() and video.dtype == bf16
     B, Cc, T, H, W = video.shape
     rows = B * (H // P) * (W // P) * T
     if out is None:
-        out = torch.empty((rows, Cc * P * P), device=video.device, dtype=bf16)
+        out = torch.empty((rows, (Cc * P * P + 7) // 8 * 8), device=video.device, dtype=bf16)
     a = L.Im2colArgs()
     a.video, a.out = video.data_ptr(), out.data_ptr()
     a.B, a.C, a.T, a.H, a.W, a.P, a.ldo = B, Cc, T, H, W, P, out.stride(0)
