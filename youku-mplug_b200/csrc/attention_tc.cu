@@ -1174,7 +1174,10 @@ int attn_tc_fwd_try(const ymp_attn_args* a, cudaStream_t st) {
   p.kv_rows = lng ? 256 : ((a->s_kv + 31) & ~31);
   // pair-tile persistent kernel: both query tiles of a (sequence, head) share one K / V fetch, two stages in flight
   static const bool no_pair = [] { const char* e = getenv("YMP_ATTN_NO_PAIR"); return e && e[0] == '1'; }();
-  if (!lng && !no_pair && a->s_q > 128 && a->s_q <= 256 && (a->mask == YMP_MASK_NONE || a->mask == YMP_MASK_CAUSAL)) {
+  // measured (profiles/r02e_attn_probe_*.log): +3 % on the ViT spatial shape (197 rows: the second tile is mostly padding,
+  // sharing K / V pays), -3 % on the causal GPT shape (tile 0 needs half the keys: the single-tile kernel loads less)
+  static const bool pair_causal = [] { const char* e = getenv("YMP_ATTN_PAIR_CAUSAL"); return e && e[0] == '1'; }();
+  if (!lng && !no_pair && a->s_q > 128 && a->s_q <= 256 && (a->mask == YMP_MASK_NONE || (pair_causal && a->mask == YMP_MASK_CAUSAL))) {
     const int HDp = a->head_dim == 64 ? 64 : 96;
     const int smem = 2 * 128 * HDp * 2 + 2 * 2 * p.kv_rows * HDp * 2 + 64 + 1024;
     if (smem <= 227 * 1024) return HDp == 64 ? launch_tc_pair<64>(p, smem, st) : launch_tc_pair<96>(p, smem, st);

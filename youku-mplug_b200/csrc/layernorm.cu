@@ -128,8 +128,8 @@ struct LnBwdParams {
   DropSpec drop;
 };
 
-template <int VPL, bool WGRAD, bool XF32>
-__global__ void __launch_bounds__(LN_WARPS * 32, WGRAD ? (VPL <= 4 ? 3 : 1) : 4) ln_bwd_kernel(const LnBwdParams p) {
+template <int VPL, bool WGRAD, bool XF32, bool DROP>
+__global__ void __launch_bounds__(LN_WARPS * 32, WGRAD ? (VPL <= 4 ? 3 : 1) : (DROP ? 2 : 4)) ln_bwd_kernel(const LnBwdParams p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nvec = p.D >> 3;
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, WGRAD ? (VPL <= 4 ? 3 : 1) : 4)
   }
   const uint4* g4 = reinterpret_cast<const uint4*>(p.gamma);
   DropState ds = {};
-  if (p.dx_drop) ds = drop_state(p.drop);
+  if (DROP) ds = drop_state(p.drop);
   for (int row = blockIdx.x * LN_WARPS + warp; row < p.rows; row += gridDim.x * LN_WARPS) {
     const int irow = p.in_rows ? p.in_rows[row] : row;
     if (irow < 0) continue;  // padding slot of the forward: no input row behind it
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, WGRAD ? (VPL <= 4 ? 3 : 1) : 4)
           for (int e = 0; e < 8; ++e) o[e] += a[e];
         }
         dxr[vi] = pack8(o);
-        if (p.dx_drop) {  // gradient w.r.t. the pre-dropout branch output: same mask bits as the forward epilogue
+        if (DROP) {  // gradient w.r.t. the pre-dropout branch output: same mask bits as the forward epilogue
           drop4(ds, (uint32_t)irow, (uint32_t)(vi * 8), o[0], o[1], o[2], o[3]);
           drop4(ds, (uint32_t)irow, (uint32_t)(vi * 8 + 4), o[4], o[5], o[6], o[7]);
           reinterpret_cast<uint4*>(p.dx_drop + (size_t)irow * p.ldx)[vi] = pack8(o);
@@ -284,7 +284,7 @@ extern "C" int ymp_layernorm_bwd(const ymp_layernorm_bwd_args* a, void* stream) 
   const int blocks = min((a->rows + LN_WARPS - 1) / LN_WARPS, cap);
   const int thr = LN_WARPS * 32;
   const bool xf = (a->x_dtype == YMP_DT_F32);
-#define YMP_LN_BWD(V, W, X) ln_bwd_kernel<V, W, X><<<blocks, thr, 0, st>>>(p)
+#define YMP_LN_BWD(V, W, X) do { if (p.dx_drop) ln_bwd_kernel<V, W, X, true><<<blocks, thr, 0, st>>>(p); else ln_bwd_kernel<V, W, X, false><<<blocks, thr, 0, st>>>(p); } while (0)
 #define YMP_LN_BWD_V(W, X) do { if (vpl <= 3) YMP_LN_BWD(3, W, X); else if (vpl <= 8) YMP_LN_BWD(8, W, X); else YMP_LN_BWD(16, W, X); } while (0)
   if (wg) { if (xf) YMP_LN_BWD_V(true, true); else YMP_LN_BWD_V(true, false); }
   else { if (xf) YMP_LN_BWD_V(false, true); else YMP_LN_BWD_V(false, false); }

@@ -283,7 +283,8 @@ def patch_embed_wgrad(dy, video, P, out):
 
 
 def fused_im2col_ok(T, P):
-    return P == 16 and T % 8 == 0 and 64 % T == 0
+    import os
+    return os.environ.get("YMP_FUSED_IM2COL", "1") != "0" and P == 16 and T % 8 == 0 and 64 % T == 0
 
 
 def im2col(video, P, out=None):
