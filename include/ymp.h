@@ -118,12 +118,11 @@ typedef struct ymp_gemm_args {
   /* Fused im2col (the patch embedding, models/vision_transformer.py:392-398: `(b t) c h w` rearrange + Conv2d(k = stride
    * = P) as ONE GEMM): when im2col_P > 0, A is not a matrix but the video [B, C, T, H, W] (bf16, contiguous); row
    * m = (b*N + n)*T + t (n = py*(W/P) + px: the encoder's patch-major token order), column k = (c, iy, ix) as in
-   * conv_weight.flatten(1).  The TMA producer gathers each 128-row x 64-column operand tile straight from the video
-   * with 5-D tensor-map boxes {P, 4, T, 1, 1}; no patch matrix is ever written.  Needs P = 16, T % 8 == 0,
-   * 128 % T == 0, M = B*N*T, K = C*P*P, a_mn_major = 0.
-   * im2col_operand = 1: the implicit patch matrix is the B operand instead, MN-major ([K = B*N*T rows, N = C*P*P]):
-   * the weight gradient of the patch embedding, dW = dY^T . patches (b_mn_major = 1, B = the video). */
-  int32_t im2col_P, im2col_B, im2col_C, im2col_T, im2col_H, im2col_W, im2col_operand;
+   * conv_weight.flatten(1).  The TMA producer gathers each 128-row x 64-column operand tile straight from the video as
+   * four 16-column sub-tiles (one pixel row of every patch: 5-D boxes {16 px, 1 row, T frames} = T rows x 32 bytes, i.e.
+   * SWIZZLE_32B atoms; one tcgen05.mma K-step per sub-tile); no patch matrix is written.  Needs P = 16, T % 8 == 0,
+   * 128 % T == 0, M = B*N*T, K = C*P*P, a_mn_major = 0. */
+  int32_t im2col_P, im2col_B, im2col_C, im2col_T, im2col_H, im2col_W;
 } ymp_gemm_args;
 
 int ymp_gemm(const ymp_gemm_args* a, void* stream);

@@ -37,8 +37,7 @@ struct GemmKParams {
   int n_fast;                      // tile order: consecutive units walk N first (A streamed once) or M first
   bool v32_d, v32_aux, v32_res, v32_bias;  // 32-byte aligned -> 256-bit accesses
   float alpha;
-  int im2col_T, im2col_N, im2col_Wp;  // fused im2col operand (im2col_T > 0): frames, patches per frame, patches per row
-  int im2col_b;                       // 0: the A operand (K-major), 1: the B operand (MN-major)
+  int im2col_T, im2col_N, im2col_Wp;  // fused im2col A operand (im2col_T > 0): frames, patches per frame, patches per row
   DropSpec drop;                   // dropout before the residual add (has_drop)
   int has_drop;
   int epi_tma;                     // CTA-pair kernel: outputs staged in swizzled smem and written by TMA (bulk tensor
@@ -276,10 +275,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
 }
 
 // ---------------------------------------------------------------- fused im2col A operand (patch embedding)
-// One 128-row x 64-column K-major tile of the implicit patch matrix: rows m0 .. m0+127 are 128/T consecutive
-// patches x T frames, columns kb*64 .. +63 are 4 pixel rows x 16 pixels of one channel.  Each patch is one 5-D
-// box {16 px, 4 rows, T frames} = T rows x 128 bytes, i.e. whole SWIZZLE_128B atoms, written where the UMMA
-// descriptor expects rows (patch*T + t); rows past the last sample are out of range and arrive as zeros.
+// One 128-row x 64-column tile of the implicit patch matrix (rows m0 .. m0+127 = 128/T consecutive patches x T frames,
+// columns kb*64 .. +63 = 4 pixel rows x 16 pixels of one channel) arrives as FOUR 16-column sub-tiles of 4 KB, one per
+// pixel row: every patch contributes one 5-D box {16 px, 1 row, T frames} = T rows x 32 bytes, which with
+// SWIZZLE_32B is exactly T/8 shared-memory atoms of 8 rows x 32 bytes, dense (a 128-byte-swizzled box would give every
+// 32-byte line its own 128-byte row: tools/tma_box_probe.cu).  Each sub-tile is the A operand of one tcgen05.mma K-step
+// (K = 16) through a SWIZZLE_32B descriptor; rows past the last sample are out of range and arrive as zeros.
+constexpr int IM2COL_SUB_BYTES = BM * 32;  // one 128-row x 16-column sub-tile
 template <bool CTA2>
 __device__ __forceinline__ void load_a_im2col(uint8_t* sa, const CUtensorMap* tma, uint64_t* bar, int m0, int kb,
                                               const GemmKParams& p) {
@@ -288,29 +290,23 @@ __device__ __forceinline__ void load_a_im2col(uint8_t* sa, const CUtensorMap* tm
   for (int i = 0; i < BM / T; ++i) {
     const int g = pt + i, b = g / p.im2col_N, n = g - b * p.im2col_N;
     const int ny = n / p.im2col_Wp, nx = n - ny * p.im2col_Wp;
-    if (CTA2) tma_load_5d_cta2(sa + i * T * 128, tma, bar, nx * 16, ny * 16 + y0, 0, c, b);
-    else tma_load_5d(sa + i * T * 128, tma, bar, nx * 16, ny * 16 + y0, 0, c, b);
-  }
-}
-
-// The same implicit matrix as an MN-major B operand (weight gradient): 64 k-rows (patch rows) x `ncols` columns
-// starting at column n0.  MN-major SWIZZLE_128B atoms are 8 k-rows x 64 columns, 1024 bytes apart along k and
-// 64*BK*2 bytes apart along n: the box of one patch (T k-rows x {4 pixel rows x 16 pixels}) is T/8 such atoms.
-template <bool CTA2>
-__device__ __forceinline__ void load_b_im2col(uint8_t* sb, const CUtensorMap* tma, uint64_t* bar, int n0, int ncols, int kb,
-                                              const GemmKParams& p) {
-  const int T = p.im2col_T;
-  const int pt = kb * BK / T;
-  for (int ch = 0; ch < ncols / 64; ++ch) {
-    const int col = n0 + ch * 64, c = col >> 8, y0 = (col & 255) >> 4;
-    for (int i = 0; i < BK / T; ++i) {
-      const int g = pt + i, b = g / p.im2col_N, n = g - b * p.im2col_N;
-      const int ny = n / p.im2col_Wp, nx = n - ny * p.im2col_Wp;
-      uint8_t* dst = sb + ch * (64 * BK * 2) + i * T * 128;
-      if (CTA2) tma_load_5d_cta2(dst, tma, bar, nx * 16, ny * 16 + y0, 0, c, b);
-      else tma_load_5d(dst, tma, bar, nx * 16, ny * 16 + y0, 0, c, b);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint8_t* dst = sa + ks * IM2COL_SUB_BYTES + i * T * 32;
+      if (CTA2) tma_load_5d_cta2(dst, tma, bar, nx * 16, ny * 16 + y0 + ks, 0, c, b);
+      else tma_load_5d(dst, tma, bar, nx * 16, ny * 16 + y0 + ks, 0, c, b);
     }
   }
+}
+// SWIZZLE_32B K-major descriptor of sub-tile ks: 8-row atoms of 256 bytes, contiguous along M
+__device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                       // LBO: unused (one atom along K)
+  d |= (uint64_t)((256 >> 4) & 0x3FFF) << 32;   // SBO: next 8-row group
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                       // SWIZZLE_32B
+  return d;
 }
 
 // ---------------------------------------------------------------- TMA epilogue (CTA-pair kernel)
@@ -499,7 +495,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
-          if (p.im2col_T && !p.im2col_b) {
+          if (p.im2col_T) {
             load_a_im2col<false>(sa, &tma_a, &full_bar[stage], m_blk * BM, kb, p);
           } else if (!p.a_mn) {
             tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
@@ -509,9 +505,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
               tma_load_2d(sa + c * (64 * BK * 2), &tma_a, &full_bar[stage], m_blk * BM + c * 64,
                           kb * BK);
           }
-          if (p.im2col_T && p.im2col_b) {
-            load_b_im2col<false>(sb, &tma_b, &full_bar[stage], n_blk * BN, BN, kb, p);
-          } else if (!p.b_mn) {
+          if (!p.b_mn) {
             tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
           } else {
 #pragma unroll
@@ -550,7 +544,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t adesc = p.im2col_T ? make_smem_desc_sw32(sa + k * IM2COL_SUB_BYTES) : make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
             umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
@@ -708,7 +702,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);  // bytes of both CTAs land here
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * B2_STAGE_BYTES;
-          if (p.im2col_T && !p.im2col_b) {
+          if (p.im2col_T) {
             load_a_im2col<true>(sa, &tma_a, &full_bar[stage], m0, kb, p);
           } else if (!p.a_mn) {
             tma_load_2d_cta2(sa, &tma_a, &full_bar[stage], kb * BK, m0);
@@ -717,9 +711,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
             for (int c = 0; c < BM / 64; ++c)
               tma_load_2d_cta2(sa + c * (64 * BK * 2), &tma_a, &full_bar[stage], m0 + c * 64, kb * BK);
           }
-          if (p.im2col_T && p.im2col_b) {
-            load_b_im2col<true>(sb, &tma_b, &full_bar[stage], n0, BN2 / 2, kb, p);
-          } else if (!p.b_mn) {
+          if (!p.b_mn) {
             tma_load_2d_cta2(sb, &tma_b, &full_bar[stage], kb * BK, n0);
           } else {
 #pragma unroll
@@ -766,7 +758,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
           const uint32_t sb = smem_u32(smem_b + stage * B2_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t adesc = p.im2col_T ? make_smem_desc_sw32(sa + k * IM2COL_SUB_BYTES) : make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
             umma_bf16_cta2(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
@@ -951,17 +943,17 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t ou
   return YMP_OK;
 }
 
-// 5D map over a bf16 video [B, C, T, H, W] for the fused im2col A operand: box {16 px, 4 rows, T frames, 1, 1}
-static int make_video_map(CUtensorMap* m, const ymp_gemm_args* a, const void* video) {
+// 5D map over a bf16 video [B, C, T, H, W] for the fused im2col A operand: box {16 px, 1 row, T frames, 1, 1}, SWIZZLE_32B
+static int make_video_map(CUtensorMap* m, const ymp_gemm_args* a) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(YMP_ECUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
   const cuuint64_t W = a->im2col_W, H = a->im2col_H, T = a->im2col_T, C = a->im2col_C, B = a->im2col_B;
   cuuint64_t dims[5] = {W, H, T, C, B};
   cuuint64_t strides[4] = {W * 2, H * W * 2, T * H * W * 2, C * T * H * W * 2};
-  cuuint32_t box[5] = {16, 4, (cuuint32_t)T, 1, 1};
+  cuuint32_t box[5] = {16, 1, (cuuint32_t)T, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(video), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a->A), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(YMP_ECUDA, "cuTensorMapEncodeTiled (video, 5-D) failed (%d)", (int)r);
   return YMP_OK;
@@ -989,12 +981,11 @@ static int launch_gemm(const ymp_gemm_args* a, const GemmKParams& kp, cudaStream
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb;
   int rc;
-  if (a->im2col_P && !a->im2col_operand) rc = make_video_map(&ta, a, a->A);
+  if (a->im2col_P) rc = make_video_map(&ta, a);
   else if (!a->a_mn_major) rc = make_map(&ta, a->A, a->K, a->M, a->lda, BK, BM);
   else rc = make_map(&ta, a->A, a->M, a->K, a->lda, 64, BK);
   if (rc) return rc;
-  if (a->im2col_P && a->im2col_operand) rc = make_video_map(&tb, a, a->B);
-  else if (!a->b_mn_major) rc = make_map(&tb, a->B, a->K, a->N, a->ldb, BK, BN);
+  if (!a->b_mn_major) rc = make_map(&tb, a->B, a->K, a->N, a->ldb, BK, BN);
   else rc = make_map(&tb, a->B, a->N, a->K, a->ldb, 64, BK);
   if (rc) return rc;
 
@@ -1033,12 +1024,11 @@ static int launch_gemm_2cta(const ymp_gemm_args* a, GemmKParams kp, cudaStream_t
     }
   }
 
-  if (a->im2col_P && !a->im2col_operand) rc = make_video_map(&ta, a, a->A);
+  if (a->im2col_P) rc = make_video_map(&ta, a);
   else if (!a->a_mn_major) rc = make_map(&ta, a->A, a->K, a->M, a->lda, BK, BM);
   else rc = make_map(&ta, a->A, a->M, a->K, a->lda, 64, BK);
   if (rc) return rc;
-  if (a->im2col_P && a->im2col_operand) rc = make_video_map(&tb, a, a->B);
-  else if (!a->b_mn_major) rc = make_map(&tb, a->B, a->K, a->N, a->ldb, BK, BN2 / 2);
+  if (!a->b_mn_major) rc = make_map(&tb, a->B, a->K, a->N, a->ldb, BK, BN2 / 2);
   else rc = make_map(&tb, a->B, a->N, a->K, a->ldb, 64, BK);
   if (rc) return rc;
   static bool attr_set = false;
@@ -1070,21 +1060,17 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
   YMP_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "ymp_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
   if (a->im2col_P) {
     const int P = a->im2col_P, T = a->im2col_T;
-    YMP_CHECK_ARG(P == 16 && T > 0 && T % 8 == 0 && 64 % T == 0 && a->im2col_H % P == 0 && a->im2col_W % P == 0,
-                  "ymp_gemm(im2col): needs P = 16, T %% 8 == 0, 64 %% T == 0, H, W multiples of P (P=%d T=%d H=%d W=%d)", P, T,
+    YMP_CHECK_ARG(P == 16 && T > 0 && T % 8 == 0 && 128 % T == 0 && a->im2col_H % P == 0 && a->im2col_W % P == 0 && !a->a_mn_major,
+                  "ymp_gemm(im2col): needs P = 16, T %% 8 == 0, 128 %% T == 0, H, W multiples of P (P=%d T=%d H=%d W=%d)", P, T,
                   a->im2col_H, a->im2col_W);
     const long rows = (long)a->im2col_B * (a->im2col_H / P) * (a->im2col_W / P) * T;
-    const int cols = a->im2col_C * P * P;
-    if (!a->im2col_operand)
-      YMP_CHECK_ARG(!a->a_mn_major && a->M == rows && a->K == cols, "ymp_gemm(im2col A): needs a_mn_major = 0, M = B*N*T, K = C*P*P (M=%d K=%d)", a->M, a->K);
-    else
-      YMP_CHECK_ARG(a->b_mn_major && a->K == rows && a->N == cols, "ymp_gemm(im2col B): needs b_mn_major = 1, K = B*N*T, N = C*P*P (K=%d N=%d)", a->K, a->N);
+    YMP_CHECK_ARG(a->M == rows && a->K == a->im2col_C * P * P, "ymp_gemm(im2col): needs M = B*N*T, K = C*P*P (M=%d K=%d)", a->M, a->K);
   }
-  const bool ia = a->im2col_P && !a->im2col_operand, ib = a->im2col_P && a->im2col_operand;
-  YMP_CHECK_ARG((ia || a->lda % 8 == 0) && (ib || a->ldb % 8 == 0), "ymp_gemm: lda/ldb must be multiples of 8 (lda=%d ldb=%d)", a->lda, a->ldb);
+  const bool ia = a->im2col_P != 0;
+  YMP_CHECK_ARG((ia || a->lda % 8 == 0) && a->ldb % 8 == 0, "ymp_gemm: lda/ldb must be multiples of 8 (lda=%d ldb=%d)", a->lda, a->ldb);
   YMP_CHECK_ARG(aligned16(a->A) && aligned16(a->B) && aligned16(a->D), "ymp_gemm: A/B/D must be 16-byte aligned");
   YMP_CHECK_ARG(ia || a->lda >= (a->a_mn_major ? a->M : a->K), "ymp_gemm: lda too small");
-  YMP_CHECK_ARG(ib || a->ldb >= (a->b_mn_major ? a->N : a->K), "ymp_gemm: ldb too small");
+  YMP_CHECK_ARG(a->ldb >= (a->b_mn_major ? a->N : a->K), "ymp_gemm: ldb too small");
   YMP_CHECK_ARG(a->ldd >= a->N && a->ldd % 8 == 0, "ymp_gemm: ldd must be >= N and a multiple of 8 (ldd=%d)", a->ldd);
   YMP_CHECK_ARG(a->act >= 0 && a->act <= 2, "ymp_gemm: bad act %d", a->act);
   YMP_CHECK_ARG(!a->residual || (a->ldr >= a->N && a->ldr % 8 == 0 && aligned16(a->residual)), "ymp_gemm: bad residual ld/alignment");
@@ -1155,7 +1141,6 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
   kp.res_row_mod = a->res_row_mod; kp.d_row_block = a->d_row_block; kp.d_row_stride = a->d_row_stride;
   kp.epi_tma = 0;
   kp.im2col_T = a->im2col_P ? a->im2col_T : 0;
-  kp.im2col_b = a->im2col_operand ? 1 : 0;
   kp.im2col_Wp = a->im2col_P ? a->im2col_W / a->im2col_P : 0;
   kp.im2col_N = a->im2col_P ? (a->im2col_H / a->im2col_P) * kp.im2col_Wp : 0;
   kp.has_drop = (a->drop.rng && a->drop.p > 0.f) ? 1 : 0;

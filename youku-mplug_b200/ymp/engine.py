@@ -265,13 +265,16 @@ def vit_bwd(W, G, c, d_out):
             G[VE + "pos_embed"].view(d.N + 1, d.D)[1:].add_(dtab.sum(1))
         if VE + "temporal_embed" in G:
             G[VE + "temporal_embed"].view(d.T, d.D).add_(dtab.sum(0))
-    if c.patches is not None:
-        linear_wgrad(dx0[:d.R], c.patches, VE + "patch_embed.proj.weight", VE + "patch_embed.proj.bias", G)
-    else:   # fused im2col on the B operand of the weight-gradient GEMM
-        if VE + "patch_embed.proj.weight" in G:
-            ops.patch_embed_wgrad(dx0[:d.R], c.video, d.P, G[VE + "patch_embed.proj.weight"].view(d.D, -1))
-        if VE + "patch_embed.proj.bias" in G:
-            ops.colsum(dx0[:d.R], G[VE + "patch_embed.proj.bias"])
+    patches = c.patches
+    if patches is None and VE + "patch_embed.proj.weight" in G:
+        # the forward gathered its operand tiles from the video; the weight gradient (an MN-major B operand: four pixel
+        # rows per 128-byte shared-memory row, which TMA boxes cannot produce from [B,C,T,H,W]) materialises the patch
+        # matrix here, in the backward only
+        patches = ops.im2col(c.video, d.P)
+    if patches is not None:
+        linear_wgrad(dx0[:d.R], patches, VE + "patch_embed.proj.weight", VE + "patch_embed.proj.bias", G)
+    elif VE + "patch_embed.proj.bias" in G:
+        ops.colsum(dx0[:d.R], G[VE + "patch_embed.proj.bias"])
 
 
 # ------------------------------------------------------------------------------------------

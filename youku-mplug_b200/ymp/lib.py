@@ -47,7 +47,7 @@ class GemmArgs(C.Structure):
         ("alpha", C.c_float), ("tile_n", c_i32),
         ("res_row_mod", c_i32), ("d_row_block", c_i32), ("d_row_stride", c_i32), ("residual_dtype", c_i32),
         ("drop", DropoutSpec),
-        ("im2col_P", c_i32), ("im2col_B", c_i32), ("im2col_C", c_i32), ("im2col_T", c_i32), ("im2col_H", c_i32), ("im2col_W", c_i32), ("im2col_operand", c_i32),
+        ("im2col_P", c_i32), ("im2col_B", c_i32), ("im2col_C", c_i32), ("im2col_T", c_i32), ("im2col_H", c_i32), ("im2col_W", c_i32),
     ]
 
 

@@ -68,17 +68,12 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, 
     """
     _chk2d(a, "a"); _chk2d(b, "b")
     assert a.dtype == bf16 and b.dtype == bf16
-    im_b = _im2col is not None and len(_im2col) > 6 and _im2col[6]
-    if _im2col is not None and not im_b:
-        P, vB, vC, vT, vH, vW = _im2col[:6]
+    if _im2col is not None:
+        P, vB, vC, vT, vH, vW = _im2col
         M, K = vB * (vH // P) * (vW // P) * vT, vC * P * P
     else:
         M, K = (a.shape[1], a.shape[0]) if a_t else (a.shape[0], a.shape[1])
-    if im_b:
-        P, vB, vC, vT, vH, vW = _im2col[:6]
-        N, Kb = vC * P * P, vB * (vH // P) * (vW // P) * vT
-    else:
-        N, Kb = (b.shape[1], b.shape[0]) if b_t else (b.shape[0], b.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_t else (b.shape[0], b.shape[1])
     assert K == Kb, f"gemm: K mismatch {K} vs {Kb}"
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=out_dtype)
@@ -114,8 +109,7 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, 
     g.res_row_mod, g.d_row_block, g.d_row_stride = res_row_mod, d_row_block, d_row_stride
     _set_drop(g.drop, drop)
     if _im2col is not None:
-        g.im2col_P, g.im2col_B, g.im2col_C, g.im2col_T, g.im2col_H, g.im2col_W = _im2col[:6]
-        g.im2col_operand = int(bool(im_b))
+        g.im2col_P, g.im2col_B, g.im2col_C, g.im2col_T, g.im2col_H, g.im2col_W = _im2col
     L.call(L._gemm, g, "ymp_gemm")
     return out
 
@@ -274,17 +268,9 @@ def patch_embed_gemm(video, weight2d, P, **kw):
     return gemm(video.view(B * Cc * T * H, W), weight2d, _im2col=(P, B, Cc, T, H, W), **kw)
 
 
-def patch_embed_wgrad(dy, video, P, out):
-    """out [D, C*P*P] (fp32, accumulated) += dy^T . patches with the patch matrix gathered from the video by the
-    TMA producer of the B operand (MN-major): the weight gradient of the patch embedding without an im2col buffer."""
-    assert video.is_contiguous() and video.dtype == bf16 and video.dim() == 5
-    B, Cc, T, H, W = video.shape
-    return gemm(dy, video.view(B * Cc * T * H, W), a_t=True, b_t=True, out=out, accumulate=True, _im2col=(P, B, Cc, T, H, W, 1))
-
-
 def fused_im2col_ok(T, P):
     import os
-    return os.environ.get("YMP_FUSED_IM2COL", "1") != "0" and P == 16 and T % 8 == 0 and 64 % T == 0
+    return os.environ.get("YMP_FUSED_IM2COL", "1") != "0" and P == 16 and T % 8 == 0 and 128 % T == 0
 
 
 def im2col(video, P, out=None):

@@ -238,6 +238,9 @@ class TrainEngine:
             st["calls"] += 1
             return loss.detach()
         if "graph" not in st:
+            # the eager warm-up steps left their activations in the caching allocator; the graph gets a private pool of
+            # the same size, so hand the cached blocks back first (B = 96 retrieval / 2.7B caption steps would not fit twice)
+            torch.cuda.empty_cache()
             st["static"] = [_static_like(x) for x in inputs]
             for s_, x in zip(st["static"], inputs):
                 _copy_into(s_, x)
@@ -299,7 +302,8 @@ def _tensors_of(x):
 def _signature(x):
     if x is None:
         return None
-    return tuple((k, tuple(v.shape), str(v.dtype)) for k, v in sorted(_tensors_of(x).items()))
+    # floating inputs of any dtype share one graph: their static buffer is bf16 (the copy casts)
+    return tuple((k, tuple(v.shape), "float" if v.is_floating_point() else str(v.dtype)) for k, v in sorted(_tensors_of(x).items()))
 
 
 def _static_like(x):
