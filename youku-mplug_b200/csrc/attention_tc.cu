@@ -142,7 +142,7 @@ __device__ __forceinline__ void tc_load256(uint8_t* blk0, uint8_t* blk1, const T
   }
 }
 
-template <int HD, bool LONG>
+template <int HD, bool LONG, bool DROP>
 __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) {
   static_assert(HD == 64 || HD == 96, "head_dim 64 or 96 (80 / 88 are padded to 96)");
   constexpr bool TWO = (HD == 96);
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) 
   if (p.mask == TC_MASK_BLOCK) { lo = (row / p.mask_block) * p.mask_block; hi = min(hi, lo + p.mask_block); }
 
   DropState ds = {};
-  if (p.has_drop) ds = drop_state(p.drop);
+  if (DROP) ds = drop_state(p.drop);
   const uint32_t drow = ((uint32_t)s * p.n_heads + h) * p.s_q + row;   // logical row of the probability matrix
   float m_run = -CUDART_INF_F, l_run = 0.f;   // running row max (raw scores) and row sum
   float oacc[LONG ? 2 : 1][LONG ? 32 : 1];    // LONG: this thread's O chunks (chunk c of HD/32 belongs to warpgroup c & 1)
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const AttnTcParams p) 
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) lsum += pv[i];
-        if (p.has_drop) {  // O = dropout(P) V; the normaliser stays that of the undropped P (:772-780: softmax, then dropout)
+        if (DROP) {  // O = dropout(P) V; the normaliser stays that of the undropped P (:772-780: softmax, then dropout)
 #pragma unroll
           for (int j = 0; j < 8; ++j) drop4(ds, drow, (uint32_t)(k0 + c * 32 + 4 * j), pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
         }
@@ -451,7 +451,7 @@ __device__ __forceinline__ void tc_load128(uint8_t* blk0, uint8_t* blk1, const T
 }
 __device__ __forceinline__ void wg_sync(int w) { asm volatile("bar.sync %0, 128;" ::"r"(1 + w) : "memory"); }
 
-template <int HD>
+template <int HD, bool DROP>
 __global__ void __launch_bounds__(256, 1) attn_tc_fwd_pair_kernel(const AttnTcParams p) {
   static_assert(HD == 64 || HD == 96, "head_dim 64 or 96 (80 / 88 are padded to 96)");
   constexpr bool TWO = (HD == 96);
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(256, 1) attn_tc_fwd_pair_kernel(const AttnTcPa
     fence_mbar_init();
   }
   DropState ds = {};
-  if (p.has_drop) ds = drop_state(p.drop);
+  if (DROP) ds = drop_state(p.drop);
 
   // loads of one item: K, V by all 256 threads, the Q tile of warpgroup w by its 128 threads
   auto item_len = [&](int it, int& sq, int& skv) {
@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(256, 1) attn_tc_fwd_pair_kernel(const AttnTcPa
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) lsum += pv[i];
-        if (p.has_drop) {
+        if (DROP) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) drop4(ds, drow, (uint32_t)(c * 32 + 4 * j), pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
         }
@@ -795,7 +795,7 @@ __device__ __forceinline__ void tc_rows_load256(uint8_t* stage, const TcMat& m, 
 }
 
 
-template <int HD>
+template <int HD, bool DROP>
 __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdParams p) {
   static_assert(HD == 64 || HD == 96, "head_dim 64 or 96");
   constexpr bool TWO = (HD == 96);
@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
   const uint32_t tl = tmem + ((uint32_t)(wq * 32) << 16);
   const int kr = wq * 32 + lane;  // this thread's TMEM lane: key row (softmax, dK/dV) or query row (dQ)
   DropState ds = {};
-  if (p.has_drop) ds = drop_state(p.drop);
+  if (DROP) ds = drop_state(p.drop);
   const uint32_t drow0 = ((uint32_t)s * p.n_heads + h) * p.s_q;  // logical row of query 0 in the probability matrix
   TDBG(1);
 
@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
         // consecutive KEYS of one query, so the 4 lanes of a key group split the 32 queries (8 calls each) and
         // exchange their packed keep-bits - 8 calls + 4 shuffles per chunk instead of 32 calls
         uint32_t kb[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-        if (p.has_drop) {
+        if (DROP) {
           uint32_t mine = 0;
           const uint32_t kg = (uint32_t)(kj0 + kr) >> 2;
 #pragma unroll
@@ -979,7 +979,7 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
 #pragma unroll
           for (int i = 0; i < 4; ++i) kb[i] = __shfl_sync(0xffffffffu, mine, (lane & ~3) + i) >> (lane & 3);
         }
-        const float dsc = p.has_drop ? ds.scale : 1.f;
+        const float dsc = DROP ? ds.scale : 1.f;
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float4 st = st4[e];  // (lse2, delta) of two consecutive queries, warp-broadcast
@@ -1124,11 +1124,13 @@ static int launch_tc(const AttnTcParams& p, cudaStream_t st) {
   const int smem = 128 * 128 + 2 * kvr * 128 + (HD == 96 ? 128 * 64 + 2 * kvr * 64 : 0) + 1024 + 64 + 1024;
   static int cur = 0;
   if (smem > cur) {
-    YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<HD, LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<HD, LONG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<HD, LONG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cur = smem;
   }
   dim3 grid((p.s_q + 127) / 128, p.n_heads, p.n_seq);
-  attn_tc_fwd_kernel<HD, LONG><<<grid, 256, smem, st>>>(p);
+  if (p.has_drop) attn_tc_fwd_kernel<HD, LONG, true><<<grid, 256, smem, st>>>(p);
+  else attn_tc_fwd_kernel<HD, LONG, false><<<grid, 256, smem, st>>>(p);
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }
@@ -1137,11 +1139,13 @@ template <int HD>
 static int launch_tc_pair(const AttnTcParams& p, int smem, cudaStream_t st) {
   static int cur = 0;
   if (smem > cur) {
-    YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_pair_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_pair_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_pair_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cur = smem;
   }
   const int items = p.n_seq * p.n_heads;
-  attn_tc_fwd_pair_kernel<HD><<<min(items, num_sms()), 256, smem, st>>>(p);
+  if (p.has_drop) attn_tc_fwd_pair_kernel<HD, true><<<min(items, num_sms()), 256, smem, st>>>(p);
+  else attn_tc_fwd_pair_kernel<HD, false><<<min(items, num_sms()), 256, smem, st>>>(p);
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }
@@ -1190,9 +1194,14 @@ template <int HD>
 static int launch_tc_bwd(const AttnTcBwdParams& p, cudaStream_t st) {
   const int smem = 8 * 16384 + (HD == 96 ? 6 * 8192 : 0) + 128 * (HD * 2 + 16) + ((p.s_q + 127) & ~127) * 8 + 64 + 1024;
   static int cur = 0;
-  if (smem > cur) { YMP_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cur = smem; }
+  if (smem > cur) {
+    YMP_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    YMP_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cur = smem;
+  }
   dim3 grid(p.n_heads, p.n_seq);
-  attn_tc_bwd_kernel<HD><<<grid, 256, smem, st>>>(p);
+  if (p.has_drop) attn_tc_bwd_kernel<HD, true><<<grid, 256, smem, st>>>(p);
+  else attn_tc_bwd_kernel<HD, false><<<grid, 256, smem, st>>>(p);
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }

@@ -144,6 +144,7 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmKParams& p, int row,
 }
 
 // Epilogue for one thread: 32 consecutive columns of one output row.
+template <bool DROP>
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint32_t (&r)[32],
                                                int row, int col0, const EpiPrefetch& pf, const DropState& ds) {
   if (row >= p.M || col0 >= p.N) return;
@@ -197,7 +198,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
       store16(p.aux_out + off, p.v32_aux, v);
       store16(p.aux_out + off + 16, p.v32_aux, v + 16);
     }
-    if (p.has_drop) {  // bias-dropout-add: residual + dropout(x + bias)
+    if constexpr (DROP) {  // bias-dropout-add: residual + dropout(x + bias)
 #pragma unroll
       for (int j = 0; j < 8; ++j) drop4(ds, (uint32_t)row, (uint32_t)(col0 + 4 * j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
@@ -258,7 +259,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
         } else if (p.aux_out) {
           p.aux_out[off] = __float2bfloat16(x);
         }
-        if (p.has_drop) {
+        if constexpr (DROP) {
           const uint4 w = drop_words(ds, (uint32_t)row, (uint32_t)col >> 2);
           const uint32_t wc = (col & 3) == 0 ? w.x : (col & 3) == 1 ? w.y : (col & 3) == 2 ? w.z : w.w;
           x = wc >= ds.thresh ? x * ds.scale : 0.f;
@@ -354,6 +355,7 @@ __device__ __forceinline__ void epilogue_pre(const GemmKParams& p, uint32_t (&r)
     }
   }
 }
+template <bool DROP>
 __device__ __forceinline__ void epilogue_post(const GemmKParams& p, uint32_t (&r)[32], const EpiPrefetch& pf, const DropState& ds,
                                               int row, int col0) {
   if (p.aux_in) {
@@ -369,7 +371,7 @@ __device__ __forceinline__ void epilogue_post(const GemmKParams& p, uint32_t (&r
 #pragma unroll
     for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(gelu_tanh(__uint_as_float(r[i])));
   }
-  if (p.has_drop) {
+  if constexpr (DROP) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint4 w = drop_words(ds, (uint32_t)row, (uint32_t)(col0 >> 2) + j);
@@ -429,7 +431,7 @@ __device__ __forceinline__ void stage_f32(uint8_t* buf, int lr, const uint32_t (
     st_shared_v4(buf + lr * 128 + ((j ^ (lr & 7)) << 4), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
 }
 
-template <int BN>
+template <int BN, bool DROP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                          const __grid_constant__ CUtensorMap tma_b, const GemmKParams p) {
@@ -560,8 +562,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     const int q = warp_idx & 3;              // TMEM lane quarter this warp may access
     const int half = (warp_idx - 4) >> 2;    // which half of the BN columns
     constexpr int CHUNKS = BN / 2 / 32;
-    DropState ds = {};
-    if (p.has_drop) ds = drop_state(p.drop);
+    DropState ds;   // only touched by the DROP instantiations
+    if constexpr (DROP) ds = drop_state(p.drop);
     int as = 0;
     uint32_t aphase = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -585,7 +587,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
-        epilogue_chunk(p, r, row, n_blk * BN + coff, pf, ds);
+        epilogue_chunk<DROP>(p, r, row, n_blk * BN + coff, pf, ds);
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -624,7 +626,7 @@ __device__ unsigned long long ymp_gemm_dbg_buf[16];
 #define GDBG_T() 0ll
 #endif
 
-template <bool TMA_EPI>
+template <bool TMA_EPI, bool DROP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
                               const __grid_constant__ CUtensorMap tma_b,
@@ -702,9 +704,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);  // bytes of both CTAs land here
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * B2_STAGE_BYTES;
-          if (p.im2col_T) {
-            load_a_im2col<true>(sa, &tma_a, &full_bar[stage], m0, kb, p);
-          } else if (!p.a_mn) {
+          if (!p.a_mn) {
             tma_load_2d_cta2(sa, &tma_a, &full_bar[stage], kb * BK, m0);
           } else {
 #pragma unroll
@@ -758,7 +758,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
           const uint32_t sb = smem_u32(smem_b + stage * B2_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = p.im2col_T ? make_smem_desc_sw32(sa + k * IM2COL_SUB_BYTES) : make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t adesc = make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
             umma_bf16_cta2(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
@@ -774,8 +774,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
     const int q = warp_idx & 3;
     const int half = (warp_idx - 4) >> 2;
     constexpr int CHUNKS = BN2 / 2 / 32;
-    DropState ds = {};
-    if (p.has_drop) ds = drop_state(p.drop);
+    DropState ds;   // only touched by the DROP instantiations
+    if constexpr (DROP) ds = drop_state(p.drop);
     int as = 0;
     uint32_t aphase = 0;
     uint32_t ebox = 0;   // running count of this warp's bulk stores (staging buffer parity)
@@ -812,7 +812,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
             if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // always on the leader's barrier
           }
           epilogue_pre(p, r, pf);
-          if (!p.aux_out) epilogue_post(p, r, pf, ds, row, col0);
+          if (!p.aux_out) epilogue_post<DROP>(p, r, pf, ds, row, col0);
           if (p.out_f32) {
             // one box per chunk (32 fp32 columns = 128 bytes per row); the two buffers alternate
             uint8_t* buf = ebuf + (ebox & 1) * EPI_BUF_BYTES;
@@ -883,7 +883,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // always on the leader's barrier
         }
-        epilogue_chunk(p, r, row, n_blk * BN2 + coff, pf, ds);
+        epilogue_chunk<DROP>(p, r, row, n_blk * BN2 + coff, pf, ds);
       }
       }
 #ifdef YMP_GEMM_DBG
@@ -991,14 +991,17 @@ static int launch_gemm(const ymp_gemm_args* a, const GemmKParams& kp, cudaStream
 
   static bool attr_set = false;
   if (!attr_set) {
-    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>,
+    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int num_m = (a->M + BM - 1) / BM, num_n = (a->N + BN - 1) / BN;
   const int units = num_m * num_n * kp.split_k;
   const int grid = units < num_sms() ? units : num_sms();
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, kp);
+  if (kp.has_drop) gemm_bf16_tcgen05_kernel<BN, true><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, kp);
+  else gemm_bf16_tcgen05_kernel<BN, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, kp);
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }
@@ -1024,8 +1027,7 @@ static int launch_gemm_2cta(const ymp_gemm_args* a, GemmKParams kp, cudaStream_t
     }
   }
 
-  if (a->im2col_P) rc = make_video_map(&ta, a);
-  else if (!a->a_mn_major) rc = make_map(&ta, a->A, a->K, a->M, a->lda, BK, BM);
+  if (!a->a_mn_major) rc = make_map(&ta, a->A, a->K, a->M, a->lda, BK, BM);
   else rc = make_map(&ta, a->A, a->M, a->K, a->lda, 64, BK);
   if (rc) return rc;
   if (!a->b_mn_major) rc = make_map(&tb, a->B, a->K, a->N, a->ldb, BK, BN2 / 2);
@@ -1033,8 +1035,10 @@ static int launch_gemm_2cta(const ymp_gemm_args* a, GemmKParams kp, cudaStream_t
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair<true>::SMEM_BYTES));
-    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair<false>::SMEM_BYTES));
+    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair<true>::SMEM_BYTES));
+    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair<false>::SMEM_BYTES));
+    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair<true>::SMEM_BYTES));
+    YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair<false>::SMEM_BYTES));
     attr_set = true;
   }
   const int num_m = (a->M + 2 * BM - 1) / (2 * BM), num_n = (a->N + BN2 - 1) / BN2;
@@ -1042,10 +1046,12 @@ static int launch_gemm_2cta(const ymp_gemm_args* a, GemmKParams kp, cudaStream_t
   const int pairs = min(units, num_sms() / 2);
   if (!kp.epi_tma) {
     td = tx = ta;        // never dereferenced
-    gemm_bf16_tcgen05_2cta_kernel<false><<<2 * pairs, GEMM_THREADS, Pair<false>::SMEM_BYTES, stream>>>(ta, tb, td, tx, kp);
+    if (kp.has_drop) gemm_bf16_tcgen05_2cta_kernel<false, true><<<2 * pairs, GEMM_THREADS, Pair<false>::SMEM_BYTES, stream>>>(ta, tb, td, tx, kp);
+    else gemm_bf16_tcgen05_2cta_kernel<false, false><<<2 * pairs, GEMM_THREADS, Pair<false>::SMEM_BYTES, stream>>>(ta, tb, td, tx, kp);
   } else {
     if (!a->aux_out) tx = td;
-    gemm_bf16_tcgen05_2cta_kernel<true><<<2 * pairs, GEMM_THREADS, Pair<true>::SMEM_BYTES, stream>>>(ta, tb, td, tx, kp);
+    if (kp.has_drop) gemm_bf16_tcgen05_2cta_kernel<true, true><<<2 * pairs, GEMM_THREADS, Pair<true>::SMEM_BYTES, stream>>>(ta, tb, td, tx, kp);
+    else gemm_bf16_tcgen05_2cta_kernel<true, false><<<2 * pairs, GEMM_THREADS, Pair<true>::SMEM_BYTES, stream>>>(ta, tb, td, tx, kp);
   }
   YMP_LAUNCH_CHECK();
   return YMP_OK;
@@ -1091,6 +1097,7 @@ extern "C" int ymp_gemm(const ymp_gemm_args* a, void* stream) {
   const int kb_total = (a->K + BK - 1) / BK;
   const int sms = num_sms();
   int bn = a->tile_n;
+  if (a->im2col_P) bn = (a->N <= 128) ? 128 : 256;   // the fused-im2col producer lives in the 1-CTA kernels (one GEMM per step)
   if (bn == 0) {
     // CTA-pair 256x256 tiles when there are enough of them to fill the machine; otherwise the
     // 128x256 tile, or 128x128 when even that leaves most SMs idle or N is narrow
