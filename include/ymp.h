@@ -127,6 +127,20 @@ typedef struct ymp_gemm_args {
 
 int ymp_gemm(const ymp_gemm_args* a, void* stream);
 
+/* Skinny GEMM for single-token decoding (KV-cache steps of sample() / beam_search(),
+ * models/modeling_distributed_gpt3.py:1620-1886): y[M, N] = epilogue(x[M, K] . w[N, K]^T), 1 <= M <= 8.  One pass over the
+ * weights, HBM-bound, no tensor cores (csrc/gemv.cu).  Epilogue: + bias[n], act (YMP_ACT_*), + residual[m, n], store. */
+typedef struct ymp_gemm_skinny_args {
+  const void* x;         /* bf16 [M, K], row stride ldx */
+  const void* w;         /* bf16 [N, K], row stride ldw (an nn.Linear weight) */
+  const void* bias;      /* bf16 [N] or NULL */
+  const void* residual;  /* bf16 / fp32 [M, N] (residual_dtype), row stride ldr, or NULL */
+  void* y;               /* bf16 / fp32 [M, N] (out_dtype), row stride ldy */
+  int32_t M, N, K, ldx, ldw, ldr, ldy;
+  int32_t act, residual_dtype, out_dtype;
+} ymp_gemm_skinny_args;
+int ymp_gemm_skinny(const ymp_gemm_skinny_args* a, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * LayerNorm (fp32 statistics, bf16 in/out), one warp per row.
  * Replaces LayerNormWithForceFP32.forward (models/vision_transformer.py:69-71: cast->LN->cast,
@@ -220,6 +234,9 @@ typedef struct ymp_attn_args {
   float scale;
   ymp_dropout_spec drop;  /* dropout of the attention probabilities (tcgen05 kernels only): O = dropout(P) V, the
                              softmax statistics (lse) stay those of the undropped P */
+  const int32_t* s_kv_dev; /* optional DEVICE scalar: only the first min(s_kv, *s_kv_dev) keys exist.  Lets a captured
+                             CUDA graph of the single-token decoding step follow the growing KV cache (forward only,
+                             served by the mma.sync kernels) */
 } ymp_attn_args;
 int ymp_attn_fwd(const ymp_attn_args* a, void* stream);
 

@@ -167,3 +167,45 @@ def test_gemm_pair_tile_tma_epilogue_variants(cuda, M):
     # many tiles per pair
     big = torch.randn(40000, K, device=cuda).bfloat16()
     _close(ops.gemm(big, b, bias=bias, tile_n=512), big.float() @ b.float().t() + bias.float(), 1e-2)
+
+
+@pytest.mark.parametrize("M", [1, 5, 8])
+@pytest.mark.parametrize("N,K", [(2048, 2048), (6144, 2048), (8192, 2048), (2048, 8192), (51200, 2048), (50, 64), (130, 2560)])
+def test_gemm_skinny_decode_shapes(cuda, M, N, K):
+    """ymp_gemm_skinny (single-token decoding linears, csrc/gemv.cu) vs fp32 torch on the same bf16 inputs: every
+    K-split the host heuristic picks at the 1.3B / 2.7B shapes, ragged N, all epilogues."""
+    from ymp import ops
+    torch.manual_seed(M + N)
+    x = torch.randn(M, K, device=cuda).bfloat16()
+    w = (torch.randn(N, K, device=cuda) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device=cuda).bfloat16()
+    res32 = torch.randn(M, N, device=cuda)
+    resb = torch.randn(M, N, device=cuda).bfloat16()
+    pre = x.float() @ w.float().t()
+    _close(ops.gemm_skinny(x, w), pre)
+    _close(ops.gemm_skinny(x, w, out_dtype=torch.float32), pre, tol=1e-4)
+    _close(ops.gemm_skinny(x, w, bias=bias, act=2), torch.nn.functional.gelu(pre + bias.float(), approximate="tanh"))
+    _close(ops.gemm_skinny(x, w, bias=bias, act=1), torch.nn.functional.gelu(pre + bias.float()))
+    _close(ops.gemm_skinny(x, w, bias=bias, residual=res32, out_dtype=torch.float32), pre + bias.float() + res32, tol=1e-4)
+    _close(ops.gemm_skinny(x, w, bias=bias, residual=resb), pre + bias.float() + resb.float())
+    # against the tensor-core GEMM on the same inputs (fp32 accumulation on both sides, different summation order)
+    _close(ops.gemm_skinny(x, w, bias=bias, out_dtype=torch.float32), ops.gemm(x, w, bias=bias, out_dtype=torch.float32).float(), tol=1e-4)
+    # strided rows: x and y as column slices of wider buffers
+    xw = torch.randn(M, K + 64, device=cuda).bfloat16()
+    yw = torch.zeros(M, N + 8, device=cuda, dtype=torch.bfloat16)
+    ops.gemm_skinny(xw[:, 32:32 + K], w, out=yw[:, :N])
+    _close(yw[:, :N], (xw[:, 32:32 + K].float() @ w.float().t()))
+    assert float(yw[:, N:].abs().max()) == 0.0
+
+
+def test_gemm_skinny_rejects_wide_inputs(cuda):
+    from ymp import lib, ops
+    x = torch.randn(8, 64, device=cuda).bfloat16()
+    w = torch.randn(16, 64, device=cuda).bfloat16()
+    a = lib.GemmSkinnyArgs()
+    a.x, a.w, a.y = x.data_ptr(), w.data_ptr(), torch.empty(9, 16, device=cuda, dtype=torch.bfloat16).data_ptr()
+    a.M, a.N, a.K, a.ldx, a.ldw, a.ldy = 9, 16, 64, 64, 64, 16
+    import ctypes
+    assert lib._gemm_skinny(ctypes.byref(a), lib.cur_stream()) == -1
+    with pytest.raises(AssertionError):
+        ops.gemm_skinny(torch.randn(9, 64, device=cuda).bfloat16(), w)

@@ -104,3 +104,45 @@ def test_greedy_sampling_matches_reference(cuda):
             t = int(diff[0])
             assert margins.get((i, t), 0.0) < 0.1, (i, t, out[i].tolist(), ref[i].tolist(), margins.get((i, t)))
     assert out.shape == ref.shape
+
+
+def test_token_step_graph_equals_eager_and_survives_reuse(cuda, monkeypatch):
+    """The captured single-token step (skinny GEMMs, device-side cache length) against the same kernels enqueued
+    eagerly, bit for bit, over a beam-shaped decode with cache reordering; then a second generate-style call that
+    reuses the pooled cache and its graph."""
+    import models.modeling_distributed_gpt3 as M
+    from ymp import lib
+    fx, model, video, _ = _setup(cuda)
+    dec, Q, beam = model.text_decoder, fx["Q"], 3
+    with torch.no_grad():
+        qf = model.visual_prefix(video.to(cuda).bfloat16())[3]
+
+    def run(sample, n_steps):
+        seq, plen = fx["greedy"][sample], int(fx["prompt_length"][sample])
+        dec.inference_params = M.InferenceParams(beam, plen + n_steps + 1 + Q)
+        outs = []
+        with torch.no_grad():
+            out = dec(tokens=seq[None, :plen].repeat(beam, 1).to(cuda), query_embeds=qf[sample:sample + 1].repeat(beam, 1, 1))
+            outs.append(out.logits[:, -1].clone())
+            for t in range(n_steps):
+                tok = out.logits[:, -1].argmax(-1, keepdim=True)
+                tok[1] = (tok[1] + 1 + t) % fx["gcfg"]["vocab_size"]   # make the beams differ
+                dec.inference_params.swap_key_value_dict([1, 0, 2] if t % 2 else [0, 2, 1])
+                out = dec(tokens=tok)
+                outs.append(out.logits[:, -1].clone())
+        return torch.stack(outs)
+
+    monkeypatch.setenv("YMP_DECODE_GRAPH", "0")
+    eager = run(0, 6)
+    monkeypatch.setenv("YMP_DECODE_GRAPH", "1")
+    dec.__dict__.pop("_decode_pool", None)
+    n0 = lib.launch_count()
+    graphed = run(0, 6)
+    assert torch.equal(eager, graphed)
+    ts = dec.inference_params.cache.token
+    assert ts is not None and ts.graph is not None
+    cache = dec.inference_params.cache
+    again = run(0, 6)                      # pooled cache + graph reused after reset()
+    assert dec.inference_params.cache is cache and cache.token is ts
+    assert torch.equal(eager, again)
+    assert lib.launch_count() > n0

@@ -38,8 +38,43 @@ def run(n_steps):
     return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]) / n_steps
 
 
-run(4)
-pre, step = run(32)
 wbytes = sum(p.numel() for p in dec.parameters()) * 2
-print("DECODE " + json.dumps(dict(beam=beam, prefill_rows=beam * (Q + P), prefill_ms=round(pre, 3), step_ms=round(step, 3),
-                                  weight_gb=round(wbytes / 1e9, 2), hbm_floor_ms=round(wbytes / 6.4e12 * 1e3, 3))))
+for mode in ("0", "1"):
+    os.environ["YMP_DECODE_GRAPH"] = mode
+    dec.__dict__.pop("_decode_pool", None)
+    run(4)
+    pre, step = run(32)
+    print("DECODE " + json.dumps(dict(graph=int(mode), beam=beam, prefill_rows=beam * (Q + P), prefill_ms=round(pre, 3),
+                                      step_ms=round(step, 3), weight_gb=round(wbytes / 1e9, 2),
+                                      hbm_floor_ms=round(wbytes / 6.4e12 * 1e3, 3))))
+
+# the skinny GEMM alone at the decode shapes, cycling through enough weight copies to defeat the 126 MB L2
+from ymp import ops  # noqa: E402
+for name, N, K, kw in (("qkv", 6144, 2048, {}), ("dense", 2048, 2048, dict(res=True)), ("fc1", 8192, 2048, dict(act=2)),
+                       ("fc2", 2048, 8192, dict(res=True)), ("lm_head", 51200, 2048, dict(f32=True))):
+    copies = max(2, int(400e6 // (N * K * 2)))
+    ws = [(torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16) for _ in range(copies)]
+    x = torch.randn(beam, K, device=dev).to(torch.bfloat16)
+    b = torch.randn(N, device=dev).to(torch.bfloat16)
+    r = torch.randn(beam, N, device=dev) if kw.get("res") else None
+    od = torch.float32 if (kw.get("res") or kw.get("f32")) else torch.bfloat16
+    for skinny in (True, False):
+        def call(w):
+            if skinny:
+                return ops.gemm_skinny(x, w, bias=b, residual=r, act=kw.get("act", 0), out_dtype=od)
+            return ops.gemm(x, w, bias=b, residual=r, act=kw.get("act", 0), out_dtype=od)
+        for w in ws:
+            call(w)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            for w in ws:
+                call(w)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / (reps * copies) * 1e3
+        print("SKINNY " + json.dumps(dict(shape=name, N=N, K=K, rows=beam, kernel="skinny" if skinny else "tcgen05",
+                                          us=round(us, 2), gbs=round(N * K * 2 / us / 1e3, 1))))
+    del ws

@@ -115,11 +115,13 @@ struct AttnKParams {
   float* delta;
   int lddo, hsdo, lddq, lddk, lddv, hsdq, hsdk, hsdv;
   SeqMap mdo, mdq, mdkv;
+  const int* skv_dev;  // optional device scalar: number of keys that exist (KV-cache decoding under a CUDA graph)
 };
 
 // effective lengths of sequence s (short last sequence when total_rows is set)
 __device__ __forceinline__ void eff_len(const AttnKParams& p, int s, int& sq, int& skv) {
   sq = p.s_q; skv = p.s_kv;
+  if (p.skv_dev) skv = min(skv, *p.skv_dev);
   if (p.total_rows > 0) {
     const long left = p.total_rows - (long)s * p.s_q;
     if (left < sq) sq = (int)left;
@@ -691,6 +693,7 @@ static int fill_params(const ymp_attn_args* a, AttnKParams& p, const char* who) 
   p.n_seq = a->n_seq; p.n_heads = a->n_heads; p.s_q = a->s_q; p.s_kv = a->s_kv;
   p.mask = a->mask; p.mask_block = a->mask_block > 0 ? a->mask_block : 1; p.total_rows = a->total_rows;
   p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.skv_dev = a->s_kv_dev;
   return YMP_OK;
 }
 
@@ -743,7 +746,10 @@ extern "C" int ymp_attn_fwd(const ymp_attn_args* a, void* stream) {
   static const bool legacy = [] { const char* e = getenv("YMP_ATTN_LEGACY"); return e && e[0] == '1'; }();
   const bool dropped = a->drop.rng && a->drop.p > 0.f;
   YMP_CHECK_ARG(!dropped || a->drop.p < 1.f, "ymp_attn_fwd: dropout p must be < 1");
-  if (!legacy || dropped) {
+  const bool dev_len = a->s_kv_dev != nullptr;  // key count read on the device: the mma.sync kernels bound their KV loop by it
+  YMP_CHECK_ARG(!dev_len || (!dropped && a->mask == YMP_MASK_NONE && a->total_rows == 0 && a->head_dim != 88),
+                "ymp_attn_fwd: s_kv_dev needs mask none, no dropout, no total_rows, head_dim in {64,80,96,128}");
+  if ((!legacy || dropped) && !dev_len) {
     if (!dropped) {
       rc = attn_small_fwd_try(a, st);  // short dense block-diagonal sequences (attention_small.cu)
       if (rc != YMP_ENOSUP) { g_attn_path = YMP_ATTN_PATH_SMALL; return rc; }
@@ -771,6 +777,7 @@ extern "C" int ymp_attn_bwd(const ymp_attn_bwd_args* b, void* stream) {
   if (rc) return rc;
   YMP_CHECK_ARG(a->o && a->lse && b->dout && b->dq && b->dk && b->dv && b->delta_ws, "ymp_attn_bwd: null o/lse/dout/dq/dk/dv/delta_ws");
   YMP_CHECK_ARG(b->lddo % 8 == 0 && b->lddq % 8 == 0 && b->lddk % 8 == 0 && b->lddv % 8 == 0, "ymp_attn_bwd: grad row strides must be multiples of 8");
+  YMP_CHECK_ARG(!a->s_kv_dev, "ymp_attn_bwd: s_kv_dev is forward only");
   p.dout = (const __nv_bfloat16*)b->dout; p.dq = (__nv_bfloat16*)b->dq; p.dk = (__nv_bfloat16*)b->dk; p.dv = (__nv_bfloat16*)b->dv;
   p.delta = b->delta_ws;
   p.lddo = b->lddo; p.hsdo = b->do_head_stride;

@@ -32,6 +32,6 @@ int num_sms() {
 
 extern "C" {
 const char* ymp_last_error(void) { return ymp::g_err; }
-int ymp_abi_version(void) { return 2; }
+int ymp_abi_version(void) { return 3; }
 uint64_t ymp_launch_count(void) { return ymp::g_launches.load(std::memory_order_relaxed); }
 }

@@ -176,12 +176,26 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const uint3
       if (p.aux_out) {
         float d[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_erf_both(v[i], d[i]);
+        for (int j = 0; j < 4; ++j) {
+          float x8[8], v8[8], d8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x8[e] = v[8 * j + e];
+          gelu_erf_both_x8(x8, v8, d8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { v[8 * j + e] = v8[e]; d[8 * j + e] = d8[e]; }
+        }
         store16(p.aux_out + off, p.v32_aux, d);
         store16(p.aux_out + off + 16, p.v32_aux, d + 16);
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        for (int j = 0; j < 4; ++j) {
+          float x8[8], v8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x8[e] = v[8 * j + e];
+          gelu_erf_x8(x8, v8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[8 * j + e] = v8[e];
+        }
       }
     } else if (p.act == YMP_ACT_GELU_TANH) {
       if (p.aux_out) {
@@ -366,7 +380,14 @@ __device__ __forceinline__ void epilogue_post(const GemmKParams& p, uint32_t (&r
     }
   } else if (p.act == YMP_ACT_GELU_ERF) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(gelu_erf(__uint_as_float(r[i])));
+    for (int j = 0; j < 4; ++j) {
+      float x8[8], v8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x8[e] = __uint_as_float(r[8 * j + e]);
+      gelu_erf_x8(x8, v8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[8 * j + e] = __float_as_uint(v8[e]);
+    }
   } else if (p.act == YMP_ACT_GELU_TANH) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(gelu_tanh(__uint_as_float(r[i])));
@@ -398,12 +419,18 @@ __device__ __forceinline__ void epilogue_post(const GemmKParams& p, uint32_t (&r
 __device__ __forceinline__ void epilogue_act8(const GemmKParams& p, const uint32_t (&r)[32], const EpiPrefetch& pf, int j,
                                               uint32_t (&vo)[4], uint32_t (&ao)[4]) {
   float v[8], d[8];
+  if (p.act == YMP_ACT_GELU_ERF) {
+    float x8[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const float x = __uint_as_float(r[8 * j + e]);
-    if (p.act == YMP_ACT_GELU_ERF) v[e] = gelu_erf_both(x, d[e]);
-    else if (p.act == YMP_ACT_GELU_TANH) v[e] = gelu_tanh_both(x, d[e]);
-    else { v[e] = x; d[e] = x; }
+    for (int e = 0; e < 8; ++e) x8[e] = __uint_as_float(r[8 * j + e]);
+    gelu_erf_both_x8(x8, v, d);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float x = __uint_as_float(r[8 * j + e]);
+      if (p.act == YMP_ACT_GELU_TANH) v[e] = gelu_tanh_both(x, d[e]);
+      else { v[e] = x; d[e] = x; }
+    }
   }
   if (p.residual) {
 #pragma unroll

@@ -233,6 +233,12 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
 }
 
 // ---------------------------------------------------------------- small math helpers
+// streaming 128-bit load that does not allocate in L1 (weights read exactly once)
+__device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
+  uint4 v;
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -281,6 +287,84 @@ __device__ __forceinline__ float norm_cdf_pdf(float x, float& pdf) {
 __device__ __forceinline__ float gelu_erf(float x) {
   float e;
   return x * norm_cdf_pdf(x, e);
+}
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two IEEE operations, bit-identical to the
+// scalar instructions).  The GEMM epilogues are issue-slot / dependency-latency bound on the activation polynomials.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 splat2(float c) { return make_float2(c, c); }
+
+// Phi and the normal pdf of EIGHT values in lockstep (four packed pairs): the same arithmetic as norm_cdf_pdf, element
+// by element, written coefficient-major so that the four dependency chains interleave.
+__device__ __forceinline__ void norm_cdf_pdf_x8(const float (&x)[8], float2 (&cdf)[4], float2 (&pdf)[4]) {
+  float2 xc[4], u[4], q[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    xc[i] = make_float2(fminf(fmaxf(x[2 * i], -4.5f), 4.5f), fminf(fmaxf(x[2 * i + 1], -4.5f), 4.5f));
+    u[i] = fmul2(xc[i], xc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = ffma2(u[i], splat2(-0.72134752044f), splat2(-1.32574806474f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pdf[i].x) : "f"(a.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pdf[i].y) : "f"(a.y));
+    q[i] = ffma2(splat2(-1.6543631001e-12f), u[i], splat2(1.9532824653e-10f));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = ffma2(q[i], u[i], splat2(-1.0287317553e-08f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = ffma2(q[i], u[i], splat2(3.2170341066e-07f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = ffma2(q[i], u[i], splat2(-6.7323919166e-06f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = ffma2(q[i], u[i], splat2(1.0108823657e-04f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = ffma2(q[i], u[i], splat2(-1.1397043329e-03f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = ffma2(q[i], u[i], splat2(9.8841767687e-03f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = ffma2(q[i], u[i], splat2(-6.6411978624e-02f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = ffma2(q[i], u[i], splat2(3.9892175804e-01f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) cdf[i] = ffma2(xc[i], q[i], splat2(0.5f));
+}
+// v = gelu_erf(x), d = gelu_erf'(x) for eight values (bit-identical to gelu_erf_both element by element)
+__device__ __forceinline__ void gelu_erf_both_x8(const float (&x)[8], float (&v)[8], float (&d)[8]) {
+  float2 cdf[4], pdf[4];
+  norm_cdf_pdf_x8(x, cdf, pdf);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 xv = make_float2(x[2 * i], x[2 * i + 1]);
+    const float2 dd = ffma2(xv, pdf[i], cdf[i]), vv = fmul2(xv, cdf[i]);
+    d[2 * i] = dd.x; d[2 * i + 1] = dd.y; v[2 * i] = vv.x; v[2 * i + 1] = vv.y;
+  }
+}
+__device__ __forceinline__ void gelu_erf_x8(const float (&x)[8], float (&v)[8]) {
+  float2 cdf[4], pdf[4];
+  norm_cdf_pdf_x8(x, cdf, pdf);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 vv = fmul2(make_float2(x[2 * i], x[2 * i + 1]), cdf[i]);
+    v[2 * i] = vv.x; v[2 * i + 1] = vv.y;
+  }
 }
 // GELU and its derivative together (the derivative is what backward needs; it is stored in bf16 by the
 // forward epilogue so that the backward epilogue is a plain multiply)

@@ -549,17 +549,39 @@ class DistributedGPT3(nn.Module):
             raise ValueError("no labels and no inference_params: call sample()/beam_search()/generate()")
         ip = self.inference_params
         keys, params = self._param_list()
-        W = {k: YF.as_bf16(p) for k, p in zip(keys, params)}
         B, n, H = input_embeds.shape
         if ip.cache is None:
-            ip.cache = engine.KVCache(self.config.engine_cfg(), ip.max_batch_size, ip.max_sequence_len, input_embeds.device)
+            # one cache (and one captured token step) per (batch, length) is kept on the model and reused by later
+            # sample() / beam_search() calls: caption evaluation decodes thousands of clips with the same shape
+            key = (ip.max_batch_size, ip.max_sequence_len, str(input_embeds.device))
+            pool = self.__dict__.setdefault("_decode_pool", {})
+            if key not in pool:
+                pool.clear()   # keep one shape resident (a 1.3B cache at beam 5 x 400 positions is 0.6 GB)
+                pool[key] = engine.KVCache(self.config.engine_cfg(), ip.max_batch_size, ip.max_sequence_len, input_embeds.device)
+            ip.cache = pool[key]
+            ip.cache.reset()
             ip.key_value_memory_dict = {i + 1: t for i, t in enumerate(ip.cache.qkv)}
         off = ip.sequence_len_offset
         assert off == ip.cache.len and B == ip.cache.B
-        pos = W[engine.GPT + "embedding.position_embeddings.weight"]
-        x = (input_embeds.float() + pos[off:off + n][None].float()).reshape(B * n, H).contiguous()
-        hid = engine.gpt_decode(W, x, ip.cache, n)
-        logits = ops.gemm(hid, W[engine.GPT + "embedding.word_embeddings.weight"]).float()
+        if n == 1 and off > 0 and B <= ops.SKINNY_MAX_ROWS:
+            # single-token step: skinny GEMMs + device-side cache length, replayed as one CUDA graph
+            sig = (params[0].data_ptr(), params[-1].data_ptr(), sum(p._version for p in params))
+            ts = ip.cache.token
+            if ts is None or ts.sig != sig:
+                # weights the graph may hold raw pointers to: bf16 parameters (used in place) and frozen fp32 ones
+                # (their bf16 copy is cached until the version changes); trainable fp32 ones are re-cast every step
+                static = all(p.dtype == torch.bfloat16 or not p.requires_grad for p in params)
+                ts = ip.cache.token = engine.TokenStep(ip.cache, {k: YF.as_bf16(p) for k, p in zip(keys, params)},
+                                                       input_embeds.dtype, sig, static)
+            elif not ts.static:
+                ts.W = {k: YF.as_bf16(p) for k, p in zip(keys, params)}
+            hid, logits = ts.run(input_embeds.reshape(B, H))
+        else:
+            W = {k: YF.as_bf16(p) for k, p in zip(keys, params)}
+            pos = W[engine.GPT + "embedding.position_embeddings.weight"]
+            x = (input_embeds.float() + pos[off:off + n][None].float()).reshape(B * n, H).contiguous()
+            hid = engine.gpt_decode(W, x, ip.cache, n)
+            logits = ops.gemm(hid, W[engine.GPT + "embedding.word_embeddings.weight"]).float()
         ip.sequence_len_offset += n  # tokens.size(1) + query_embeds.size(1) of the reference
         return AttrDict(logits=logits.view(B, 1, -1), loss=None, losses=None, last_hidden_state=hid.view(B, 1, H))
 

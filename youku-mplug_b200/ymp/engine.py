@@ -636,18 +636,117 @@ class KVCache:
     """Incremental-decoding state (the reference's InferenceParams.key_value_memory_dict,
     models/modeling_distributed_gpt3.py:874-923).  One packed QKV buffer [B*max_len, 3H] per layer in the
     per-head [q|k|v] column layout of the QKV GEMM, so new rows are written by the GEMM epilogue itself
-    (row re-blocking) and the attention kernels read K/V of all cached positions in place."""
+    (row re-blocking) and the attention kernels read K/V of all cached positions in place.  All layers live in
+    one allocation that never moves (the captured single-token step holds its pointers), and the number of
+    cached positions is mirrored on the device (`len_idx`, `len1`) for that graph."""
 
     def __init__(self, gcfg, batch, max_len, device):
         g = GptDims(gcfg)
         self.g, self.B, self.max_len, self.len = g, batch, max_len, 0
-        self.qkv = [torch.zeros((batch * max_len, 3 * g.H), device=device, dtype=bf16) for _ in range(g.layers)]
+        self.store = torch.zeros((g.layers, batch * max_len, 3 * g.H), device=device, dtype=bf16)
+        self.qkv = [self.store[i] for i in range(g.layers)]
+        self.len_idx = torch.zeros(1, device=device, dtype=torch.int64)   # = len: position / cache row of the next token
+        self.len1 = torch.ones(1, device=device, dtype=torch.int32)       # = len + 1: keys the next token attends to
+        self.token = None   # TokenStep of the single-token steps (built by the caller that owns the weights)
+
+    def reset(self):
+        """Forget the cached positions (the rows are overwritten by the next prefill; stale rows past `len` are never read)."""
+        self.len = 0
+        self.len_idx.zero_()
+        self.len1.fill_(1)
+
+    def _set_len(self, n):
+        self.len = n
+        self.len_idx.fill_(n)
+        self.len1.fill_(n + 1)
 
     def reorder(self, idx):
-        """Row b of the cache becomes old row idx[b] (beam search, swap_key_value_dict :1460-1473)."""
+        """Row b of the cache becomes old row idx[b] (beam search, swap_key_value_dict :1460-1473), in place and for
+        the cached positions only: two launches for all layers."""
         assert idx.numel() == self.B
-        for i, t in enumerate(self.qkv):
-            self.qkv[i] = t.view(self.B, self.max_len, -1).index_select(0, idx).reshape(self.B * self.max_len, -1)
+        if self.len == 0:
+            return
+        v = self.store.view(self.g.layers, self.B, self.max_len, -1)[:, :, :self.len]
+        v.copy_(v.index_select(1, idx))
+
+
+class TokenStep:
+    """The single-token decoding step (n == 1, cache not empty) for at most ops.SKINNY_MAX_ROWS sequences, as ONE CUDA
+    graph: every linear is a skinny GEMM (one pass over its weights, csrc/gemv.cu), the new K/V row goes into the cache
+    at the device-side position `len_idx`, attention reads `len1` keys (ymp_attn_args.s_kv_dev), and the graph ends by
+    advancing both counters - so one captured graph serves every position of every generate() call that reuses this
+    cache.  ~8 kernels per layer; the latency floor is the weight stream (2.6 GB at 1.3B)."""
+
+    def __init__(self, cache, W, emb_dtype, sig=None, static=True):
+        """sig: anything that changes when the weight tensors behind W move; static: W may be captured (raw pointers)."""
+        g, dev = cache.g, cache.store.device
+        self.cache, self.W, self.sig, self.static = cache, W, sig, static
+        self.emb_in = torch.zeros((cache.B, g.H), device=dev, dtype=emb_dtype)
+        self.stage = torch.zeros((cache.B, 3 * g.H), device=dev, dtype=bf16)   # the new token's [q|k|v] row per sequence
+        self.graph = None
+        self.out = None
+        self.warm = False
+
+    def body(self):
+        """Enqueue the step on the current stream (eagerly or under capture): reads emb_in, returns (hid, logits)."""
+        c, W = self.cache, self.W
+        g, B, ML = c.g, c.B, c.max_len
+        H, hd = g.H, g.hd
+        pos = W[GPT + "embedding.position_embeddings.weight"]
+        x = self.emb_in.float() + pos.index_select(0, c.len_idx).float()
+        mkv = ops.dense_map(ML)
+        for i in range(g.layers):
+            pre = f"{GPT}encoder.layers.{i}."
+            ln1, _, _ = ops.layernorm_fwd(x, W[pre + "input_layernorm.weight"], W[pre + "input_layernorm.bias"], g.eps, stats=False)
+            st = self.stage
+            ops.gemm_skinny(ln1, W[pre + "self_attention.query_key_value.weight"], bias=W[pre + "self_attention.query_key_value.bias"], out=st)
+            buf = c.qkv[i]
+            buf.view(B, ML, 3 * H).index_copy_(1, c.len_idx, st.view(B, 1, 3 * H))
+            att = torch.empty((B, H), device=x.device, dtype=bf16)
+            q = TView(st, 0, 3 * hd, ops.dense_map(1))
+            k, v = TView(buf, hd, 3 * hd, mkv), TView(buf, 2 * hd, 3 * hd, mkv)
+            ops.attn_fwd(q, k, v, TView(att, 0, hd, ops.dense_map(1)), n_seq=B, n_heads=g.heads, head_dim=hd, s_q=1, s_kv=ML,
+                         causal=False, scale=g.scale, s_kv_dev=c.len1)
+            x1 = ops.gemm_skinny(att, W[pre + "self_attention.dense.weight"], bias=W[pre + "self_attention.dense.bias"], residual=x,
+                                 out_dtype=torch.float32)
+            ln2, _, _ = ops.layernorm_fwd(x1, W[pre + "post_attention_layernorm.weight"], W[pre + "post_attention_layernorm.bias"],
+                                          g.eps, stats=False)
+            h = ops.gemm_skinny(ln2, W[pre + "mlp.dense_h_to_4h.weight"], bias=W[pre + "mlp.dense_h_to_4h.bias"], act=ACT_GELU_TANH)
+            x = ops.gemm_skinny(h, W[pre + "mlp.dense_4h_to_h.weight"], bias=W[pre + "mlp.dense_4h_to_h.bias"], residual=x1,
+                                out_dtype=torch.float32)
+        hid, _, _ = ops.layernorm_fwd(x, W[GPT + "encoder.final_layernorm.weight"], W[GPT + "encoder.final_layernorm.bias"], g.eps,
+                                      stats=False)
+        logits = ops.gemm_skinny(hid, W[GPT + "embedding.word_embeddings.weight"], out_dtype=torch.float32)
+        c.len_idx += 1
+        c.len1 += 1
+        return hid, logits
+
+    def run(self, emb):
+        c = self.cache
+        use_graph = self.static and decode_graph_enabled()
+        if c.len + 1 > c.max_len:
+            raise ValueError(f"KV cache overflow: {c.len} + 1 > {c.max_len}")
+        self.emb_in.copy_(emb)
+        if not use_graph or not self.warm:
+            # the first step runs eagerly: it is also the warm-up the capture needs (lazy kernel attributes)
+            hid, logits = self.body()
+            self.warm = True
+        else:
+            if self.graph is None:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self.out = self.body()
+                self.graph = graph
+            self.graph.replay()
+            hid, logits = self.out[0].clone(), self.out[1].clone()
+        c.len += 1
+        return hid, logits
+
+
+def decode_graph_enabled():
+    import os
+    return os.environ.get("YMP_DECODE_GRAPH", "1") != "0"
 
 
 def gpt_decode(W, x, cache, n):
@@ -682,7 +781,7 @@ def gpt_decode(W, x, cache, n):
         h = ops.gemm(ln2, W[pre + "mlp.dense_h_to_4h.weight"], bias=W[pre + "mlp.dense_h_to_4h.bias"], act=ACT_GELU_TANH)
         x = ops.gemm(h, W[pre + "mlp.dense_4h_to_h.weight"], bias=W[pre + "mlp.dense_4h_to_h.bias"], residual=x1,
                      out_dtype=torch.float32)
-    cache.len = off + n
+    cache._set_len(off + n)
     last = torch.arange(B, device=x.device, dtype=torch.int32) * n + (n - 1)
     hid, _, _ = ops.layernorm_fwd(x, W[GPT + "encoder.final_layernorm.weight"], W[GPT + "encoder.final_layernorm.bias"], g.eps,
                                   in_rows=last, stats=False)

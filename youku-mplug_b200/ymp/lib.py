@@ -84,8 +84,14 @@ class AttnArgs(C.Structure):
         ("map_q", SeqMap), ("map_kv", SeqMap), ("map_o", SeqMap),
         ("n_seq", c_i32), ("n_heads", c_i32), ("head_dim", c_i32), ("s_q", c_i32), ("s_kv", c_i32),
         ("mask", c_i32), ("mask_block", c_i32), ("total_rows", C.c_int64), ("scale", C.c_float),
-        ("drop", DropoutSpec),
+        ("drop", DropoutSpec), ("s_kv_dev", c_vp),
     ]
+
+
+class GemmSkinnyArgs(C.Structure):
+    _fields_ = [("x", c_vp), ("w", c_vp), ("bias", c_vp), ("residual", c_vp), ("y", c_vp),
+                ("M", c_i32), ("N", c_i32), ("K", c_i32), ("ldx", c_i32), ("ldw", c_i32), ("ldr", c_i32), ("ldy", c_i32),
+                ("act", c_i32), ("residual_dtype", c_i32), ("out_dtype", c_i32)]
 
 
 class AttnBwdArgs(C.Structure):
@@ -154,6 +160,7 @@ def _declare(name, argstruct):
 
 
 _gemm = _declare("ymp_gemm", GemmArgs)
+_gemm_skinny = _declare("ymp_gemm_skinny", GemmSkinnyArgs)
 _ln_fwd = _declare("ymp_layernorm_fwd", LayerNormArgs)
 _ln_bwd = _declare("ymp_layernorm_bwd", LayerNormBwdArgs)
 _attn_fwd = _declare("ymp_attn_fwd", AttnArgs)

@@ -114,6 +114,32 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, 
     return out
 
 
+SKINNY_MAX_ROWS = 8
+
+
+def gemm_skinny(x, w, *, bias=None, residual=None, act=ACT_NONE, out=None, out_dtype=bf16):
+    """y[M, N] = act(x[M, K] @ w[N, K]^T + bias) + residual for M <= 8 rows (single-token decoding): one pass over
+    the weights on the HBM-bound kernel of csrc/gemv.cu instead of a mostly empty 128-row tensor-core tile."""
+    _chk2d(x, "x"); _chk2d(w, "w")
+    assert x.dtype == bf16 and w.dtype == bf16 and x.shape[1] == w.shape[1] and x.shape[0] <= SKINNY_MAX_ROWS
+    M, K, N = x.shape[0], x.shape[1], w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=out_dtype)
+    _chk2d(out, "out")
+    assert out.shape == (M, N)
+    a = L.GemmSkinnyArgs()
+    a.x, a.w, a.bias, a.residual, a.y = x.data_ptr(), w.data_ptr(), L.ptr(bias), L.ptr(residual), out.data_ptr()
+    a.M, a.N, a.K, a.ldx, a.ldw, a.ldy = M, N, K, x.stride(0), w.stride(0), out.stride(0)
+    if residual is not None:
+        assert residual.dtype in (bf16, torch.float32) and residual.stride(1) == 1 and residual.shape == (M, N)
+        a.ldr = residual.stride(0)
+        a.residual_dtype = DT_F32 if residual.dtype == torch.float32 else DT_BF16
+    a.act = act
+    a.out_dtype = DT_F32 if out.dtype == torch.float32 else DT_BF16
+    L.call(L._gemm_skinny, a, "ymp_gemm_skinny")
+    return out
+
+
 # ---------------------------------------------------------------------------------- LayerNorm
 def layernorm_fwd(x, gamma, beta, eps, out=None, in_rows=None, rows=None, stats=True, out_dtype=bf16):
     """y = LN(x) row-wise (fp32 statistics); x and y may each be bf16 or fp32.  Returns (y, mean, rstd)."""
@@ -193,7 +219,8 @@ class TView:
         return self.t.stride(0)
 
 
-def _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, mask_block=0, total_rows=0, drop=None):
+def _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, mask_block=0, total_rows=0, drop=None,
+               s_kv_dev=None):
     a = L.AttnArgs()
     a.q, a.k, a.v, a.o, a.lse = q.p, k.p, v.p, o.p, L.ptr(lse)
     a.ldq, a.ldk, a.ldv, a.ldo = q.ld, k.ld, v.ld, o.ld
@@ -203,15 +230,19 @@ def _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, sca
     # `causal` may be a bool or one of MASK_NONE / MASK_CAUSAL / MASK_BLOCK
     a.mask, a.mask_block, a.total_rows, a.scale = int(causal), mask_block, total_rows, scale
     _set_drop(a.drop, drop)
+    if s_kv_dev is not None:
+        assert s_kv_dev.dtype == torch.int32 and s_kv_dev.is_cuda and s_kv_dev.numel() == 1
+        a.s_kv_dev = s_kv_dev.data_ptr()
     return a
 
 
 def attn_fwd(q, k, v, o, *, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, lse=None, mask_block=0,
-             total_rows=0, drop=None):
-    """q,k,v,o: TView.  Returns lse [n_seq, n_heads, s_q] fp32."""
+             total_rows=0, drop=None, s_kv_dev=None):
+    """q,k,v,o: TView.  Returns lse [n_seq, n_heads, s_q] fp32.  s_kv_dev: int32 device scalar, only the first
+    min(s_kv, s_kv_dev) keys exist (the captured decoding step)."""
     if lse is None:
         lse = torch.empty((n_seq, n_heads, s_q), device=q.t.device, dtype=torch.float32)
-    a = _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, mask_block, total_rows, drop)
+    a = _attn_args(q, k, v, o, lse, n_seq, n_heads, head_dim, s_q, s_kv, causal, scale, mask_block, total_rows, drop, s_kv_dev)
     L.call(L._attn_fwd, a, "ymp_attn_fwd")
     return lse
 
