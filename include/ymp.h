@@ -35,6 +35,10 @@ const char* ymp_last_error(void);
 int ymp_abi_version(void);
 /* Number of kernel launches this process has enqueued through the library (for gpu_launches). */
 uint64_t ymp_launch_count(void);
+/* Programmatic dependent launch for the calling thread's next launches of ymp_gemm_skinny, ymp_layernorm_fwd and the
+ * mma.sync ymp_attn_fwd (the single-token decoding step): each of those kernels may then start while its predecessor in
+ * the stream drains (it waits on the device before reading the predecessor's output).  Returns the previous setting. */
+int ymp_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------
  * Dropout of the GPT-3 decoder (the reference keeps the frozen decoder in train() mode, so
@@ -138,6 +142,11 @@ typedef struct ymp_gemm_skinny_args {
   void* y;               /* bf16 / fp32 [M, N] (out_dtype), row stride ldy */
   int32_t M, N, K, ldx, ldw, ldr, ldy;
   int32_t act, residual_dtype, out_dtype;
+  /* optional second copy of the bf16 result at a row offset read on the device: y2[m * ldy2 + *y2_off_dev * y2_off_stride + n]
+   * (the new token's K/V row written straight into the KV cache at the device-side cache length) */
+  void* y2;
+  const int64_t* y2_off_dev;
+  int64_t ldy2, y2_off_stride;
 } ymp_gemm_skinny_args;
 int ymp_gemm_skinny(const ymp_gemm_skinny_args* a, void* stream);
 

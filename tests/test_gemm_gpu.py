@@ -189,7 +189,8 @@ def test_gemm_skinny_decode_shapes(cuda, M, N, K):
     _close(ops.gemm_skinny(x, w, bias=bias, residual=res32, out_dtype=torch.float32), pre + bias.float() + res32, tol=1e-4)
     _close(ops.gemm_skinny(x, w, bias=bias, residual=resb), pre + bias.float() + resb.float())
     # against the tensor-core GEMM on the same inputs (fp32 accumulation on both sides, different summation order)
-    _close(ops.gemm_skinny(x, w, bias=bias, out_dtype=torch.float32), ops.gemm(x, w, bias=bias, out_dtype=torch.float32).float(), tol=1e-4)
+    if N % 8 == 0:
+        _close(ops.gemm_skinny(x, w, bias=bias, out_dtype=torch.float32), ops.gemm(x, w, bias=bias, out_dtype=torch.float32).float(), tol=1e-4)
     # strided rows: x and y as column slices of wider buffers
     xw = torch.randn(M, K + 64, device=cuda).bfloat16()
     yw = torch.zeros(M, N + 8, device=cuda, dtype=torch.bfloat16)

@@ -39,15 +39,19 @@ def run(n_steps):
 
 
 wbytes = sum(p.numel() for p in dec.parameters()) * 2
-for mode in ("0", "1"):
+MODES = os.environ.get("DECODE_PROBE_MODES", "0,1").split(",")
+STEPS = int(os.environ.get("DECODE_PROBE_STEPS", "32"))
+for mode in MODES:
     os.environ["YMP_DECODE_GRAPH"] = mode
     dec.__dict__.pop("_decode_pool", None)
     run(4)
-    pre, step = run(32)
+    pre, step = run(STEPS)
     print("DECODE " + json.dumps(dict(graph=int(mode), beam=beam, prefill_rows=beam * (Q + P), prefill_ms=round(pre, 3),
                                       step_ms=round(step, 3), weight_gb=round(wbytes / 1e9, 2),
                                       hbm_floor_ms=round(wbytes / 6.4e12 * 1e3, 3))))
 
+if os.environ.get("DECODE_PROBE_SKINNY", "1") == "0":
+    sys.exit(0)
 # the skinny GEMM alone at the decode shapes, cycling through enough weight copies to defeat the 126 MB L2
 from ymp import ops  # noqa: E402
 for name, N, K, kw in (("qkv", 6144, 2048, {}), ("dense", 2048, 2048, dict(res=True)), ("fc1", 8192, 2048, dict(act=2)),

@@ -179,6 +179,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 64, h = blockIdx.y, s = blockIdx.z;
   const int g = lane >> 2, t4 = lane & 3;
+  griddep_launch();   // (programmatic dependent launch in the decoding step; no-ops for an ordinary launch)
+  griddep_wait();
   int sq, skv;
   eff_len(p, s, sq, skv);
   if (q0 >= sq) return;
@@ -703,7 +705,7 @@ static int launch_fwd(const AttnKParams& p, cudaStream_t st) {
   static bool set = false;
   if (!set) { YMP_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
   dim3 grid((p.s_q + 63) / 64, p.n_heads, p.n_seq);
-  attn_fwd_kernel<D><<<grid, 128, smem, st>>>(p);
+  launch_k(attn_fwd_kernel<D>, grid, dim3(128), smem, st, p);
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }

@@ -6,6 +6,7 @@ namespace ymp {
 
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+thread_local int g_pdl = 0;
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -34,4 +35,5 @@ extern "C" {
 const char* ymp_last_error(void) { return ymp::g_err; }
 int ymp_abi_version(void) { return 3; }
 uint64_t ymp_launch_count(void) { return ymp::g_launches.load(std::memory_order_relaxed); }
+int ymp_set_pdl(int on) { const int prev = ymp::g_pdl; ymp::g_pdl = on ? 1 : 0; return prev; }
 }

@@ -1,21 +1,27 @@
 // Skinny GEMM for single-token decoding: y[M, N] = epilogue(x[M, K] . w[N, K]^T) with M <= 8 rows
 // (beam width / decode batch).  Replaces the GPT-3 layer's linears at the KV-cache step of
 // models/modeling_distributed_gpt3.py:868-938,580-595,1348-1350.  With a handful of rows the work is one pass over
-// the weight matrix: HBM-bound, so no tensor cores - a 128-row tcgen05 tile would occupy N/128 CTAs (16 for N = 2048)
-// and stream the weights at a fraction of the memory bandwidth.
-//   * a warp owns FOUR output columns and one K slice; its lanes stride the slice with 128-bit loads (four independent
-//     weight streams per lane per iteration), x is re-read through L1/L2 (M*K*2 bytes, shared by every CTA);
-//   * the 8 warps of a CTA are ksplit K-slices x (8 / ksplit) column groups: the host picks ksplit so that even the
-//     N = hidden GEMMs put >= 3 CTAs on every SM (enough loads in flight to cover the HBM latency);
-//   * partial sums are combined with warp shuffles (+ shared memory across K slices) and lane (m, col) applies
-//       v = acc + bias[n] ; v = gelu(v) (optional) ; v += residual[m, n] (bf16 or fp32) ; store bf16 or fp32.
+// the weight matrix: HBM-bound.  A 128-row tcgen05 tile would occupy N/128 CTAs (16 for N = 2048) and stream the
+// weights at a fraction of the memory bandwidth; a CUDA-core dot product needs ~2.5 issue slots per weight byte-pair
+// (bf16 -> fp32 converts + FMAs for every row) and is issue-bound at a quarter of the bandwidth.  So:
+//   * a warp owns 8 output columns and one K slice and feeds mma.sync.m16n8k16 (bf16, fp32 accumulate) STRAIGHT FROM
+//     GLOBAL MEMORY: lane (g, t) loads 16 bytes (8 consecutive k) of weight row n0+g and of activation row g.  The
+//     tensor-core fragment wants k = {2t, 2t+1, 2t+8, 2t+9} per lane - but a dot product does not care in which order
+//     k is summed as long as both operands use the same order, so the 8 consecutive elements are simply declared to be
+//     those positions of two k-steps (a k permutation inside each 32-element block).  No shared memory, no converts:
+//     two loads and two MMAs per 16 weight bytes per lane.  x is the A operand (rows >= M are zero registers);
+//   * the 8 warps of a CTA are `ksplit` K-slices x (8 / ksplit) column tiles; every lane keeps UNROLL k-blocks
+//     (UNROLL x 16 bytes of weights) in flight, ~8 CTAs resident per SM;
+//   * partial sums meet in shared memory; lane (g, t) of the slice-0 warp owns (row g, columns n0+2t, n0+2t+1) and applies
+//       v = acc + bias[n] ; v = gelu(v) (optional) ; v += residual[m, n] (bf16 or fp32) ; store bf16 or fp32
+//     (+ an optional second bf16 copy at a device-side row offset: the KV-cache row of the new token).
 // Algorithmic bytes per call: N*K*2 (weights) + M*(K + N)*2..4.
 #include "common.h"
 #include "ptx.cuh"
 
 namespace ymp {
 
-constexpr int SK_MAXM = 8, SK_COLS = 4, SK_WARPS = 8;
+constexpr int SK_MAXM = 8, SK_TILE_N = 8, SK_WARPS = 8;
 
 struct SkinnyParams {
   const __nv_bfloat16* x;
@@ -23,76 +29,99 @@ struct SkinnyParams {
   const __nv_bfloat16* bias;
   const void* residual;
   void* y;
+  __nv_bfloat16* y2;
+  const long long* y2_off;
+  long long ldy2, y2_stride;
   int M, N, K, ldx, ldw, ldr, ldy;
   int act, res_f32, out_f32, ksplit;
 };
 
-__device__ __forceinline__ void fma8(float& acc, const uint4& x, const uint4& w) {
-  acc = fmaf(bf16_lo(x.x), bf16_lo(w.x), acc); acc = fmaf(bf16_hi(x.x), bf16_hi(w.x), acc);
-  acc = fmaf(bf16_lo(x.y), bf16_lo(w.y), acc); acc = fmaf(bf16_hi(x.y), bf16_hi(w.y), acc);
-  acc = fmaf(bf16_lo(x.z), bf16_lo(w.z), acc); acc = fmaf(bf16_hi(x.z), bf16_hi(w.z), acc);
-  acc = fmaf(bf16_lo(x.w), bf16_lo(w.w), acc); acc = fmaf(bf16_hi(x.w), bf16_hi(w.w), acc);
+__device__ __forceinline__ void mma16816_bf16(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  // rows 8..15 of the A operand (a1, a3) are zero: only M <= 8 activation rows exist
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%5}, {%7,%8}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(0u), "r"(a2), "r"(b0), "r"(b1));
 }
 
+template <int SK_UNROLL>
 __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const SkinnyParams p) {
-  __shared__ float part[SK_WARPS][SK_MAXM * SK_COLS];
+  __shared__ float part[SK_WARPS][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ks = p.ksplit, kpart = warp % ks, cgrp = warp / ks, groups = SK_WARPS / ks;
-  const int n0 = (blockIdx.x * groups + cgrp) * SK_COLS;
+  const int g = lane >> 2, t = lane & 3;
+  const int ks = p.ksplit, kpart = warp % ks, tile = blockIdx.x * (SK_WARPS / ks) + warp / ks;
+  const int n0 = tile * SK_TILE_N;
   const bool live = n0 < p.N;
-  float acc[SK_MAXM][SK_COLS];
-#pragma unroll
-  for (int m = 0; m < SK_MAXM; ++m)
-#pragma unroll
-    for (int c = 0; c < SK_COLS; ++c) acc[m][c] = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  griddep_launch();
   if (live) {
-    const uint4* wr[SK_COLS];
+    // 16-byte chunks of the K dimension: chunk c = elements [8c, 8c+8); a k-block is 4 chunks (one per t)
+    const int nchunk = p.K >> 3, nblk = (nchunk + 3) >> 2;
+    const int b_lo = (int)((long)nblk * kpart / ks), b_hi = (int)((long)nblk * (kpart + 1) / ks);
+    const uint4* wr = reinterpret_cast<const uint4*>(p.w + (size_t)min(n0 + g, p.N - 1) * p.ldw);
+    const uint4* xr = reinterpret_cast<const uint4*>(p.x + (size_t)min(g, p.M - 1) * p.ldx);
+    const bool xrow = g < p.M;
+    // two register batches of SK_UNROLL k-blocks: the next batch is requested before the current one is consumed, so a
+    // warp always has SK_UNROLL..2*SK_UNROLL x 16 bytes of weights in flight
+    uint4 wv[SK_UNROLL], xv[SK_UNROLL];
+    auto fetch_w = [&](int b, uint4 (&wd)[SK_UNROLL]) {
 #pragma unroll
-    for (int c = 0; c < SK_COLS; ++c) wr[c] = reinterpret_cast<const uint4*>(p.w + (size_t)min(n0 + c, p.N - 1) * p.ldw);
-    const int nvec = p.K >> 3;
-    const int v_lo = (int)((long)nvec * kpart / ks), v_hi = (int)((long)nvec * (kpart + 1) / ks);
-#pragma unroll 2
-    for (int v = v_lo + lane; v < v_hi; v += 32) {
-      uint4 wv[SK_COLS];
-#pragma unroll
-      for (int c = 0; c < SK_COLS; ++c) wv[c] = ld_nc_v4(wr[c] + v);
-#pragma unroll
-      for (int m = 0; m < SK_MAXM; ++m) {
-        if (m < p.M) {
-          const uint4 xv = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)m * p.ldx) + v);
-#pragma unroll
-          for (int c = 0; c < SK_COLS; ++c) fma8(acc[m][c], xv, wv[c]);
-        }
+      for (int u = 0; u < SK_UNROLL; ++u) {
+        const int c = (b + u) * 4 + t;
+        wd[u] = ((b + u) < b_hi && c < nchunk) ? ld_nc_v4(wr + c) : make_uint4(0, 0, 0, 0);
       }
-    }
-  }
-  // lane (m * 4 + c) ends up with this warp's sum of (row m, column n0 + c)
-  float mine = 0.f;
+    };
+    auto fetch_x = [&](int b, uint4 (&xd)[SK_UNROLL]) {
 #pragma unroll
-  for (int m = 0; m < SK_MAXM; ++m) {
+      for (int u = 0; u < SK_UNROLL; ++u) {
+        const int c = (b + u) * 4 + t;
+        xd[u] = ((b + u) < b_hi && c < nchunk && xrow) ? __ldg(xr + c) : make_uint4(0, 0, 0, 0);
+      }
+    };
+    // the weights do not depend on the previous kernel of the stream: their first batch is already in flight while that
+    // kernel drains (programmatic dependent launch); the activations are read only after it has completed
+    fetch_w(b_lo, wv);
+    griddep_wait();
+    fetch_x(b_lo, xv);
+    for (int b = b_lo; b < b_hi; b += SK_UNROLL) {
+      uint4 wn[SK_UNROLL], xn[SK_UNROLL];
+      fetch_w(b + SK_UNROLL, wn);     // (all-zero past the end of the slice)
+      fetch_x(b + SK_UNROLL, xn);
 #pragma unroll
-    for (int c = 0; c < SK_COLS; ++c) {
-      const float s = warp_sum(acc[m][c]);
-      if (lane == m * SK_COLS + c) mine = s;
+      for (int u = 0; u < SK_UNROLL; ++u) {
+        mma16816_bf16(acc, xv[u].x, xv[u].y, wv[u].x, wv[u].y);
+        mma16816_bf16(acc, xv[u].z, xv[u].w, wv[u].z, wv[u].w);
+      }
+#pragma unroll
+      for (int u = 0; u < SK_UNROLL; ++u) { wv[u] = wn[u]; xv[u] = xn[u]; }
     }
+  } else {
+    griddep_wait();
   }
+  // acc[0], acc[1] = (row g, columns n0 + 2t, n0 + 2t + 1) summed over this warp's K slice
   if (ks > 1) {
-    part[warp][lane] = mine;
+    part[warp][2 * lane] = acc[0];
+    part[warp][2 * lane + 1] = acc[1];
     __syncthreads();
     if (kpart == 0)
-      for (int j = 1; j < ks; ++j) mine += part[warp + j][lane];
+      for (int j = 1; j < ks; ++j) { acc[0] += part[warp + j][2 * lane]; acc[1] += part[warp + j][2 * lane + 1]; }
   }
-  const int m = lane >> 2, c = lane & 3, n = n0 + c;
-  if (live && kpart == 0 && m < p.M && n < p.N) {
-    float v = mine;
-    if (p.bias) v += __bfloat162float(p.bias[n]);
-    if (p.act == YMP_ACT_GELU_TANH) v = gelu_tanh(v);
-    else if (p.act == YMP_ACT_GELU_ERF) v = gelu_erf(v);
-    if (p.residual)
-      v += p.res_f32 ? reinterpret_cast<const float*>(p.residual)[(size_t)m * p.ldr + n]
-                     : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[(size_t)m * p.ldr + n]);
-    if (p.out_f32) reinterpret_cast<float*>(p.y)[(size_t)m * p.ldy + n] = v;
-    else reinterpret_cast<__nv_bfloat16*>(p.y)[(size_t)m * p.ldy + n] = __float2bfloat16(v);
+  if (live && kpart == 0 && g < p.M) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int n = n0 + 2 * t + e;
+      if (n >= p.N) break;
+      float v = acc[e];
+      if (p.bias) v += __bfloat162float(p.bias[n]);
+      if (p.act == YMP_ACT_GELU_TANH) v = gelu_tanh(v);
+      else if (p.act == YMP_ACT_GELU_ERF) v = gelu_erf(v);
+      if (p.residual)
+        v += p.res_f32 ? reinterpret_cast<const float*>(p.residual)[(size_t)g * p.ldr + n]
+                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[(size_t)g * p.ldr + n]);
+      if (p.out_f32) reinterpret_cast<float*>(p.y)[(size_t)g * p.ldy + n] = v;
+      else reinterpret_cast<__nv_bfloat16*>(p.y)[(size_t)g * p.ldy + n] = __float2bfloat16(v);
+      if (p.y2) p.y2[(long long)g * p.ldy2 + *p.y2_off * p.y2_stride + n] = __float2bfloat16(v);
+    }
   }
 }
 
@@ -108,17 +137,24 @@ extern "C" int ymp_gemm_skinny(const ymp_gemm_skinny_args* a, void* stream) {
   SkinnyParams p;
   p.x = (const __nv_bfloat16*)a->x; p.w = (const __nv_bfloat16*)a->w; p.bias = (const __nv_bfloat16*)a->bias;
   p.residual = a->residual; p.y = a->y;
+  YMP_CHECK_ARG(!a->y2 || (a->y2_off_dev && a->out_dtype == YMP_DT_BF16), "ymp_gemm_skinny: y2 needs y2_off_dev and a bf16 result");
+  p.y2 = (__nv_bfloat16*)a->y2; p.y2_off = (const long long*)a->y2_off_dev; p.ldy2 = a->ldy2; p.y2_stride = a->y2_off_stride;
   p.M = a->M; p.N = a->N; p.K = a->K; p.ldx = a->ldx; p.ldw = a->ldw; p.ldr = a->ldr; p.ldy = a->ldy;
   p.act = a->act; p.res_f32 = a->residual_dtype == YMP_DT_F32; p.out_f32 = a->out_dtype == YMP_DT_F32;
-  // K slices per CTA: the fewest that still give >= 3 CTAs per SM (each warp keeps >= 32 16-byte chunks of its slice)
+  // K slices per CTA (the warps of a CTA that share one 8-column tile): as many as leave >= 4 k-blocks of 32 per slice
   int ks = 1;
   static const int force = [] { const char* e = getenv("YMP_SKINNY_KSPLIT"); return e ? atoi(e) : 0; }();
-  while (ks < SK_WARPS && (a->N + (SK_WARPS / ks) * SK_COLS - 1) / ((SK_WARPS / ks) * SK_COLS) < 3 * num_sms() && a->K / (2 * ks) >= 256) ks *= 2;
+  const int ks_max = a->N <= 4096 ? 8 : 4;   // measured (tools/skinny_probe.py): wide outputs prefer fatter CTAs
+  while (ks < ks_max && a->K / (2 * ks) >= 128) ks *= 2;
   if (force == 1 || force == 2 || force == 4 || force == 8) ks = force;
   p.ksplit = ks;
-  const int cols_per_cta = (SK_WARPS / ks) * SK_COLS;
-  const int blocks = (a->N + cols_per_cta - 1) / cols_per_cta;
-  gemm_skinny_kernel<<<blocks, SK_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  const int tiles = (a->N + SK_TILE_N - 1) / SK_TILE_N, tiles_per_cta = SK_WARPS / ks;
+  const int blocks = (tiles + tiles_per_cta - 1) / tiles_per_cta;
+  static const int unroll = [] { const char* e = getenv("YMP_SKINNY_UNROLL"); return e ? atoi(e) : 4; }();
+  cudaStream_t st = (cudaStream_t)stream;
+  if (unroll == 8) launch_k(gemm_skinny_kernel<8>, dim3(blocks), dim3(SK_WARPS * 32), 0, st, p);
+  else if (unroll == 2) launch_k(gemm_skinny_kernel<2>, dim3(blocks), dim3(SK_WARPS * 32), 0, st, p);
+  else launch_k(gemm_skinny_kernel<4>, dim3(blocks), dim3(SK_WARPS * 32), 0, st, p);
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }

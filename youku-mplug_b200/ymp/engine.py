@@ -21,6 +21,7 @@ import math
 
 import torch
 
+from . import lib as L
 from . import ops
 from .ops import ACT_GELU_ERF, ACT_GELU_TANH, TView, bf16
 
@@ -688,7 +689,18 @@ class TokenStep:
         self.warm = False
 
     def body(self):
-        """Enqueue the step on the current stream (eagerly or under capture): reads emb_in, returns (hid, logits)."""
+        """Enqueue the step on the current stream (eagerly or under capture): reads emb_in, returns (hid, logits).
+        YMP_DECODE_PDL=1 chains the kernels by programmatic dependent launch (each may start - and the GEMMs already
+        stream their first weights - while the previous one drains).  Off by default: measured SLOWER inside the
+        captured graph on B200 (1.63 vs 1.47 ms per token at 1.3B / beam 5, profiles/r02l_pdl.log)."""
+        import os
+        prev = L.set_pdl(os.environ.get("YMP_DECODE_PDL", "0") == "1")
+        try:
+            return self._body()
+        finally:
+            L.set_pdl(prev)
+
+    def _body(self):
         c, W = self.cache, self.W
         g, B, ML = c.g, c.B, c.max_len
         H, hd = g.H, g.hd
@@ -699,9 +711,10 @@ class TokenStep:
             pre = f"{GPT}encoder.layers.{i}."
             ln1, _, _ = ops.layernorm_fwd(x, W[pre + "input_layernorm.weight"], W[pre + "input_layernorm.bias"], g.eps, stats=False)
             st = self.stage
-            ops.gemm_skinny(ln1, W[pre + "self_attention.query_key_value.weight"], bias=W[pre + "self_attention.query_key_value.bias"], out=st)
             buf = c.qkv[i]
-            buf.view(B, ML, 3 * H).index_copy_(1, c.len_idx, st.view(B, 1, 3 * H))
+            # [q|k|v] of the new token: into the staging rows (q for this step) and into cache row b*ML + len (k, v)
+            ops.gemm_skinny(ln1, W[pre + "self_attention.query_key_value.weight"], bias=W[pre + "self_attention.query_key_value.bias"],
+                            out=st, out2=buf, out2_row_stride=ML, out2_off=c.len_idx)
             att = torch.empty((B, H), device=x.device, dtype=bf16)
             q = TView(st, 0, 3 * hd, ops.dense_map(1))
             k, v = TView(buf, hd, 3 * hd, mkv), TView(buf, 2 * hd, 3 * hd, mkv)

@@ -91,7 +91,8 @@ class AttnArgs(C.Structure):
 class GemmSkinnyArgs(C.Structure):
     _fields_ = [("x", c_vp), ("w", c_vp), ("bias", c_vp), ("residual", c_vp), ("y", c_vp),
                 ("M", c_i32), ("N", c_i32), ("K", c_i32), ("ldx", c_i32), ("ldw", c_i32), ("ldr", c_i32), ("ldy", c_i32),
-                ("act", c_i32), ("residual_dtype", c_i32), ("out_dtype", c_i32)]
+                ("act", c_i32), ("residual_dtype", c_i32), ("out_dtype", c_i32),
+                ("y2", c_vp), ("y2_off_dev", c_vp), ("ldy2", C.c_int64), ("y2_off_stride", C.c_int64)]
 
 
 class AttnBwdArgs(C.Structure):
@@ -149,6 +150,8 @@ lib.ymp_last_error.restype = C.c_char_p
 lib.ymp_abi_version.restype = C.c_int
 lib.ymp_launch_count.restype = C.c_uint64
 lib.ymp_attn_last_path.restype = C.c_int
+lib.ymp_set_pdl.restype = C.c_int
+lib.ymp_set_pdl.argtypes = [C.c_int]
 ATTN_PATH_MMA_SYNC, ATTN_PATH_TCGEN05, ATTN_PATH_SMALL = 0, 1, 2
 
 
@@ -186,6 +189,12 @@ def check(rc, what):
 
 def launch_count():
     return int(lib.ymp_launch_count())
+
+
+def set_pdl(on):
+    """Programmatic dependent launch for this thread's next skinny-GEMM / LayerNorm / mma.sync attention launches
+    (the decoding step).  Returns the previous setting."""
+    return int(lib.ymp_set_pdl(int(bool(on))))
 
 
 def attn_last_path():

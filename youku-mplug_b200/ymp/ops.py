@@ -117,9 +117,12 @@ def gemm(a, b, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, 
 SKINNY_MAX_ROWS = 8
 
 
-def gemm_skinny(x, w, *, bias=None, residual=None, act=ACT_NONE, out=None, out_dtype=bf16):
+def gemm_skinny(x, w, *, bias=None, residual=None, act=ACT_NONE, out=None, out_dtype=bf16, out2=None, out2_row_stride=0,
+                out2_off=None):
     """y[M, N] = act(x[M, K] @ w[N, K]^T + bias) + residual for M <= 8 rows (single-token decoding): one pass over
-    the weights on the HBM-bound kernel of csrc/gemv.cu instead of a mostly empty 128-row tensor-core tile."""
+    the weights on the HBM-bound kernel of csrc/gemv.cu instead of a mostly empty 128-row tensor-core tile.
+    out2 [R, N] bf16 with out2_off (int64 device scalar): result row m is also written to out2 row
+    m * out2_row_stride + out2_off (the KV-cache row at the device-side cache length)."""
     _chk2d(x, "x"); _chk2d(w, "w")
     assert x.dtype == bf16 and w.dtype == bf16 and x.shape[1] == w.shape[1] and x.shape[0] <= SKINNY_MAX_ROWS
     M, K, N = x.shape[0], x.shape[1], w.shape[0]
@@ -136,6 +139,12 @@ def gemm_skinny(x, w, *, bias=None, residual=None, act=ACT_NONE, out=None, out_d
         a.residual_dtype = DT_F32 if residual.dtype == torch.float32 else DT_BF16
     a.act = act
     a.out_dtype = DT_F32 if out.dtype == torch.float32 else DT_BF16
+    if out2 is not None:
+        _chk2d(out2, "out2")
+        assert out2.dtype == bf16 and out2.shape[1] == N and out2_off.dtype == torch.int64 and out2_off.numel() == 1
+        assert out2.shape[0] >= (M - 1) * out2_row_stride + 1
+        a.y2, a.y2_off_dev = out2.data_ptr(), out2_off.data_ptr()
+        a.ldy2, a.y2_off_stride = out2_row_stride * out2.stride(0), out2.stride(0)
     L.call(L._gemm_skinny, a, "ymp_gemm_skinny")
     return out
 
