@@ -376,6 +376,7 @@ def run_ymp(args, rank, local_rank, world):
     e2e_val = B * world * args.steps / (ms_e2e * 1e-3)
     h2d = video_h.numel() * 4 + ids_h.numel() * 8 + att_h.numel() * 8
     if rank != 0:
+        _teardown(eng, world)
         return
     line = dict(metric=cfg["metric"], value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
@@ -416,7 +417,32 @@ def run_ymp(args, rank, local_rank, world):
         line["cpu_baseline"] = dict(value=val, unit="samples/s", cores=cores, kind="port", sample=sample)
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _teardown(eng, world)
+
+
+def _teardown(eng, world):
+    """Leave a multi-rank run without hanging: the captured step graphs hold NCCL kernels and the engine holds async
+    work handles, so they are released before the communicator on EVERY rank (a rank that simply returned used to
+    block in interpreter shutdown while its peer sat in destroy_process_group); a watchdog guarantees the exit."""
+    if world <= 1:
+        return
+    import gc
+    import threading
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    t = threading.Timer(30.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    torch.cuda.synchronize()
+    eng._graphs.clear()
+    eng._pending.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 def main():

@@ -147,6 +147,15 @@ typedef struct ymp_gemm_skinny_args {
   void* y2;
   const int64_t* y2_off_dev;
   int64_t ldy2, y2_off_stride;
+  /* optional fused LayerNorm of the complete fp32 result (the next sub-layer's input): the CTA that finishes last
+   * (ticket in *ln_counter, which must be 0 at launch and is reset to 0) writes ln_out[m, :] = LN(y[m, :]) in bf16 with
+   * exactly the arithmetic of ymp_layernorm_fwd - one kernel boundary less per sub-layer of the decoding step */
+  const void* ln_gamma;  /* bf16 [N] */
+  const void* ln_beta;   /* bf16 [N] */
+  void* ln_out;          /* bf16 [M, N], row stride ld_ln */
+  uint32_t* ln_counter;
+  int32_t ld_ln;
+  float ln_eps;
 } ymp_gemm_skinny_args;
 int ymp_gemm_skinny(const ymp_gemm_skinny_args* a, void* stream);
 
@@ -268,6 +277,7 @@ int ymp_attn_bwd(const ymp_attn_bwd_args* a, void* stream);
 #define YMP_ATTN_PATH_MMA_SYNC 0
 #define YMP_ATTN_PATH_TCGEN05 1
 #define YMP_ATTN_PATH_SMALL 2
+#define YMP_ATTN_PATH_DECODE 3  /* one query row per sequence: streaming kernel of the decoding step */
 int ymp_attn_last_path(void);
 
 /* ------------------------------------------------------------------------------------------

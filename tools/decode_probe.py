@@ -46,7 +46,25 @@ for mode in MODES:
     dec.__dict__.pop("_decode_pool", None)
     run(4)
     pre, step = run(STEPS)
-    print("DECODE " + json.dumps(dict(graph=int(mode), beam=beam, prefill_rows=beam * (Q + P), prefill_ms=round(pre, 3),
+    replay_ms = None
+    ts = dec.inference_params.cache.token
+    if mode == "1" and ts is not None and ts.graph is not None:
+        # the captured step alone (device time, no host work between replays; the cache keeps growing - stop before max_len)
+        n_rep = 8
+        dec.inference_params = M.InferenceParams(beam, Q + P + STEPS + 1)
+        with torch.no_grad():
+            out = dec(tokens=prompt, query_embeds=qf)
+            dec(tokens=out.logits[:, -1].argmax(-1, keepdim=True))
+            dec(tokens=out.logits[:, -1].argmax(-1, keepdim=True))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_rep):
+            ts.graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        replay_ms = round(e0.elapsed_time(e1) / n_rep, 3)
+    print("DECODE " + json.dumps(dict(graph=int(mode), graph_replay_only_ms=replay_ms, beam=beam, prefill_rows=beam * (Q + P), prefill_ms=round(pre, 3),
                                       step_ms=round(step, 3), weight_gb=round(wbytes / 1e9, 2),
                                       hbm_floor_ms=round(wbytes / 6.4e12 * 1e3, 3))))
 

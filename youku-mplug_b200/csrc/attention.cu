@@ -674,6 +674,121 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const AttnKParams p)
   }
 }
 
+// ------------------------------------------------------------------------------ single-query forward (decoding)
+// One query row per (sequence, head) over the KV cache: the step of sample() / beam_search()
+// (models/modeling_distributed_gpt3.py:874-938).  Pure streaming: every lane owns whole keys (its D-element K and V rows
+// arrive as D/8 independent 16-byte loads), keeps a private un-normalised output row in registers under a warp-uniform
+// running maximum, and the 128 private rows meet once at the end through shared memory.  Nothing waits on a tile:
+// one round trip to the cache per 128 keys instead of a load / mma.sync / softmax pipeline on a 64-row tile with a
+// single live row.  Algorithmic bytes: 2 * s_kv * D * 2 per (sequence, head).
+template <int D>
+__global__ void __launch_bounds__(128) attn_decode_kernel(const AttnKParams p) {
+  constexpr int CH = D / 8;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  float (*o_part)[D + 1] = reinterpret_cast<float (*)[D + 1]>(smem_attn);   // [128][D + 1]
+  float* l_part = reinterpret_cast<float*>(smem_attn) + 128 * (D + 1);      // [128]
+  float* m_part = l_part + 128;                                              // [4]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = blockIdx.x, s = blockIdx.y;
+  griddep_launch();
+  griddep_wait();
+  const RSeq mkv = resolve(p.mkv, s);
+  const RMat Mk = rmat(p.k, mkv, p.ldk, h * p.hsk), Mv = rmat(p.v, mkv, p.ldv, h * p.hsv);
+  const __nv_bfloat16* qrow = p.q + rrow(resolve(p.mq, s), 0) * p.ldq + h * p.hsq;
+  constexpr bool TWO_PHASE = D > 80;   // wide heads: V is requested after K has been consumed (register budget)
+  uint4 qv[CH], kv[CH], vv[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) qv[c] = __ldg(reinterpret_cast<const uint4*>(qrow) + c);
+  auto fetch_k = [&](int key) {
+    const uint4* kr = reinterpret_cast<const uint4*>(mrow(Mk, key));
+#pragma unroll
+    for (int c = 0; c < CH; ++c) kv[c] = __ldg(kr + c);
+  };
+  auto fetch_v = [&](int key) {
+    const uint4* vr = reinterpret_cast<const uint4*>(mrow(Mv, key));
+#pragma unroll
+    for (int c = 0; c < CH; ++c) vv[c] = __ldg(vr + c);
+  };
+  // the first 128 keys are requested before the device-side key count is known (rows < s_kv always exist in the cache
+  // buffer; what lies past the count is masked below), so the count's own load is off the critical path
+  if (warp * 32 + lane < p.s_kv) {
+    fetch_k(warp * 32 + lane);
+    if (!TWO_PHASE) fetch_v(warp * 32 + lane);
+  }
+  int sq, skv;
+  eff_len(p, s, sq, skv);
+  float o[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) o[d] = 0.f;
+  float m_run = -CUDART_INF_F, l_run = 0.f;
+  for (int k0 = 0; k0 < skv; k0 += 128) {
+    const int key = k0 + warp * 32 + lane;
+    const bool valid = key < skv;
+    if (k0 > 0 && valid) {
+      fetch_k(key);
+      if (!TWO_PHASE) fetch_v(key);
+    }
+    float sc = -CUDART_INF_F;
+    if (valid) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const uint32_t* qp = &qv[c].x; const uint32_t* kp = &kv[c].x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { a0 = fmaf(bf16_lo(qp[e]), bf16_lo(kp[e]), a0); a1 = fmaf(bf16_hi(qp[e]), bf16_hi(kp[e]), a1); }
+      }
+      sc = (a0 + a1) * p.scale_log2;
+    }
+    if (TWO_PHASE && valid) fetch_v(key);
+    const float m_new = fmaxf(m_run, warp_max(sc));   // finite: key k0 + warp*32 is valid whenever this warp has any key
+    if (m_new == -CUDART_INF_F) continue;              // (a warp past the end of a short cache)
+    const float corr = exp2f(m_run - m_new), pr = valid ? exp2f(sc - m_new) : 0.f;
+    l_run = l_run * corr + pr;
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const uint32_t* vp = &vv[c].x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          o[8 * c + 2 * e] = fmaf(pr, bf16_lo(vp[e]), o[8 * c + 2 * e] * corr);
+          o[8 * c + 2 * e + 1] = fmaf(pr, bf16_hi(vp[e]), o[8 * c + 2 * e + 1] * corr);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) o[d] *= corr;
+    }
+    m_run = m_new;
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) o_part[threadIdx.x][d] = o[d];
+  l_part[threadIdx.x] = l_run;
+  if (lane == 0) m_part[warp] = m_run;
+  __syncthreads();
+  const float m_all = fmaxf(fmaxf(m_part[0], m_part[1]), fmaxf(m_part[2], m_part[3]));
+  float wgt[4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) wgt[w] = m_part[w] == -CUDART_INF_F ? 0.f : exp2f(m_part[w] - m_all);
+  float l_all = 0.f;
+  for (int r = 0; r < 128; ++r) l_all += l_part[r] * wgt[r >> 5];
+  __nv_bfloat16* orow = p.o + rrow(resolve(p.mo, s), 0) * p.ldo + h * p.hso;
+  for (int d = threadIdx.x; d < D; d += 128) {
+    float acc = 0.f;
+    for (int r = 0; r < 128; ++r) acc += o_part[r][d] * wgt[r >> 5];
+    orow[d] = __float2bfloat16(acc / l_all);
+  }
+  if (p.lse && threadIdx.x == 0) p.lse[((long)s * p.n_heads + h) * p.s_q] = (m_all + log2f(l_all)) * 0.6931471805599453f;
+}
+template <int D>
+static int launch_decode(const AttnKParams& p, cudaStream_t st) {
+  constexpr int smem = (128 * (D + 1) + 128 + 4) * 4;
+  static bool set = false;
+  if (!set) { YMP_CUDA(cudaFuncSetAttribute(attn_decode_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+  launch_k(attn_decode_kernel<D>, dim3(p.n_heads, p.n_seq), dim3(128), smem, st, p);
+  YMP_LAUNCH_CHECK();
+  return YMP_OK;
+}
+
 static int fill_params(const ymp_attn_args* a, AttnKParams& p, const char* who) {
   YMP_CHECK_ARG(a && a->q && a->k && a->v, "%s: null q/k/v", who);
   YMP_CHECK_ARG(a->head_dim == 64 || a->head_dim == 80 || a->head_dim == 88 || a->head_dim == 96 || a->head_dim == 128,
@@ -748,6 +863,14 @@ extern "C" int ymp_attn_fwd(const ymp_attn_args* a, void* stream) {
   static const bool legacy = [] { const char* e = getenv("YMP_ATTN_LEGACY"); return e && e[0] == '1'; }();
   const bool dropped = a->drop.rng && a->drop.p > 0.f;
   YMP_CHECK_ARG(!dropped || a->drop.p < 1.f, "ymp_attn_fwd: dropout p must be < 1");
+  if (a->s_q == 1 && a->mask == YMP_MASK_NONE && a->total_rows == 0 && !dropped && a->head_dim != 88 && a->head_dim != 128 && !legacy) {
+    g_attn_path = YMP_ATTN_PATH_DECODE;   // one query row per sequence: the streaming kernel (also follows s_kv_dev)
+    switch (a->head_dim) {
+      case 64: return launch_decode<64>(p, st);
+      case 80: return launch_decode<80>(p, st);
+      default: return launch_decode<96>(p, st);
+    }
+  }
   const bool dev_len = a->s_kv_dev != nullptr;  // key count read on the device: the mma.sync kernels bound their KV loop by it
   YMP_CHECK_ARG(!dev_len || (!dropped && a->mask == YMP_MASK_NONE && a->total_rows == 0 && a->head_dim != 88),
                 "ymp_attn_fwd: s_kv_dev needs mask none, no dropout, no total_rows, head_dim in {64,80,96,128}");

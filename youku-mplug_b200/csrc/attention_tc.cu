@@ -862,11 +862,18 @@ __global__ void __launch_bounds__(256, 1) attn_tc_bwd_kernel(const AttnTcBwdPara
       const TcMat Mo = tc_mat(p.o, p.mo, s, p.ldo, h * p.hso);
       const uint4* po = reinterpret_cast<const uint4*>(tc_row(Mo, r));
       const uint4* pd = reinterpret_cast<const uint4*>(tc_row(Mdo, r));
+      // all 2 * HD / 8 row chunks are requested before the first one is used (one round trip instead of HD / 8)
+      uint4 oa[HD / 8], ob[HD / 8];
+#pragma unroll
+      for (int c = 0; c < HD / 8; ++c) {
+        const bool in = c * 8 < p.hd;
+        oa[c] = in ? __ldg(po + c) : make_uint4(0, 0, 0, 0);
+        ob[c] = in ? __ldg(pd + c) : make_uint4(0, 0, 0, 0);
+      }
       float acc = 0.f;
 #pragma unroll
       for (int c = 0; c < HD / 8; ++c) {
-        if (c * 8 >= p.hd) break;
-        const uint4 a = __ldg(po + c), b = __ldg(pd + c);
+        const uint4 a = oa[c], b = ob[c];
         acc += bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) + bf16_hi(a.y) * bf16_hi(b.y) +
                bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) + bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
       }

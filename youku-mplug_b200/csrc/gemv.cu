@@ -34,7 +34,87 @@ struct SkinnyParams {
   long long ldy2, y2_stride;
   int M, N, K, ldx, ldw, ldr, ldy;
   int act, res_f32, out_f32, ksplit;
+  const __nv_bfloat16* ln_gamma;
+  const __nv_bfloat16* ln_beta;
+  __nv_bfloat16* ln_out;
+  unsigned int* ln_counter;
+  int ld_ln;
+  float ln_eps;
 };
+
+// LayerNorm of all M rows of the finished fp32 result by the whole (last) CTA, read back from L2 (ld.cg: other CTAs
+// wrote it).  Three passes (sum, squared deviations, normalise), each with every load of every row in flight at once -
+// three L2 round trips on the critical path, not one per 8-element chunk.  Same formula as ln_fwd_kernel (layernorm.cu):
+// mean = sum / N, rstd = rsqrt(sum((x - mean)^2) / N + eps), y = ((x - mean) * rstd) * gamma + beta.
+template <int PASS>
+__device__ __forceinline__ void skinny_ln_pass(const SkinnyParams& p, const float* mu, const float* rs, float* red) {
+  const int nvec = p.N >> 3, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[SK_MAXM];
+#pragma unroll
+  for (int m = 0; m < SK_MAXM; ++m) acc[m] = 0.f;
+  for (int vi = threadIdx.x; vi < nvec; vi += SK_WARPS * 32) {
+    float4 a[SK_MAXM], b[SK_MAXM];
+#pragma unroll
+    for (int m = 0; m < SK_MAXM; ++m) {
+      if (m < p.M) {
+        const float4* yr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.y) + (size_t)m * p.ldy) + 2 * vi;
+        a[m] = __ldcg(yr); b[m] = __ldcg(yr + 1);
+      }
+    }
+    uint4 gv, bv;
+    if (PASS == 2) { gv = __ldg(reinterpret_cast<const uint4*>(p.ln_gamma) + vi); bv = __ldg(reinterpret_cast<const uint4*>(p.ln_beta) + vi); }
+#pragma unroll
+    for (int m = 0; m < SK_MAXM; ++m) {
+      if (m < p.M) {
+        const float v[8] = {a[m].x, a[m].y, a[m].z, a[m].w, b[m].x, b[m].y, b[m].z, b[m].w};
+        if (PASS == 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[m] += v[e];
+        } else if (PASS == 1) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { const float d = v[e] - mu[m]; acc[m] += d * d; }
+        } else {
+          const uint32_t* gp = &gv.x; const uint32_t* bp = &bv.x;
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[e] = pack_bf16(fmaf((v[2 * e] - mu[m]) * rs[m], bf16_lo(gp[e]), bf16_lo(bp[e])),
+                             fmaf((v[2 * e + 1] - mu[m]) * rs[m], bf16_hi(gp[e]), bf16_hi(bp[e])));
+          reinterpret_cast<uint4*>(p.ln_out + (size_t)m * p.ld_ln)[vi] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  }
+  if (PASS < 2) {
+#pragma unroll
+    for (int m = 0; m < SK_MAXM; ++m) {
+      const float t = warp_sum(acc[m]);
+      if (lane == 0) red[warp * SK_MAXM + m] = t;
+    }
+    __syncthreads();
+  }
+}
+__device__ __forceinline__ void skinny_ln_rows(const SkinnyParams& p, float* red /* [SK_WARPS * SK_MAXM] */) {
+  float mu[SK_MAXM], rs[SK_MAXM];
+  skinny_ln_pass<0>(p, mu, rs, red);
+#pragma unroll
+  for (int m = 0; m < SK_MAXM; ++m) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < SK_WARPS; ++w) t += red[w * SK_MAXM + m];
+    mu[m] = t / (float)p.N;
+  }
+  __syncthreads();
+  skinny_ln_pass<1>(p, mu, rs, red);
+#pragma unroll
+  for (int m = 0; m < SK_MAXM; ++m) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < SK_WARPS; ++w) t += red[w * SK_MAXM + m];
+    rs[m] = rsqrtf(t / (float)p.N + p.ln_eps);
+  }
+  skinny_ln_pass<2>(p, mu, rs, red);
+}
 
 __device__ __forceinline__ void mma16816_bf16(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
   // rows 8..15 of the A operand (a1, a3) are zero: only M <= 8 activation rows exist
@@ -44,8 +124,8 @@ __device__ __forceinline__ void mma16816_bf16(float (&c)[4], uint32_t a0, uint32
       : "r"(a0), "r"(0u), "r"(a2), "r"(b0), "r"(b1));
 }
 
-template <int SK_UNROLL>
-__global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const SkinnyParams p) {
+template <int SK_UNROLL, bool LN>
+__global__ void __launch_bounds__(SK_WARPS * 32, (LN ? 2 : 1)) gemm_skinny_kernel(const SkinnyParams p) {
   __shared__ float part[SK_WARPS][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -110,7 +190,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const Skinny
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int n = n0 + 2 * t + e;
-      if (n >= p.N) break;
+      if (n >= p.N) continue;
       float v = acc[e];
       if (p.bias) v += __bfloat162float(p.bias[n]);
       if (p.act == YMP_ACT_GELU_TANH) v = gelu_tanh(v);
@@ -121,6 +201,20 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(const Skinny
       if (p.out_f32) reinterpret_cast<float*>(p.y)[(size_t)g * p.ldy + n] = v;
       else reinterpret_cast<__nv_bfloat16*>(p.y)[(size_t)g * p.ldy + n] = __float2bfloat16(v);
       if (p.y2) p.y2[(long long)g * p.ldy2 + *p.y2_off * p.y2_stride + n] = __float2bfloat16(v);
+    }
+    if (LN) __threadfence();   // this thread's rows are visible device-wide before its CTA takes a ticket
+  }
+  if constexpr (LN) {
+    // fused LayerNorm: the CTA that takes the last ticket sees every other CTA's rows (writers' fences + atomic) and
+    // normalises them
+    __shared__ unsigned int ticket;
+    __syncthreads();
+    if (threadIdx.x == 0) ticket = atomicAdd(p.ln_counter, 1u);
+    __syncthreads();
+    if (ticket == gridDim.x - 1) {
+      __threadfence();
+      skinny_ln_rows(p, &part[0][0]);
+      if (threadIdx.x == 0) *p.ln_counter = 0u;
     }
   }
 }
@@ -140,6 +234,12 @@ extern "C" int ymp_gemm_skinny(const ymp_gemm_skinny_args* a, void* stream) {
   YMP_CHECK_ARG(!a->y2 || (a->y2_off_dev && a->out_dtype == YMP_DT_BF16), "ymp_gemm_skinny: y2 needs y2_off_dev and a bf16 result");
   p.y2 = (__nv_bfloat16*)a->y2; p.y2_off = (const long long*)a->y2_off_dev; p.ldy2 = a->ldy2; p.y2_stride = a->y2_off_stride;
   p.M = a->M; p.N = a->N; p.K = a->K; p.ldx = a->ldx; p.ldw = a->ldw; p.ldr = a->ldr; p.ldy = a->ldy;
+  const bool ln = a->ln_out != nullptr;
+  YMP_CHECK_ARG(!ln || (a->ln_gamma && a->ln_beta && a->ln_counter && a->out_dtype == YMP_DT_F32 && a->N % 8 == 0 && a->ld_ln % 8 == 0 &&
+                        a->ldy % 4 == 0 && aligned16(a->y) && aligned16(a->ln_out) && aligned16(a->ln_gamma) && aligned16(a->ln_beta)),
+                "ymp_gemm_skinny: fused LayerNorm needs gamma/beta/counter, an fp32 result, N %% 8 == 0 and 16-byte aligned rows");
+  p.ln_gamma = (const __nv_bfloat16*)a->ln_gamma; p.ln_beta = (const __nv_bfloat16*)a->ln_beta; p.ln_out = (__nv_bfloat16*)a->ln_out;
+  p.ln_counter = a->ln_counter; p.ld_ln = a->ld_ln; p.ln_eps = a->ln_eps;
   p.act = a->act; p.res_f32 = a->residual_dtype == YMP_DT_F32; p.out_f32 = a->out_dtype == YMP_DT_F32;
   // K slices per CTA (the warps of a CTA that share one 8-column tile): as many as leave >= 4 k-blocks of 32 per slice
   int ks = 1;
@@ -152,9 +252,10 @@ extern "C" int ymp_gemm_skinny(const ymp_gemm_skinny_args* a, void* stream) {
   const int blocks = (tiles + tiles_per_cta - 1) / tiles_per_cta;
   static const int unroll = [] { const char* e = getenv("YMP_SKINNY_UNROLL"); return e ? atoi(e) : 4; }();
   cudaStream_t st = (cudaStream_t)stream;
-  if (unroll == 8) launch_k(gemm_skinny_kernel<8>, dim3(blocks), dim3(SK_WARPS * 32), 0, st, p);
-  else if (unroll == 2) launch_k(gemm_skinny_kernel<2>, dim3(blocks), dim3(SK_WARPS * 32), 0, st, p);
-  else launch_k(gemm_skinny_kernel<4>, dim3(blocks), dim3(SK_WARPS * 32), 0, st, p);
+  if (ln) launch_k(gemm_skinny_kernel<4, true>, dim3(blocks), dim3(SK_WARPS * 32), 0, st, p);
+  else if (unroll == 8) launch_k(gemm_skinny_kernel<8, false>, dim3(blocks), dim3(SK_WARPS * 32), 0, st, p);
+  else if (unroll == 2) launch_k(gemm_skinny_kernel<2, false>, dim3(blocks), dim3(SK_WARPS * 32), 0, st, p);
+  else launch_k(gemm_skinny_kernel<4, false>, dim3(blocks), dim3(SK_WARPS * 32), 0, st, p);
   YMP_LAUNCH_CHECK();
   return YMP_OK;
 }

@@ -314,6 +314,7 @@ class InferenceParams:
         self.batch_size_offset = 0
         self.key_value_memory_dict = {}
         self.cache = None
+        self.token_step = None   # ymp.engine.TokenStep once this call's single-token steps have been validated
 
     def swap_key_value_dict(self, batch_idx):
         'swap between batches'
@@ -548,8 +549,16 @@ class DistributedGPT3(nn.Module):
         if self.inference_params is None:
             raise ValueError("no labels and no inference_params: call sample()/beam_search()/generate()")
         ip = self.inference_params
-        keys, params = self._param_list()
         B, n, H = input_embeds.shape
+        ts = ip.token_step
+        if ts is not None and n == 1:
+            # steady state of sample() / beam_search(): nothing but the graph replay on the host path (walking the module
+            # tree for the parameter list alone costs more than the whole device step; weights cannot change inside
+            # one generate call - the step object was validated when this call acquired its cache)
+            hid, logits = ts.run(input_embeds.reshape(B, H))
+            ip.sequence_len_offset += 1
+            return AttrDict(logits=logits.view(B, 1, -1), loss=None, losses=None, last_hidden_state=hid.view(B, 1, H))
+        keys, params = self._param_list()
         if ip.cache is None:
             # one cache (and one captured token step) per (batch, length) is kept on the model and reused by later
             # sample() / beam_search() calls: caption evaluation decodes thousands of clips with the same shape
@@ -575,6 +584,8 @@ class DistributedGPT3(nn.Module):
                                                        input_embeds.dtype, sig, static)
             elif not ts.static:
                 ts.W = {k: YF.as_bf16(p) for k, p in zip(keys, params)}
+            if ts.static:
+                ip.token_step = ts
             hid, logits = ts.run(input_embeds.reshape(B, H))
         else:
             W = {k: YF.as_bf16(p) for k, p in zip(keys, params)}

@@ -684,6 +684,7 @@ class TokenStep:
         self.cache, self.W, self.sig, self.static = cache, W, sig, static
         self.emb_in = torch.zeros((cache.B, g.H), device=dev, dtype=emb_dtype)
         self.stage = torch.zeros((cache.B, 3 * g.H), device=dev, dtype=bf16)   # the new token's [q|k|v] row per sequence
+        self.ticket = torch.zeros(1, device=dev, dtype=torch.int32)            # last-CTA ticket of the fused LayerNorms
         self.graph = None
         self.out = None
         self.warm = False
@@ -707,9 +708,29 @@ class TokenStep:
         pos = W[GPT + "embedding.position_embeddings.weight"]
         x = self.emb_in.float() + pos.index_select(0, c.len_idx).float()
         mkv = ops.dense_map(ML)
+
+        import os
+        # YMP_DECODE_FUSED_LN=1: every LayerNorm but the first is computed by the last CTA of the GEMM that completes its
+        # input (one kernel boundary less per sub-layer).  Off by default: measured neutral on B200 (captured step 1.466
+        # vs 1.438 ms, profiles/r02p_decode_ab.log) - the ticket + three L2 round trips of the tail cost what the
+        # stand-alone kernel and its launch gap cost.
+        fused_ln = os.environ.get("YMP_DECODE_FUSED_LN", "0") == "1"
+
+        def ln_of(prefix):
+            return (W[prefix + ".weight"], W[prefix + ".bias"], g.eps, self.ticket)
+
+        def gemm_ln(a, wname, residual, ln_prefix):
+            """fp32 residual-stream GEMM followed by the LayerNorm of its complete result: (y, LN(y))."""
+            if fused_ln:  # the LayerNorm is computed by the GEMM's last CTA
+                return ops.gemm_skinny(a, W[wname + ".weight"], bias=W[wname + ".bias"], residual=residual, out_dtype=torch.float32,
+                                       ln=ln_of(ln_prefix))
+            y = ops.gemm_skinny(a, W[wname + ".weight"], bias=W[wname + ".bias"], residual=residual, out_dtype=torch.float32)
+            return y, ops.layernorm_fwd(y, W[ln_prefix + ".weight"], W[ln_prefix + ".bias"], g.eps, stats=False)[0]
+
+        ln1, _, _ = ops.layernorm_fwd(x, W[f"{GPT}encoder.layers.0.input_layernorm.weight"], W[f"{GPT}encoder.layers.0.input_layernorm.bias"],
+                                      g.eps, stats=False)
         for i in range(g.layers):
             pre = f"{GPT}encoder.layers.{i}."
-            ln1, _, _ = ops.layernorm_fwd(x, W[pre + "input_layernorm.weight"], W[pre + "input_layernorm.bias"], g.eps, stats=False)
             st = self.stage
             buf = c.qkv[i]
             # [q|k|v] of the new token: into the staging rows (q for this step) and into cache row b*ML + len (k, v)
@@ -720,15 +741,11 @@ class TokenStep:
             k, v = TView(buf, hd, 3 * hd, mkv), TView(buf, 2 * hd, 3 * hd, mkv)
             ops.attn_fwd(q, k, v, TView(att, 0, hd, ops.dense_map(1)), n_seq=B, n_heads=g.heads, head_dim=hd, s_q=1, s_kv=ML,
                          causal=False, scale=g.scale, s_kv_dev=c.len1)
-            x1 = ops.gemm_skinny(att, W[pre + "self_attention.dense.weight"], bias=W[pre + "self_attention.dense.bias"], residual=x,
-                                 out_dtype=torch.float32)
-            ln2, _, _ = ops.layernorm_fwd(x1, W[pre + "post_attention_layernorm.weight"], W[pre + "post_attention_layernorm.bias"],
-                                          g.eps, stats=False)
+            x1, ln2 = gemm_ln(att, pre + "self_attention.dense", x, pre + "post_attention_layernorm")
             h = ops.gemm_skinny(ln2, W[pre + "mlp.dense_h_to_4h.weight"], bias=W[pre + "mlp.dense_h_to_4h.bias"], act=ACT_GELU_TANH)
-            x = ops.gemm_skinny(h, W[pre + "mlp.dense_4h_to_h.weight"], bias=W[pre + "mlp.dense_4h_to_h.bias"], residual=x1,
-                                out_dtype=torch.float32)
-        hid, _, _ = ops.layernorm_fwd(x, W[GPT + "encoder.final_layernorm.weight"], W[GPT + "encoder.final_layernorm.bias"], g.eps,
-                                      stats=False)
+            nxt = f"{GPT}encoder.layers.{i + 1}.input_layernorm" if i + 1 < g.layers else GPT + "encoder.final_layernorm"
+            x, ln1 = gemm_ln(h, pre + "mlp.dense_4h_to_h", x1, nxt)
+        hid = ln1
         logits = ops.gemm_skinny(hid, W[GPT + "embedding.word_embeddings.weight"], out_dtype=torch.float32)
         c.len_idx += 1
         c.len1 += 1

@@ -92,7 +92,9 @@ class GemmSkinnyArgs(C.Structure):
     _fields_ = [("x", c_vp), ("w", c_vp), ("bias", c_vp), ("residual", c_vp), ("y", c_vp),
                 ("M", c_i32), ("N", c_i32), ("K", c_i32), ("ldx", c_i32), ("ldw", c_i32), ("ldr", c_i32), ("ldy", c_i32),
                 ("act", c_i32), ("residual_dtype", c_i32), ("out_dtype", c_i32),
-                ("y2", c_vp), ("y2_off_dev", c_vp), ("ldy2", C.c_int64), ("y2_off_stride", C.c_int64)]
+                ("y2", c_vp), ("y2_off_dev", c_vp), ("ldy2", C.c_int64), ("y2_off_stride", C.c_int64),
+                ("ln_gamma", c_vp), ("ln_beta", c_vp), ("ln_out", c_vp), ("ln_counter", c_vp), ("ld_ln", c_i32),
+                ("ln_eps", C.c_float)]
 
 
 class AttnBwdArgs(C.Structure):
@@ -152,7 +154,7 @@ lib.ymp_launch_count.restype = C.c_uint64
 lib.ymp_attn_last_path.restype = C.c_int
 lib.ymp_set_pdl.restype = C.c_int
 lib.ymp_set_pdl.argtypes = [C.c_int]
-ATTN_PATH_MMA_SYNC, ATTN_PATH_TCGEN05, ATTN_PATH_SMALL = 0, 1, 2
+ATTN_PATH_MMA_SYNC, ATTN_PATH_TCGEN05, ATTN_PATH_SMALL, ATTN_PATH_DECODE = 0, 1, 2, 3
 
 
 def _declare(name, argstruct):
