@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "youku-mplug_b200", "ymp", "libymp_b200.so")
 OPS = ["UTCHMMA.2CTA", "UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "LDGSTS", "HMMA.16816",
-       "MUFU.EX2", "SYNCS", "USETMAXREG", "RED.E", "ATOM", "STL", "LDL"]
+       "FFMA2", "MUFU.EX2", "SYNCS", "ACQBULK", "RED.E", "ATOM", "STL", "LDL"]
 
 
 def main():
