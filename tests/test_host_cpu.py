@@ -33,7 +33,7 @@ def test_ctypes_structs_match_header_field_order():
                "ymp_seqmap": L.SeqMap, "ymp_attn_args": L.AttnArgs, "ymp_attn_bwd_args": L.AttnBwdArgs,
                "ymp_adamw_args": L.AdamwArgs, "ymp_im2col_args": L.Im2colArgs, "ymp_clip_args": L.ClipArgs, "ymp_embed_args": L.EmbedArgs,
                "ymp_ce_args": L.CeArgs, "ymp_colsum_args": L.ColsumArgs, "ymp_group_args": L.GroupArgs,
-               "ymp_dropout_spec": L.DropoutSpec, "ymp_dropout_args": L.DropoutArgs}
+               "ymp_dropout_spec": L.DropoutSpec, "ymp_dropout_args": L.DropoutArgs, "ymp_gemm_skinny_args": L.GemmSkinnyArgs}
     for name, cls in mirrors.items():
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
