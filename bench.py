@@ -325,6 +325,9 @@ def run_ymp(args, rank, local_rank, world):
 
     def gemm_rec(a, b, **kw):
         M, K = (a.shape[1], a.shape[0]) if kw.get("a_t") else (a.shape[0], a.shape[1])
+        if kw.get("_im2col") is not None:       # fused patch embedding: A is the video, rows (b, n, t) x columns C*P*P
+            P_, B_, C_, T_, H_, W_ = kw["_im2col"]
+            M, K = B_ * (H_ // P_) * (W_ // P_) * T_, C_ * P_ * P_
         N = b.shape[1] if kw.get("b_t") else b.shape[0]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -333,7 +336,8 @@ def run_ymp(args, rank, local_rank, world):
         rec.append((2.0 * M * N * K, e0, e1, (M, N, K, int(bool(kw.get("a_t"))), int(bool(kw.get("b_t"))),
                                               int(bool(kw.get("accumulate"))), int(kw.get("act", 0)),
                                               int(kw.get("aux_out") is not None), int(kw.get("aux_in") is not None),
-                                              int(kw.get("residual") is not None))))
+                                              int(kw.get("residual") is not None), int(out.dtype == torch.float32),
+                                              int(kw.get("residual") is not None and kw["residual"].dtype == torch.float32))))
         return out
 
     ops.gemm = gemm_rec
@@ -348,7 +352,8 @@ def run_ymp(args, rank, local_rank, world):
             ent = shapes.setdefault(key, [0, 0.0, 0.0])
             ent[0] += 1; ent[1] += e0.elapsed_time(e1); ent[2] += f
         rows = sorted(([dict(M=k[0], N=k[1], K=k[2], a_t=k[3], b_t=k[4], acc=k[5], act=k[6], aux_out=k[7], aux_in=k[8],
-                             res=k[9], n=v[0], ms=v[1], tflops=v[2] / v[1] / 1e9) for k, v in shapes.items()]),
+                             res=k[9], out_f32=k[10], res_f32=k[11], n=v[0], ms=v[1], tflops=v[2] / v[1] / 1e9)
+                        for k, v in shapes.items()]),
                       key=lambda r: -r["ms"])
         with open(args.gemm_report, "w") as fh:
             json.dump(rows, fh, indent=1)
@@ -360,12 +365,14 @@ def run_ymp(args, rank, local_rank, world):
         assert abs(gf_sample - GF_PER_SAMPLE) < 0.5, gf_sample
     step_tf = gf_sample * B / ms_step  # GFLOP/ms == TFLOP/s
     traffic, traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
     if os.path.exists(tpath) and args.config == "pretrain" and (B, T, L, Q) == (32, 8, 128, 128):
         with open(tpath) as fh:
             tj = json.load(fh)
         traffic = tj["bytes_per_launch"]
-        traffic_note = ("dram__bytes_read+write per GEMM launch, ncu capture committed in profiles/r01_gemm_traffic.json "
+        traffic_note = (f"dram__bytes_read+write per GEMM launch, ncu capture committed in profiles/{os.path.basename(tpath)} "
                         f"(= {tj['measured_over_algorithmic']:.2f} x the algorithmic operand bytes)")
     roofline = dict(bound="tensor", kernel="gemm_bf16_tcgen05_2cta_kernel", achieved=tf, peak=pk["tf_sustained"], unit="TFLOP/s",
                     frac=tf / pk["tf_sustained"], traffic=traffic, traffic_note=traffic_note,
