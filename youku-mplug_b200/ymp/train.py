@@ -50,6 +50,43 @@ class _Optimizer:
         self._global_grad_norm = None
 
 
+BUCKET_MIN_ELEMS = 1 << 18   # 1 MB of fp32 gradients: smaller ranges are left to the single reduction in step()
+
+
+def plan_buckets(spans, min_elems=BUCKET_MIN_ELEMS, pattern=r"(visual_encoder\.blocks\.\d+\.)"):
+    """In-backward all-reduce buckets: spans = [(parameter name, begin, end)] in flat-buffer order; a bucket is a maximal
+    run of ADJACENT spans that belong to the same TimeSformer block (same `pattern` prefix) and holds at least
+    `min_elems` elements.  Returns {block prefix: [(begin, end), ...]} - what TrainEngine reduces the moment the
+    backward reports that block final (pure host logic, CPU-tested over gloo in tests/test_dist_cpu.py)."""
+    import re
+    buckets, cur = {}, None
+
+    def close(c):
+        if c is not None and c[0] is not None and c[2] - c[1] >= min_elems:
+            buckets.setdefault(c[0], []).append((c[1], c[2]))
+
+    for name, a, b in spans:
+        m = re.match(pattern, name)
+        key = m.group(1) if m else None
+        if cur is not None and key is not None and cur[0] == key and cur[2] == a:
+            cur[2] = b
+        else:
+            close(cur)
+            cur = [key, a, b]
+    close(cur)
+    return buckets
+
+
+def gap_ranges(reduced, total):
+    """The parts of [0, total) that the ranges in `reduced` (any order, possibly touching) do not cover."""
+    gaps, pos = [], 0
+    for a, b in sorted(reduced) + [(total, total)]:
+        if a > pos:
+            gaps.append((pos, a))
+        pos = max(pos, b)
+    return gaps
+
+
 class TrainEngine:
     def __init__(self, model, optimizer_params=None, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.05,
                  clip_grad=3.0, process_group=None, gradient_accumulation_steps=1, overlap_comm=True):
@@ -106,19 +143,7 @@ class TrainEngine:
         self.overlap_comm = overlap_comm and self.world > 1 and os.environ.get("YMP_OVERLAP_COMM", "1") != "0"   # (env: A/B knob)
         self._buckets, self._pending, self._reduced = {}, [], []
         if self.overlap_comm:
-            import re
-            cur = None
-            for name, a, b in spans:
-                m = re.match(r"(visual_encoder\.blocks\.\d+\.)", name)
-                key = m.group(1) if m else None
-                if cur is not None and key is not None and cur[0] == key and cur[2] == a:
-                    cur[2] = b
-                else:
-                    if cur is not None and cur[0] is not None and cur[2] - cur[1] >= (1 << 18):
-                        self._buckets.setdefault(cur[0], []).append((cur[1], cur[2]))
-                    cur = [key, a, b]
-            if cur is not None and cur[0] is not None and cur[2] - cur[1] >= (1 << 18):
-                self._buckets.setdefault(cur[0], []).append((cur[1], cur[2]))
+            self._buckets = plan_buckets(spans)
 
     # ---- nn.Module-like surface -----------------------------------------------------------
     def __call__(self, *args, **kwargs):
@@ -161,11 +186,8 @@ class TrainEngine:
         if self.world == 1:
             return
         self._join_comm()
-        pos = 0
-        for a, b in sorted(self._reduced) + [(self.flat_grad.numel(), self.flat_grad.numel())]:
-            if a > pos:
-                dist.all_reduce(self.flat_grad[pos:a], op=dist.ReduceOp.SUM, group=self.group)
-            pos = max(pos, b)
+        for a, b in gap_ranges(self._reduced, self.flat_grad.numel()):
+            dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.group)
         self._reduced = []
 
     def _backward(self, loss):
