@@ -200,3 +200,42 @@ def test_pretrain_image_state_dict_surface_and_oracle():
     g = E.create_eva_vit_g(img_size=224, drop_path_rate=0, norm_layer=None)
     assert g.ecfg["embed_dim"] == 1408 and g.ecfg["depth"] == 40 and g.ecfg["num_heads"] == 16 and g.pos_embed.shape == (1, 257, 1408)
     assert g.get_parameter("blocks.39.mlp.fc1.weight").shape == (6144, 1408)
+
+
+def test_task_configs_mirror_the_reference_yamls():
+    """configs/{pretrain,caption,cls,retrieval}/*.yaml: every file the reference ships for the GPT-3 models exists here
+    under the same name, parses with the YAML loader the scripts use (ruamel.yaml semantics: 1e-6 is a float), and
+    carries the same keys and values as the reference's file except for megatron_cfg (tensor parallel size 1 here)."""
+    import glob
+    import importlib
+    import sys
+    compat = os.path.join(ROOT, "youku-mplug_b200", "compat")
+    sys.path.append(compat)
+    try:
+        ryaml = importlib.import_module("ruamel.yaml")
+    finally:
+        sys.path.remove(compat)
+        for k in [k for k in sys.modules if k == "ruamel" or k.startswith("ruamel.")]:
+            del sys.modules[k]
+    cfg_root = os.path.join(ROOT, "youku-mplug_b200", "configs")
+    names = ["caption/caption_gpt3_1.3B_youku_v0.yaml", "caption/caption_gpt3_2.7B_youku_v0.yaml",
+             "cls/cls_gpt3_1.3B_youku_v0_sharp_2.yaml", "cls/cls_gpt3_2.7B_youku_v0_sharp_2.yaml",
+             "retrieval/retrieval_gpt3_1.3B_youku_v0.yaml", "retrieval/retrieval_gpt3_2.7B_youku_v0.yaml",
+             "retrieval/retrieval_itm_gpt3_1.3B_youku_v0.yaml", "retrieval/retrieval_itm_gpt3_2.7B_youku_v0.yaml",
+             "pretrain/gpt3_1.3B/pretrain_gpt3_freezeGPT_youku_v0.yaml", "pretrain/gpt3_2.7B/pretrain_gpt3_freezeGPT_youku_v0.yaml"]
+    ref_root = "/root/reference/configs"
+    for n in names:
+        cfg = ryaml.load(open(os.path.join(cfg_root, n)), Loader=ryaml.Loader)
+        assert cfg["megatron_cfg"]["tensor_model_parallel_size"] == 1 and cfg["megatron_cfg"]["model_parallel_size"] == 1
+        assert isinstance(cfg["optimizer"]["lr"], float) and isinstance(cfg["optimizer"]["opt_eps"], float)
+        assert isinstance(cfg["schedular"]["min_lr"], float) and cfg["freeze_text_decoder"] is True and cfg["num_learnable_token"] == 128
+        assert os.path.exists(os.path.join(ROOT, "youku-mplug_b200", cfg["text_cfg"])) and os.path.exists(os.path.join(ROOT, "youku-mplug_b200", cfg["visual_cfg"]))
+        if os.path.isdir(ref_root):   # (the reference checkout exists in the development container only)
+            ref = ryaml.load(open(os.path.join(ref_root, n)), Loader=ryaml.Loader)
+            assert set(ref) == set(cfg), (n, set(ref) ^ set(cfg))
+            for k in ref:
+                if k != "megatron_cfg":
+                    assert ref[k] == cfg[k], (n, k, ref[k], cfg[k])
+    if os.path.isdir(ref_root):
+        shipped = {os.path.relpath(p, ref_root) for p in glob.glob(os.path.join(ref_root, "*", "*.yaml")) + glob.glob(os.path.join(ref_root, "pretrain", "*", "*.yaml"))}
+        assert shipped <= set(names) | {n for n in shipped if "b200" in n}, shipped - set(names)
