@@ -782,8 +782,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnKParams p) {
 template <int D>
 static int launch_decode(const AttnKParams& p, cudaStream_t st) {
   constexpr int smem = (128 * (D + 1) + 128 + 4) * 4;
-  static bool set = false;
-  if (!set) { YMP_CUDA(cudaFuncSetAttribute(attn_decode_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+  static DeviceOnce once;
+  if (once.first()) { YMP_CUDA(cudaFuncSetAttribute(attn_decode_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); }
   launch_k(attn_decode_kernel<D>, dim3(p.n_heads, p.n_seq), dim3(128), smem, st, p);
   YMP_LAUNCH_CHECK();
   return YMP_OK;
@@ -817,8 +817,8 @@ static int fill_params(const ymp_attn_args* a, AttnKParams& p, const char* who) 
 template <int D>
 static int launch_fwd(const AttnKParams& p, cudaStream_t st) {
   const int smem = 5 * 64 * (D + 8) * 2;
-  static bool set = false;
-  if (!set) { YMP_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+  static DeviceOnce once;
+  if (once.first()) { YMP_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); }
   dim3 grid((p.s_q + 63) / 64, p.n_heads, p.n_seq);
   launch_k(attn_fwd_kernel<D>, grid, dim3(128), smem, st, p);
   YMP_LAUNCH_CHECK();
@@ -827,11 +827,10 @@ static int launch_fwd(const AttnKParams& p, cudaStream_t st) {
 template <int D>
 static int launch_bwd(const AttnKParams& p, cudaStream_t st) {
   const int smem = 6 * 64 * (D + 8) * 2 + 1024;
-  static bool set = false;
-  if (!set) {
+  static DeviceOnce once;
+  if (once.first()) {
     YMP_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     YMP_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    set = true;
   }
   attn_bwd_dq_kernel<D><<<dim3((p.s_q + 63) / 64, p.n_heads, p.n_seq), 128, smem, st>>>(p);
   YMP_LAUNCH_CHECK();

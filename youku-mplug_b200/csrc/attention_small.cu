@@ -305,8 +305,8 @@ void fill_small(const ymp_attn_args* a, SmallParams& p) {
 template <int HD>
 int launch_small_fwd(const SmallParams& p, cudaStream_t st) {
   const int smem = 4 * 3 * 16 * (HD * 2 + 16);
-  static bool set = false;
-  if (!set) { YMP_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+  static DeviceOnce once;
+  if (once.first()) { YMP_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); }
   attn_small_fwd_kernel<HD><<<dim3((p.n_tiles + 3) / 4, p.n_heads), 128, smem, st>>>(p);
   YMP_LAUNCH_CHECK();
   return YMP_OK;
@@ -314,8 +314,8 @@ int launch_small_fwd(const SmallParams& p, cudaStream_t st) {
 template <int HD>
 int launch_small_bwd(const SmallParams& p, cudaStream_t st) {
   const int smem = 4 * 4 * 16 * (HD * 2 + 16);
-  static bool set = false;
-  if (!set) { YMP_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+  static DeviceOnce once;
+  if (once.first()) { YMP_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); }
   attn_small_bwd_kernel<HD><<<dim3((p.n_tiles + 3) / 4, p.n_heads), 128, smem, st>>>(p);
   YMP_LAUNCH_CHECK();
   return YMP_OK;

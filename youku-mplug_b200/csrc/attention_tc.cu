@@ -1129,11 +1129,10 @@ template <int HD, bool LONG>
 static int launch_tc(const AttnTcParams& p, cudaStream_t st) {
   const int kvr = p.kv_rows;
   const int smem = 128 * 128 + 2 * kvr * 128 + (HD == 96 ? 128 * 64 + 2 * kvr * 64 : 0) + 1024 + 64 + 1024;
-  static int cur = 0;
-  if (smem > cur) {
+  static DeviceMax opted;
+  if (opted.raise(smem)) {
     YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<HD, LONG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<HD, LONG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    cur = smem;
   }
   dim3 grid((p.s_q + 127) / 128, p.n_heads, p.n_seq);
   if (p.has_drop) attn_tc_fwd_kernel<HD, LONG, true><<<grid, 256, smem, st>>>(p);
@@ -1144,11 +1143,10 @@ static int launch_tc(const AttnTcParams& p, cudaStream_t st) {
 
 template <int HD>
 static int launch_tc_pair(const AttnTcParams& p, int smem, cudaStream_t st) {
-  static int cur = 0;
-  if (smem > cur) {
+  static DeviceMax opted;
+  if (opted.raise(smem)) {
     YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_pair_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     YMP_CUDA(cudaFuncSetAttribute(attn_tc_fwd_pair_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    cur = smem;
   }
   const int items = p.n_seq * p.n_heads;
   if (p.has_drop) attn_tc_fwd_pair_kernel<HD, true><<<min(items, num_sms()), 256, smem, st>>>(p);
@@ -1200,11 +1198,10 @@ int attn_tc_fwd_try(const ymp_attn_args* a, cudaStream_t st) {
 template <int HD>
 static int launch_tc_bwd(const AttnTcBwdParams& p, cudaStream_t st) {
   const int smem = 8 * 16384 + (HD == 96 ? 6 * 8192 : 0) + 128 * (HD * 2 + 16) + ((p.s_q + 127) & ~127) * 8 + 64 + 1024;
-  static int cur = 0;
-  if (smem > cur) {
+  static DeviceMax opted;
+  if (opted.raise(smem)) {
     YMP_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     YMP_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    cur = smem;
   }
   dim3 grid(p.n_heads, p.n_seq);
   if (p.has_drop) attn_tc_bwd_kernel<HD, true><<<grid, 256, smem, st>>>(p);

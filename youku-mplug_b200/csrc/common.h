@@ -56,6 +56,31 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
     ymp::count_launch();                                                                \
   } while (0)
 
+// Per-device "done once" flag for cudaFuncSetAttribute (function attributes belong to the device's context: a process
+// that drives several GPUs must set them on each).  Usage: static DeviceOnce once; if (once.first()) { ...set... }
+struct DeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
+// Per-device running maximum (dynamic shared-memory opt-in that grows with the problem size).
+struct DeviceMax {
+  int cur[64] = {};
+  bool raise(int v) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (v <= cur[dev]) return false;
+    cur[dev] = v;
+    return true;
+  }
+};
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace ymp

@@ -1016,13 +1016,12 @@ static int launch_gemm(const ymp_gemm_args* a, const GemmKParams& kp, cudaStream
   else rc = make_map(&tb, a->B, a->N, a->K, a->ldb, 64, BK);
   if (rc) return rc;
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  if (once.first()) {
     YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
   }
   const int num_m = (a->M + BM - 1) / BM, num_n = (a->N + BN - 1) / BN;
   const int units = num_m * num_n * kp.split_k;
@@ -1060,13 +1059,12 @@ static int launch_gemm_2cta(const ymp_gemm_args* a, GemmKParams kp, cudaStream_t
   if (!a->b_mn_major) rc = make_map(&tb, a->B, a->K, a->N, a->ldb, BK, BN2 / 2);
   else rc = make_map(&tb, a->B, a->N, a->K, a->ldb, 64, BK);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  if (once.first()) {
     YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair<true>::SMEM_BYTES));
     YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair<false>::SMEM_BYTES));
     YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair<true>::SMEM_BYTES));
     YMP_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pair<false>::SMEM_BYTES));
-    attr_set = true;
   }
   const int num_m = (a->M + 2 * BM - 1) / (2 * BM), num_n = (a->N + BN2 - 1) / BN2;
   const int units = num_m * num_n * kp.split_k;

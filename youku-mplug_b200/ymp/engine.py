@@ -185,13 +185,12 @@ def vit_block_bwd(W, G, pre, c, dout, d):
 
 def _qkv_wgrad(G, apre, dqkv, x, D, dev):
     linear_wgrad(dqkv, x, apre + "qkv.weight", None, G)
-    if apre + "q_bias" in G or apre + "v_bias" in G:
-        tmp = _zeros_f32(3 * D, dev)
-        ops.colsum(dqkv, tmp)
-        if apre + "q_bias" in G:
-            G[apre + "q_bias"] += tmp[:D]
-        if apre + "v_bias" in G:
-            G[apre + "v_bias"] += tmp[2 * D:]
+    # the qkv bias is cat(q_bias, 0, v_bias) (models/vision_transformer.py:171-175): only the q and the v column blocks
+    # have a bias gradient, and their column sums accumulate straight into the flat gradient buffer
+    if apre + "q_bias" in G:
+        ops.colsum(dqkv[:, :D], G[apre + "q_bias"].view(-1))
+    if apre + "v_bias" in G:
+        ops.colsum(dqkv[:, 2 * D:], G[apre + "v_bias"].view(-1))
 
 
 def vit_fwd(W, video, vcfg, save=True):
