@@ -5,6 +5,12 @@ BatchEncoding (:139-178), DistributedGPT3Tokenizer (:180-319), DistributedGPT3 (
 No megatron_util: tensor-model-parallel size must be 1 - the path is pure data
 parallel.  Parameter names equal the reference's (`dist_model.language_model....`), including the
 per-head [q|k|v] row grouping of query_key_value, so `model/mp_rank_00_model_states.pt` loads as is.
+
+Host-side API helpers whose behaviour has to match the reference token for token - BatchEncoding (:139-176), the
+top-k / top-p logit filters and `sample` (:1369-1443), BeamHypotheses (:1908-1961) - keep the reference's control flow
+and messages on purpose (they are thin re-statements of upstream Megatron / HF utilities and are pinned against the
+reference's own outputs in tests/golden/tiny_generate.pt); everything that touches the device - parameter containers,
+the KV cache, the decoding loops run_sample / run_beam_search, the captured single-token step - is this package's own.
 """
 import json
 import math
