@@ -82,3 +82,33 @@ def test_sampling_filters():
     torch.manual_seed(3)
     s2 = port.pick_token(logits, top_k=0, top_p=0.9, temperature=0.7, vocab_size=40)
     assert torch.equal(s1, f["sample_seed3_p09_t07_v40"]) and torch.equal(s2, s1) and int(s1.max()) < 40
+
+
+def test_kv_cache_reorder_is_in_place_and_touches_cached_positions_only():
+    """ymp.engine.KVCache host logic (no kernel involved): `reorder` = InferenceParams.swap_key_value_dict
+    (modeling_distributed_gpt3.py:1460-1473) on every layer at once, IN PLACE - the captured decoding graph holds the
+    buffers' addresses - and only over the positions that hold keys; `reset` forgets the length but keeps the storage."""
+    from ymp import engine
+    gcfg = dict(port.GCFG_TINY)
+    B, ML = 3, 6
+    cache = engine.KVCache(gcfg, B, ML, torch.device("cpu"))
+    assert len(cache.qkv) == gcfg["num_hidden_layers"] and all(t.shape == (B * ML, 3 * gcfg["hidden_size"]) for t in cache.qkv)
+    ptrs = [t.data_ptr() for t in cache.qkv]
+    g = torch.Generator().manual_seed(0)
+    for t in cache.qkv:
+        t.copy_(torch.randn(t.shape, generator=g).to(t.dtype))
+    before = [t.clone() for t in cache.qkv]
+    cache._set_len(4)
+    assert int(cache.len_idx) == 4 and int(cache.len1) == 5 and cache.len == 4
+    idx = torch.tensor([2, 0, 0])
+    cache.reorder(idx)
+    for t, old in zip(cache.qkv, before):
+        new3, old3 = t.view(B, ML, -1), old.view(B, ML, -1)
+        assert torch.equal(new3[:, :4], old3.index_select(0, idx)[:, :4])      # cached positions follow the beams
+        assert torch.equal(new3[:, 4:], old3[:, 4:])                            # rows past the length are left alone
+    assert [t.data_ptr() for t in cache.qkv] == ptrs                            # nothing was re-allocated
+    cache.reset()
+    assert cache.len == 0 and int(cache.len_idx) == 0 and int(cache.len1) == 1
+    snapshot = [t.clone() for t in cache.qkv]
+    cache.reorder(torch.tensor([1, 2, 0]))                                      # empty cache: nothing to permute
+    assert all(torch.equal(a, b) for a, b in zip(cache.qkv, snapshot))
