@@ -10,11 +10,11 @@ for p in (ROOT, os.path.join(ROOT, "youku-mplug_b200"), os.path.join(ROOT, "test
 os.environ["YMP_ALLOW_RANDOM_INIT"] = "1"
 import torch  # noqa: E402
 from helpers import make_model_dir  # noqa: E402
-from oracle import port  # noqa: E402
+from bench import GCFG, VCFG_CLIP_B16  # noqa: E402  (model-shape constants; no oracle code on a probe's path)
 import models.modeling_distributed_gpt3 as M  # noqa: E402
 
 dev = torch.device("cuda")
-td = make_model_dir(port.VCFG_CLIP_B16, dict(port.GCFG_1_3B, tokens_to_generate=32))
+td = make_model_dir(VCFG_CLIP_B16, dict(GCFG["1.3B"], tokens_to_generate=32))
 with torch.device(dev):
     dec = M.DistributedGPT3(td, 0, megatron_cfg={}).to(torch.bfloat16).eval()
 beam, Q, P, H = 5, 128, 16, 2048
