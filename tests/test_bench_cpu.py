@@ -35,3 +35,16 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_is_silent_on_other_ranks():
     r = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert r.returncode == 0 and r.stdout.strip() == "", (r.stdout, r.stderr[-500:])
+
+
+def test_product_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback, no silent substitute number: without a CUDA device the product arm exits non-zero and prints no
+    JSON line (the oracle is never on its path)."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--no-cpu-baseline"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0
+    assert not any(l.lstrip().startswith("{") for l in r.stdout.splitlines())
